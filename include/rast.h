@@ -1,0 +1,159 @@
+/*
+ * rast.h -- C ABI of the B200-native frame path (librast_b200.so).
+ *
+ * Drop-in boundary for the reference renderer's frame path:
+ *     void draw_frame(model_vertices, faces, model_vertnormals, vertuvs, lights, materials,
+ *                     arguments, frame_buffer, depth_buffer)        headers/drawing.h:16-18
+ * called from renderer.cpp:89 (single frame) and renderer.cpp:111 (spin loop).  The reference has
+ * no FFI layer of its own (it is one C++ executable), so this header declares what a binding for
+ * that call needs: plain pointers and sizes, no C++/torch types.  Every entry point cites the
+ * reference interface it replaces.  include/rast_draw_frame.hpp holds the C++ shim with the
+ * reference's own draw_frame signature on top of these calls; INTEGRATION.md shows the two-line
+ * change a maintainer makes in renderer.cpp.
+ *
+ * Conventions: return 0 on success, a negative RAST_E* code on failure (never throws across the
+ * ABI); rast_last_error() gives the text.  One context per GPU; calls on one context are
+ * serialised by the caller.  There is NO CPU fallback: without a CUDA device rast_create fails.
+ * Matrices are column-major 4x4 float like glm (m[c*4+r]).  Images use CImg's planar layout
+ * (CImg.h:11715-11721): frame[c*W*H + y*W + x] (c = R,G,B), depth[y*W + x].
+ */
+#ifndef RAST_H
+#define RAST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAST_OK 0
+#define RAST_EINVAL (-1)   /* bad argument */
+#define RAST_ECUDA (-2)    /* CUDA runtime error (no device, out of memory, launch failure) */
+#define RAST_ESTATE (-3)   /* call out of order (e.g. draw before upload) */
+#define RAST_ENOMEM (-4)   /* host allocation failed */
+
+#define RAST_NO_TRIANGLE 0xFFFFFFFFu
+
+typedef struct rast_ctx rast_ctx;
+
+/* Light -- headers/light.h:7-14.  trans_dir is an output: rast_draw_* writes
+ * normalize(view * (direction,0)) into it, as Light::transform does (geometry.cpp:124-127). */
+typedef struct {
+    float direction[3];
+    float intensity;
+    float colour[3];
+    float trans_dir[3];
+} rast_light;
+
+/* Material -- headers/material.h:11-25.  texels: planar f32 [3][tex_h][tex_w], already
+ * normalised by normalize(0,1) as the Material constructor does (material.h:22); NULL when
+ * has_texture == 0.  Copied to the device by rast_upload_materials. */
+typedef struct {
+    float kd[3];
+    int32_t has_texture;
+    int32_t tex_w, tex_h;
+    const float *texels;
+} rast_material;
+
+/* The fields of Args that draw_frame consumes -- headers/arguments.h:7-21; drawing.cpp:222
+ * (scale, displacement, tait_bryan_angles), :229 (aspect_ratio), :247,255 (image size),
+ * :256 (wind_clockwise).  `flat` is carried because the CLI parses it (arguments.cpp:23,45) but,
+ * exactly like the reference, the path never reads it. */
+typedef struct {
+    uint32_t image_width, image_height;
+    float aspect_ratio;
+    float scale;
+    float displacement[3];
+    float tait_bryan_angles[3]; /* rx, ry, rz */
+    int32_t wind_clockwise;
+    int32_t flat;
+} rast_args;
+
+/* Per-pass device time of the last profiled frame batch, milliseconds (CUDA events on the
+ * context's stream).  Filled only while rast_set_profiling(ctx, 1). */
+enum { RAST_PASS_CLEAR = 0, RAST_PASS_VERTEX, RAST_PASS_SETUP, RAST_PASS_RASTER, RAST_PASS_SHADE, RAST_PASS_COUNT };
+
+/* Workload counters of the last frame (device-side tallies, optional). */
+typedef struct {
+    uint64_t triangles;      /* submitted */
+    uint64_t front_facing;   /* survived the cull (drawing.cpp:176-180) */
+    uint64_t queued_chunks;  /* work items handed to the chunk rasteriser */
+    uint64_t visible_pixels; /* pixels with a winning triangle */
+} rast_stats;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int rast_create(int device, rast_ctx **out);
+void rast_destroy(rast_ctx *ctx);
+const char *rast_last_error(const rast_ctx *ctx); /* ctx may be NULL: error of the last failed rast_create */
+const char *rast_version(void);
+
+/* Launch on this cudaStream_t (as void*) instead of the context's own stream; NULL restores it.
+ * Lets a host that owns streams (e.g. torch.cuda.current_stream().cuda_stream) time and order
+ * the kernels itself. */
+int rast_set_stream(rast_ctx *ctx, void *cuda_stream);
+
+/* ---- scene upload (once; replaces handing the std::vectors to draw_frame each call) -------- */
+/* positions xyz[n_positions], normals xyz[n_normals], uvs uv[n_uvs]; tris = 10 x int32 per
+ * triangle in the order of struct Triangle (headers/face.h:6-13): v0 v1 v2 / n0 n1 n2 /
+ * t0 t1 t2 / material, -1 = absent (uv, normal, material). */
+int rast_upload_mesh(rast_ctx *ctx, const float *positions, uint32_t n_positions,
+                     const float *normals, uint32_t n_normals, const float *uvs, uint32_t n_uvs,
+                     const int32_t *tris, uint64_t n_tris);
+int rast_upload_materials(rast_ctx *ctx, const rast_material *materials, uint32_t n_materials);
+/* lights are kept by pointer-free copy; direction/intensity/colour are read here */
+int rast_set_lights(rast_ctx *ctx, const rast_light *lights, uint32_t n_lights);
+
+/* ---- host math (drawing.cpp:222-229, geometry.cpp:22-33,101,124-133) ----------------------- */
+void rast_frame_matrices(const rast_args *args, float modelview[16], float camera[16], float normal_matrix[16], float view[16]);
+void rast_transform_lights(const float view[16], rast_light *lights, uint32_t n_lights);
+/* deterministic spin schedule replacing the wall-clock rotation of renderer.cpp:118-124:
+ * ry_k = ry0 + (float)k * (6.2831853f / (float)n_frames) */
+float rast_spin_angle(float ry0, uint32_t k, uint32_t n_frames);
+
+/* ---- sort-first band (multi-GPU single frame) --------------------------------------------- */
+/* Restrict rendering to image rows [y0, y1).  Output buffers then hold only those rows:
+ * frame [3][y1-y0][W], depth [y1-y0][W].  y0 = y1 = 0 restores the whole frame. */
+int rast_set_band(rast_ctx *ctx, uint32_t y0, uint32_t y1);
+
+/* ---- draw_frame (drawing.cpp:205-258) ------------------------------------------------------ */
+/* Clears (frame 0, depth 1.0f: renderer.cpp:85-86,107-108), draws, and copies the result into HOST
+ * buffers (pinned memory from rast_host_alloc makes the copy asynchronous and faster).  depth may
+ * be NULL.  If lights_out != NULL the n_lights trans_dir values are written back
+ * (geometry.cpp:126).  Returns after the images are complete in host memory. */
+int rast_draw_frame(rast_ctx *ctx, const rast_args *args, uint8_t *frame, float *depth, rast_light *lights_out);
+
+/* Same, but the result stays in DEVICE memory: frame_dev / depth_dev are device pointers (either
+ * may be NULL to keep the result only in the context's internal buffers).  Asynchronous on the
+ * context's stream; rast_sync waits. */
+int rast_draw_frame_device(rast_ctx *ctx, const rast_args *args, uint8_t *frame_dev, float *depth_dev);
+
+/* n frames of one scene in one call (the spin sequence): args[i] may differ in everything except
+ * image size.  Frames are batched through the kernels together.  Outputs are contiguous:
+ * frames [n][3][H][W], depths [n][H][W] (depths may be NULL).  `device_ptrs` != 0 means the
+ * outputs are device pointers (asynchronous), else host pointers (returns when complete). */
+int rast_draw_frames(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *frames, float *depths, int device_ptrs);
+
+int rast_sync(rast_ctx *ctx);
+
+/* ---- auxiliary outputs -------------------------------------------------------------------- */
+/* Winning triangle index per pixel of the most recent frame (RAST_NO_TRIANGLE = background),
+ * [H][W] u32, host pointer.  This is the visibility buffer's low word; parity tests compare it
+ * bit-exactly with the oracle. */
+int rast_read_triangle_ids(rast_ctx *ctx, uint32_t *tri_ids);
+/* depth_buffer.normalize(0,255) + uchar truncation (renderer.cpp:93; CImg.h:26786-26794,52410) of
+ * the most recent frame's depth, computed on the device; out = host [H][W] u8. */
+int rast_depth_to_u8(rast_ctx *ctx, uint8_t *out);
+int rast_get_stats(rast_ctx *ctx, rast_stats *out);
+int rast_set_profiling(rast_ctx *ctx, int enabled);
+int rast_get_pass_ms(rast_ctx *ctx, float ms[RAST_PASS_COUNT]);
+/* number of kernel launches issued by this context since creation */
+uint64_t rast_launch_count(const rast_ctx *ctx);
+
+/* pinned host memory for frame / depth buffers */
+void *rast_host_alloc(uint64_t bytes);
+void rast_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAST_H */

@@ -1,0 +1,624 @@
+// rast_ctx.cu -- context, buffer management, launch sequencing and the extern "C" rast_* ABI
+// (include/rast.h).  Host orchestration of draw_frame (drawing.cpp:205-258): the reference builds
+// matrices, runs six whole-array passes and loops the faces in order; here the host builds the
+// same matrices (hostmath.h), uploads them, and launches clear -> vertex -> setup -> chunk raster ->
+// resolve+shade for a whole batch of frames at once.  No CPU fallback exists: every entry point
+// either runs the CUDA kernels or fails with an error code.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/rast.h"
+#include "hostmath.h"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr uint32_t MAX_BATCH = 32;                 // frames in flight through one launch sequence (<= 256: 8-bit frame tag)
+constexpr size_t BATCH_BYTES_BUDGET = 6ull << 30;  // per-batch device scratch budget
+constexpr uint32_t QUEUE_MIN = 1u << 20;           // work items
+
+struct DeviceBuffer {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t want) {
+        if (want <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, want ? want : 1);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct PinnedBuffer {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t want) {
+        if (want <= bytes) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMallocHost(&p, want ? want : 1);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+} // namespace
+
+struct rast_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    std::string error;
+    uint64_t launches = 0;
+    unsigned raster_grid = 148; // persistent grid of k_raster_chunks: SMs x resident CTAs per SM
+
+    // scene
+    rk::Scene scene{};
+    DeviceBuffer d_pos, d_nrm, d_uv, d_vidx, d_attr, d_mats, d_texels;
+    bool have_mesh = false;
+    std::vector<rast_light> lights;
+
+    // view
+    uint32_t band_y0 = 0, band_y1 = 0; // 0,0 = whole frame
+
+    // per-call / per-batch buffers
+    DeviceBuffer d_frames, d_lights, d_rv, d_vis, d_queue, d_counters, d_aux;
+    DeviceBuffer d_rgb[2], d_depth[2];
+    PinnedBuffer h_frames, h_lights, h_status;
+    cudaEvent_t ev_params = nullptr, ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    bool copied_pending[2] = {false, false};
+    uint32_t queue_cap = QUEUE_MIN;
+
+    // most recent frame (for rast_read_triangle_ids / rast_depth_to_u8 / stats)
+    rk::View last_view{};
+    uint32_t last_slot_frame = 0; // index of the last frame inside d_vis / d_rv
+    const float *last_depth_dev = nullptr;
+    size_t last_frames_offset = 0; // index into d_frames of the last frame's params
+    bool have_frame = false;
+    uint64_t last_queue_count = 0;
+
+    // profiling
+    bool profiling = false;
+    cudaEvent_t ev_pass[RAST_PASS_COUNT + 1] = {};
+    float pass_ms[RAST_PASS_COUNT] = {};
+};
+
+namespace {
+
+int fail(rast_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess) {
+    if (ctx) {
+        ctx->error = what;
+        if (e != cudaSuccess) { ctx->error += ": "; ctx->error += cudaGetErrorString(e); }
+    }
+    return code;
+}
+
+#define RAST_CUDA(ctx, call)                                            \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return fail(ctx, RAST_ECUDA, #call, e__); \
+    } while (0)
+
+inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+rk::View make_view(const rast_ctx *ctx, uint32_t W, uint32_t H) {
+    rk::View v;
+    v.W = W;
+    v.H = H;
+    v.y0 = 0;
+    v.y1 = H;
+    if (ctx->band_y1 > ctx->band_y0) {
+        v.y0 = ctx->band_y0 < H ? ctx->band_y0 : H;
+        v.y1 = ctx->band_y1 < H ? ctx->band_y1 : H;
+    }
+    v.band_pixels = W * (v.y1 - v.y0);
+    return v;
+}
+
+// host side of draw_frame for one frame: matrices (drawing.cpp:222-229, geometry.cpp:101)
+void fill_frame_params(const rast_args &a, rk::FrameParams &fp) {
+    using namespace hostmath;
+    const float view_disp[3] = {0.f, 0.f, -3.f}, zero3[3] = {0.f, 0.f, 0.f};
+    const Mat4 model = transformation_matrix(a.scale, a.displacement, a.tait_bryan_angles);
+    const Mat4 view = transformation_matrix(1.f, view_disp, zero3);
+    const Mat4 modelview = mul(view, model);
+    camera_matrix(modelview, a.aspect_ratio).store(fp.camera);
+    transpose(inverse(modelview)).store(fp.normal_m);
+    fp.wind_clockwise = a.wind_clockwise ? 1u : 0u;
+    fp.pad[0] = fp.pad[1] = fp.pad[2] = 0u;
+}
+
+uint32_t batch_capacity(const rast_ctx *ctx, const rk::View &vw) {
+    const size_t per_frame = (size_t)vw.band_pixels * (8 + 2 * 7) + (size_t)ctx->scene.V * 16 + 256;
+    size_t b = BATCH_BYTES_BUDGET / (per_frame ? per_frame : 1);
+    if (b < 1) b = 1;
+    if (b > MAX_BATCH) b = MAX_BATCH;
+    return (uint32_t)b;
+}
+
+// Launch the five passes for frames [first, first+count) of the uploaded parameter block.
+int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count, uint8_t *rgb_dev, float *depth_dev) {
+    rk::Batch bt;
+    bt.frames = ctx->d_frames.as<rk::FrameParams>() + first;
+    bt.n_frames = count;
+    bt.rv = ctx->d_rv.as<float4>();
+    bt.vis = ctx->d_vis.as<unsigned long long>();
+    bt.queue = ctx->d_queue.as<uint2>();
+    bt.queue_cap = ctx->queue_cap;
+    bt.counters = ctx->d_counters.as<unsigned long long>();
+    const rk::Scene &sc = ctx->scene;
+    cudaStream_t st = ctx->stream;
+    const bool prof = ctx->profiling;
+    const size_t n_vis = (size_t)count * vw.band_pixels;
+
+    if (prof) cudaEventRecord(ctx->ev_pass[0], st);
+    rk::k_clear<<<grid_for((n_vis + 1) / 2, 256), 256, 0, st>>>(bt.vis, n_vis, bt.counters);
+    if (prof) cudaEventRecord(ctx->ev_pass[1], st);
+    if (sc.V) rk::k_vertex<<<dim3(grid_for(sc.V, 256), count), 256, 0, st>>>(sc, vw, bt);
+    if (prof) cudaEventRecord(ctx->ev_pass[2], st);
+    if (sc.T && vw.band_pixels) rk::k_setup<<<dim3(grid_for(sc.T, 256), count), 256, 0, st>>>(sc, vw, bt);
+    if (prof) cudaEventRecord(ctx->ev_pass[3], st);
+    if (sc.T && vw.band_pixels) rk::k_raster_chunks<<<ctx->raster_grid, 256, 0, st>>>(sc, vw, bt);
+    if (prof) cudaEventRecord(ctx->ev_pass[4], st);
+    if (vw.band_pixels) {
+        const bool vec = (vw.band_pixels % 4u == 0u) && (((uintptr_t)rgb_dev & 15u) == 0u) && (((uintptr_t)depth_dev & 15u) == 0u);
+        const dim3 grid(grid_for(((size_t)vw.band_pixels + 3) / 4, 256), count);
+        const rk::LightDev *lights = ctx->d_lights.as<rk::LightDev>();
+        const uint32_t nl = (uint32_t)ctx->lights.size();
+        if (vec) rk::k_resolve_shade<true><<<grid, 256, 0, st>>>(sc, vw, bt, lights, nl, rgb_dev, depth_dev);
+        else rk::k_resolve_shade<false><<<grid, 256, 0, st>>>(sc, vw, bt, lights, nl, rgb_dev, depth_dev);
+    }
+    if (prof) cudaEventRecord(ctx->ev_pass[5], st);
+    ctx->launches += 1 + (sc.V ? 1 : 0) + ((sc.T && vw.band_pixels) ? 2 : 0) + (vw.band_pixels ? 1 : 0);
+    RAST_CUDA(ctx, cudaGetLastError());
+    if (prof) {
+        RAST_CUDA(ctx, cudaEventSynchronize(ctx->ev_pass[5]));
+        for (int p = 0; p < RAST_PASS_COUNT; ++p) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev_pass[p], ctx->ev_pass[p + 1]);
+            ctx->pass_ms[p] += ms;
+        }
+    }
+    return RAST_OK;
+}
+
+// Shared implementation of every draw entry point.
+int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *frames, float *depths, bool device_ptrs) {
+    if (!ctx) return RAST_EINVAL;
+    if (!args || n == 0) return fail(ctx, RAST_EINVAL, "rast_draw: no frames");
+    if (!ctx->have_mesh) return fail(ctx, RAST_ESTATE, "rast_draw: rast_upload_mesh has not been called");
+    const uint32_t W = args[0].image_width, H = args[0].image_height;
+    if (W == 0 || H == 0 || W > 131072u || H > 131072u) return fail(ctx, RAST_EINVAL, "rast_draw: image size out of range");
+    if ((uint64_t)W * H > 0xFFFFFFFFull) return fail(ctx, RAST_EINVAL, "rast_draw: more than 2^32 pixels");
+    for (uint32_t i = 1; i < n; ++i)
+        if (args[i].image_width != W || args[i].image_height != H) return fail(ctx, RAST_EINVAL, "rast_draw_frames: all frames must share one image size");
+    RAST_CUDA(ctx, cudaSetDevice(ctx->device));
+    const rk::View vw = make_view(ctx, W, H);
+    const size_t P = vw.band_pixels;
+    if (P == 0) return RAST_OK; // empty band: nothing to render or copy
+    const uint32_t B = batch_capacity(ctx, vw);
+    const uint32_t nb = n < B ? n : B;
+
+    // the overflow flag of the previous call tells whether the work queue must grow
+    if (ctx->h_status.as<unsigned long long>()[2] != 0ull) {
+        RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const unsigned long long wanted = ctx->h_status.as<unsigned long long>()[0];
+        uint64_t cap = ctx->queue_cap;
+        while (cap < wanted && cap < (1ull << 27)) cap *= 2;
+        ctx->queue_cap = (uint32_t)cap;
+        ctx->h_status.as<unsigned long long>()[2] = 0ull;
+    }
+
+    // buffers
+    RAST_CUDA(ctx, ctx->d_frames.reserve((size_t)n * sizeof(rk::FrameParams)));
+    RAST_CUDA(ctx, ctx->d_lights.reserve((ctx->lights.size() + 1) * sizeof(rk::LightDev)));
+    RAST_CUDA(ctx, ctx->d_rv.reserve((size_t)nb * ctx->scene.V * sizeof(float4)));
+    RAST_CUDA(ctx, ctx->d_vis.reserve((size_t)nb * P * 8));
+    RAST_CUDA(ctx, ctx->d_queue.reserve((size_t)ctx->queue_cap * sizeof(uint2)));
+    RAST_CUDA(ctx, ctx->d_counters.reserve(64));
+
+    // the previous call's parameter upload must have left the pinned staging block
+    RAST_CUDA(ctx, cudaEventSynchronize(ctx->ev_params));
+    RAST_CUDA(ctx, ctx->h_frames.reserve((size_t)n * sizeof(rk::FrameParams)));
+    RAST_CUDA(ctx, ctx->h_lights.reserve((ctx->lights.size() + 1) * sizeof(rk::LightDev)));
+    rk::FrameParams *hp = ctx->h_frames.as<rk::FrameParams>();
+    for (uint32_t i = 0; i < n; ++i) fill_frame_params(args[i], hp[i]);
+
+    // transform_lights(view, lights) (drawing.cpp:238): view is the fixed translate(0,0,-3)
+    {
+        const float view_disp[3] = {0.f, 0.f, -3.f}, zero3[3] = {0.f, 0.f, 0.f};
+        const hostmath::Mat4 view = hostmath::transformation_matrix(1.f, view_disp, zero3);
+        rk::LightDev *hl = ctx->h_lights.as<rk::LightDev>();
+        for (size_t l = 0; l < ctx->lights.size(); ++l) {
+            rast_light &L = ctx->lights[l];
+            hostmath::light_direction(view, L.direction, L.trans_dir);
+            hl[l].ntx = -L.trans_dir[0];
+            hl[l].nty = -L.trans_dir[1];
+            hl[l].ntz = -L.trans_dir[2];
+            hl[l].icr = L.intensity * L.colour[0]; // light.intensity * light.colour (shading.cpp:21)
+            hl[l].icg = L.intensity * L.colour[1];
+            hl[l].icb = L.intensity * L.colour[2];
+            hl[l].pad0 = hl[l].pad1 = 0.f;
+        }
+    }
+    RAST_CUDA(ctx, cudaMemcpyAsync(ctx->d_frames.p, hp, (size_t)n * sizeof(rk::FrameParams), cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->lights.empty())
+        RAST_CUDA(ctx, cudaMemcpyAsync(ctx->d_lights.p, ctx->h_lights.p, ctx->lights.size() * sizeof(rk::LightDev), cudaMemcpyHostToDevice, ctx->stream));
+    RAST_CUDA(ctx, cudaEventRecord(ctx->ev_params, ctx->stream));
+
+    if (ctx->profiling) memset(ctx->pass_ms, 0, sizeof ctx->pass_ms);
+
+    int slot = 0;
+    for (uint32_t first = 0; first < n; first += nb) {
+        const uint32_t count = (n - first) < nb ? (n - first) : nb;
+        // outputs: the caller's device buffers, or the context's own (double-buffered when a D2H copy follows)
+        uint8_t *rgb_dst;
+        float *depth_dst = nullptr;
+        if (device_ptrs && frames) {
+            rgb_dst = frames + (size_t)first * 3 * P;
+        } else {
+            RAST_CUDA(ctx, ctx->d_rgb[slot].reserve((size_t)nb * 3 * P));
+            rgb_dst = ctx->d_rgb[slot].as<uint8_t>();
+        }
+        if (device_ptrs && depths) {
+            depth_dst = depths + (size_t)first * P;
+        } else if (depths || n == 1) { // a single frame always keeps its depth (rast_depth_to_u8); a sequence only on request
+            RAST_CUDA(ctx, ctx->d_depth[slot].reserve((size_t)nb * P * 4));
+            depth_dst = ctx->d_depth[slot].as<float>();
+        }
+        if (ctx->copied_pending[slot]) { // the copy engine must be done reading this slot
+            RAST_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0));
+            ctx->copied_pending[slot] = false;
+        }
+        int rc = launch_batch(ctx, vw, first, count, rgb_dst, depth_dst);
+        if (rc != RAST_OK) return rc;
+
+        ctx->last_view = vw;
+        ctx->last_slot_frame = count - 1;
+        ctx->last_frames_offset = first + count - 1;
+        ctx->last_depth_dev = depth_dst ? depth_dst + (size_t)(count - 1) * P : nullptr;
+        ctx->have_frame = true;
+
+        if (!device_ptrs) {
+            RAST_CUDA(ctx, cudaEventRecord(ctx->ev_done[slot], ctx->stream));
+            RAST_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[slot], 0));
+            if (frames)
+                RAST_CUDA(ctx, cudaMemcpyAsync(frames + (size_t)first * 3 * P, rgb_dst, (size_t)count * 3 * P, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            if (depths)
+                RAST_CUDA(ctx, cudaMemcpyAsync(depths + (size_t)first * P, depth_dst, (size_t)count * P * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            RAST_CUDA(ctx, cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
+            ctx->copied_pending[slot] = true;
+            slot ^= 1;
+        }
+    }
+    // queue statistics of the last batch travel back asynchronously (overflow => grow next time)
+    RAST_CUDA(ctx, cudaMemcpyAsync(ctx->h_status.p, ctx->d_counters.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!device_ptrs) {
+        RAST_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->copied_pending[0] = ctx->copied_pending[1] = false;
+        ctx->last_queue_count = ctx->h_status.as<unsigned long long>()[0];
+    }
+    return RAST_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *rast_version(void) { return "rasteriser_b200 0.1 (sm_100a)"; }
+
+int rast_create(int device, rast_ctx **out) {
+    if (!out) return RAST_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("rast_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback";
+        return RAST_ECUDA;
+    }
+    if (device < 0 || device >= count) { g_create_error = "rast_create: device index out of range"; return RAST_EINVAL; }
+    rast_ctx *ctx = new (std::nothrow) rast_ctx();
+    if (!ctx) { g_create_error = "rast_create: out of host memory"; return RAST_ENOMEM; }
+    ctx->device = device;
+    bool ok = cudaSetDevice(device) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_params, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i) {
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    for (int i = 0; i <= RAST_PASS_COUNT && ok; ++i) ok = ok && cudaEventCreate(&ctx->ev_pass[i]) == cudaSuccess;
+    ok = ok && ctx->h_status.reserve(64) == cudaSuccess;
+    if (ok) memset(ctx->h_status.p, 0, 64);
+    if (ok) {
+        int sms = 0, per_sm = 0;
+        ok = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
+        ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rk::k_raster_chunks, 256, 0) == cudaSuccess;
+        ctx->raster_grid = (unsigned)(sms > 0 ? sms : 148) * (unsigned)(per_sm > 0 ? per_sm : 1);
+    }
+    if (!ok) {
+        g_create_error = std::string("rast_create: CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
+        rast_destroy(ctx);
+        return RAST_ECUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return RAST_OK;
+}
+
+void rast_destroy(rast_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    DeviceBuffer *dev[] = {&ctx->d_pos, &ctx->d_nrm, &ctx->d_uv, &ctx->d_vidx, &ctx->d_attr, &ctx->d_mats, &ctx->d_texels, &ctx->d_frames, &ctx->d_lights,
+                           &ctx->d_rv, &ctx->d_vis, &ctx->d_queue, &ctx->d_counters, &ctx->d_aux, &ctx->d_rgb[0], &ctx->d_rgb[1], &ctx->d_depth[0], &ctx->d_depth[1]};
+    for (DeviceBuffer *b : dev) b->release();
+    ctx->h_frames.release();
+    ctx->h_lights.release();
+    ctx->h_status.release();
+    if (ctx->ev_params) cudaEventDestroy(ctx->ev_params);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+    }
+    for (int i = 0; i <= RAST_PASS_COUNT; ++i)
+        if (ctx->ev_pass[i]) cudaEventDestroy(ctx->ev_pass[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+const char *rast_last_error(const rast_ctx *ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int rast_set_stream(rast_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return RAST_EINVAL;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return RAST_OK;
+}
+
+int rast_upload_mesh(rast_ctx *ctx, const float *positions, uint32_t n_positions, const float *normals, uint32_t n_normals,
+                     const float *uvs, uint32_t n_uvs, const int32_t *tris, uint64_t n_tris) {
+    if (!ctx) return RAST_EINVAL;
+    if ((n_positions && !positions) || (n_normals && !normals) || (n_uvs && !uvs) || (n_tris && !tris)) return fail(ctx, RAST_EINVAL, "rast_upload_mesh: null array");
+    if (n_tris > 0xFFFFFFFEull) return fail(ctx, RAST_EINVAL, "rast_upload_mesh: triangle index must fit 32 bits");
+    // Out-of-range indices are undefined behaviour in the reference (vector operator[], drawing.cpp:167-173);
+    // here they are rejected up front.  -1 marks an absent normal / uv / material (face.h:6-13).
+    std::vector<int> vidx;
+    std::vector<int4> attr;
+    try {
+        vidx.resize((size_t)n_tris * 3);
+        attr.resize((size_t)n_tris * 2);
+    } catch (...) { return fail(ctx, RAST_ENOMEM, "rast_upload_mesh: out of host memory"); }
+    for (uint64_t t = 0; t < n_tris; ++t) {
+        const int32_t *f = tris + 10 * t;
+        for (int k = 0; k < 3; ++k) {
+            if (f[k] < 0 || (uint32_t)f[k] >= n_positions) return fail(ctx, RAST_EINVAL, "rast_upload_mesh: vertex index out of range");
+            if (f[3 + k] >= 0 && (uint32_t)f[3 + k] >= n_normals) return fail(ctx, RAST_EINVAL, "rast_upload_mesh: normal index out of range");
+            if (f[6 + k] >= 0 && (uint32_t)f[6 + k] >= n_uvs) return fail(ctx, RAST_EINVAL, "rast_upload_mesh: uv index out of range");
+            vidx[(size_t)k * n_tris + t] = f[k];
+        }
+        attr[2 * t] = make_int4(f[3], f[4], f[5], f[9]);
+        attr[2 * t + 1] = make_int4(f[6], f[7], f[8], 0);
+    }
+    RAST_CUDA(ctx, cudaSetDevice(ctx->device));
+    RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RAST_CUDA(ctx, ctx->d_pos.reserve((size_t)n_positions * 12));
+    RAST_CUDA(ctx, ctx->d_nrm.reserve((size_t)n_normals * 12));
+    RAST_CUDA(ctx, ctx->d_uv.reserve((size_t)n_uvs * 8));
+    RAST_CUDA(ctx, ctx->d_vidx.reserve(vidx.size() * 4));
+    RAST_CUDA(ctx, ctx->d_attr.reserve(attr.size() * 16));
+    if (n_positions) RAST_CUDA(ctx, cudaMemcpy(ctx->d_pos.p, positions, (size_t)n_positions * 12, cudaMemcpyHostToDevice));
+    if (n_normals) RAST_CUDA(ctx, cudaMemcpy(ctx->d_nrm.p, normals, (size_t)n_normals * 12, cudaMemcpyHostToDevice));
+    if (n_uvs) RAST_CUDA(ctx, cudaMemcpy(ctx->d_uv.p, uvs, (size_t)n_uvs * 8, cudaMemcpyHostToDevice));
+    if (n_tris) {
+        RAST_CUDA(ctx, cudaMemcpy(ctx->d_vidx.p, vidx.data(), vidx.size() * 4, cudaMemcpyHostToDevice));
+        RAST_CUDA(ctx, cudaMemcpy(ctx->d_attr.p, attr.data(), attr.size() * 16, cudaMemcpyHostToDevice));
+    }
+    rk::Scene &s = ctx->scene;
+    s.pos = ctx->d_pos.as<float>();
+    s.nrm = ctx->d_nrm.as<float>();
+    s.uv = ctx->d_uv.as<float2>();
+    s.vidx0 = ctx->d_vidx.as<int>();
+    s.vidx1 = s.vidx0 + n_tris;
+    s.vidx2 = s.vidx1 + n_tris;
+    s.attr = ctx->d_attr.as<int4>();
+    s.V = n_positions;
+    s.Nn = n_normals;
+    s.Nuv = n_uvs;
+    s.T = n_tris;
+    ctx->have_mesh = true;
+    ctx->have_frame = false;
+    return RAST_OK;
+}
+
+int rast_upload_materials(rast_ctx *ctx, const rast_material *materials, uint32_t n_materials) {
+    if (!ctx) return RAST_EINVAL;
+    if (n_materials && !materials) return fail(ctx, RAST_EINVAL, "rast_upload_materials: null array");
+    std::vector<rk::MaterialDev> md(n_materials);
+    size_t texel_total = 0;
+    for (uint32_t i = 0; i < n_materials; ++i) {
+        const rast_material &m = materials[i];
+        md[i].kd[0] = m.kd[0]; md[i].kd[1] = m.kd[1]; md[i].kd[2] = m.kd[2];
+        md[i].has_texture = m.has_texture ? 1 : 0;
+        md[i].tex_w = m.tex_w; md[i].tex_h = m.tex_h;
+        md[i].texel_offset = (long long)texel_total;
+        if (m.has_texture) {
+            // CImg::linear_atXY throws on an empty image (CImg.h:13467-13470)
+            if (!m.texels || m.tex_w <= 0 || m.tex_h <= 0) return fail(ctx, RAST_EINVAL, "rast_upload_materials: textured material without texels");
+            texel_total += (size_t)3 * m.tex_w * m.tex_h;
+        }
+    }
+    RAST_CUDA(ctx, cudaSetDevice(ctx->device));
+    RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RAST_CUDA(ctx, ctx->d_mats.reserve((size_t)n_materials * sizeof(rk::MaterialDev)));
+    RAST_CUDA(ctx, ctx->d_texels.reserve(texel_total * 4));
+    if (n_materials) RAST_CUDA(ctx, cudaMemcpy(ctx->d_mats.p, md.data(), md.size() * sizeof(rk::MaterialDev), cudaMemcpyHostToDevice));
+    for (uint32_t i = 0; i < n_materials; ++i)
+        if (materials[i].has_texture)
+            RAST_CUDA(ctx, cudaMemcpy(ctx->d_texels.as<float>() + md[i].texel_offset, materials[i].texels,
+                                      (size_t)3 * materials[i].tex_w * materials[i].tex_h * 4, cudaMemcpyHostToDevice));
+    ctx->scene.mats = ctx->d_mats.as<rk::MaterialDev>();
+    ctx->scene.texels = ctx->d_texels.as<float>();
+    ctx->scene.M = n_materials;
+    return RAST_OK;
+}
+
+int rast_set_lights(rast_ctx *ctx, const rast_light *lights, uint32_t n_lights) {
+    if (!ctx) return RAST_EINVAL;
+    if (n_lights && !lights) return fail(ctx, RAST_EINVAL, "rast_set_lights: null array");
+    try { ctx->lights.assign(lights, lights + n_lights); } catch (...) { return fail(ctx, RAST_ENOMEM, "rast_set_lights: out of host memory"); }
+    return RAST_OK;
+}
+
+void rast_frame_matrices(const rast_args *args, float modelview[16], float camera[16], float normal_matrix[16], float view[16]) {
+    using namespace hostmath;
+    const float view_disp[3] = {0.f, 0.f, -3.f}, zero3[3] = {0.f, 0.f, 0.f};
+    const Mat4 model = transformation_matrix(args->scale, args->displacement, args->tait_bryan_angles);
+    const Mat4 v = transformation_matrix(1.f, view_disp, zero3);
+    const Mat4 mv = mul(v, model);
+    if (modelview) mv.store(modelview);
+    if (camera) camera_matrix(mv, args->aspect_ratio).store(camera);
+    if (normal_matrix) transpose(inverse(mv)).store(normal_matrix);
+    if (view) v.store(view);
+}
+
+void rast_transform_lights(const float view[16], rast_light *lights, uint32_t n_lights) {
+    const hostmath::Mat4 v = hostmath::Mat4::load(view);
+    for (uint32_t i = 0; i < n_lights; ++i) hostmath::light_direction(v, lights[i].direction, lights[i].trans_dir);
+}
+
+float rast_spin_angle(float ry0, uint32_t k, uint32_t n_frames) { return ry0 + (float)k * (6.2831853f / (float)n_frames); }
+
+int rast_set_band(rast_ctx *ctx, uint32_t y0, uint32_t y1) {
+    if (!ctx) return RAST_EINVAL;
+    if (y1 < y0) return fail(ctx, RAST_EINVAL, "rast_set_band: y1 < y0");
+    ctx->band_y0 = y0;
+    ctx->band_y1 = y1;
+    return RAST_OK;
+}
+
+int rast_draw_frame(rast_ctx *ctx, const rast_args *args, uint8_t *frame, float *depth, rast_light *lights_out) {
+    if (!ctx) return RAST_EINVAL;
+    if (!frame) return fail(ctx, RAST_EINVAL, "rast_draw_frame: frame buffer is null");
+    int rc = draw_frames_impl(ctx, args, 1, frame, depth, false);
+    if (rc == RAST_OK && lights_out)
+        for (size_t l = 0; l < ctx->lights.size(); ++l) memcpy(lights_out[l].trans_dir, ctx->lights[l].trans_dir, sizeof(float) * 3);
+    return rc;
+}
+
+int rast_draw_frame_device(rast_ctx *ctx, const rast_args *args, uint8_t *frame_dev, float *depth_dev) {
+    return draw_frames_impl(ctx, args, 1, frame_dev, depth_dev, true);
+}
+
+int rast_draw_frames(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *frames, float *depths, int device_ptrs) {
+    if (ctx && !device_ptrs && !frames) return fail(ctx, RAST_EINVAL, "rast_draw_frames: frames buffer is null");
+    return draw_frames_impl(ctx, args, n, frames, depths, device_ptrs != 0);
+}
+
+int rast_sync(rast_ctx *ctx) {
+    if (!ctx) return RAST_EINVAL;
+    RAST_CUDA(ctx, cudaSetDevice(ctx->device));
+    RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RAST_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    ctx->last_queue_count = ctx->h_status.as<unsigned long long>()[0];
+    return RAST_OK;
+}
+
+int rast_read_triangle_ids(rast_ctx *ctx, uint32_t *tri_ids) {
+    if (!ctx || !tri_ids) return RAST_EINVAL;
+    if (!ctx->have_frame) return fail(ctx, RAST_ESTATE, "rast_read_triangle_ids: no frame has been drawn");
+    RAST_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t P = ctx->last_view.band_pixels;
+    RAST_CUDA(ctx, ctx->d_aux.reserve((size_t)P * 4 + 64));
+    const unsigned long long *vis = ctx->d_vis.as<unsigned long long>() + (size_t)ctx->last_slot_frame * P;
+    rk::k_extract_tri_ids<<<grid_for(P, 256), 256, 0, ctx->stream>>>(vis, ctx->d_aux.as<uint32_t>(), P);
+    ctx->launches++;
+    RAST_CUDA(ctx, cudaMemcpyAsync(tri_ids, ctx->d_aux.p, (size_t)P * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RAST_OK;
+}
+
+int rast_depth_to_u8(rast_ctx *ctx, uint8_t *out) {
+    if (!ctx || !out) return RAST_EINVAL;
+    if (!ctx->have_frame || !ctx->last_depth_dev) return fail(ctx, RAST_ESTATE, "rast_depth_to_u8: the last frame was drawn without a depth output");
+    RAST_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t P = ctx->last_view.band_pixels;
+    RAST_CUDA(ctx, ctx->d_aux.reserve((size_t)P + 64));
+    uint32_t *minmax = ctx->d_aux.as<uint32_t>();
+    uint8_t *u8 = ctx->d_aux.as<uint8_t>() + 64;
+    const uint32_t init[2] = {0xFFFFFFFFu, 0u};
+    RAST_CUDA(ctx, cudaMemcpyAsync(minmax, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    rk::k_depth_minmax<<<148 * 4, 256, 0, ctx->stream>>>(ctx->last_depth_dev, P, minmax);
+    rk::k_depth_to_u8<<<grid_for(P, 256), 256, 0, ctx->stream>>>(ctx->last_depth_dev, P, minmax, u8);
+    ctx->launches += 2;
+    RAST_CUDA(ctx, cudaMemcpyAsync(out, u8, P, cudaMemcpyDeviceToHost, ctx->stream));
+    RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RAST_OK;
+}
+
+int rast_get_stats(rast_ctx *ctx, rast_stats *out) {
+    if (!ctx || !out) return RAST_EINVAL;
+    if (!ctx->have_frame) return fail(ctx, RAST_ESTATE, "rast_get_stats: no frame has been drawn");
+    RAST_CUDA(ctx, cudaSetDevice(ctx->device));
+    RAST_CUDA(ctx, ctx->d_aux.reserve(64));
+    unsigned long long *cnt = ctx->d_aux.as<unsigned long long>();
+    RAST_CUDA(ctx, cudaMemsetAsync(cnt, 0, 16, ctx->stream));
+    const uint32_t P = ctx->last_view.band_pixels;
+    rk::Batch bt{};
+    bt.frames = ctx->d_frames.as<rk::FrameParams>() + (ctx->last_frames_offset - ctx->last_slot_frame);
+    bt.rv = ctx->d_rv.as<float4>();
+    rk::k_count_visible<<<148 * 4, 256, 0, ctx->stream>>>(ctx->d_vis.as<unsigned long long>() + (size_t)ctx->last_slot_frame * P, P, cnt);
+    rk::k_count_front<<<148 * 4, 256, 0, ctx->stream>>>(ctx->scene, bt, ctx->last_slot_frame, cnt + 1);
+    ctx->launches += 2;
+    unsigned long long host[2] = {0, 0};
+    RAST_CUDA(ctx, cudaMemcpyAsync(host, cnt, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    out->triangles = ctx->scene.T;
+    out->front_facing = host[1];
+    out->visible_pixels = host[0];
+    out->queued_chunks = ctx->h_status.as<unsigned long long>()[0];
+    return RAST_OK;
+}
+
+int rast_set_profiling(rast_ctx *ctx, int enabled) {
+    if (!ctx) return RAST_EINVAL;
+    ctx->profiling = enabled != 0;
+    return RAST_OK;
+}
+
+int rast_get_pass_ms(rast_ctx *ctx, float ms[RAST_PASS_COUNT]) {
+    if (!ctx || !ms) return RAST_EINVAL;
+    memcpy(ms, ctx->pass_ms, sizeof ctx->pass_ms);
+    return RAST_OK;
+}
+
+uint64_t rast_launch_count(const rast_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+void *rast_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void rast_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+} // extern "C"

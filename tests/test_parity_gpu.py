@@ -1,0 +1,210 @@
+"""Parity of the CUDA frame path (through the C ABI) with the CPU oracle.  Needs a B200: `-m gpu`."""
+import numpy as np
+import pytest
+
+import orc
+import scenes as S
+from gpu_common import assert_parity, gpu_draw, make_renderer, to_api_args, ulp_distance
+from rasteriser_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+CASES = S.golden_cases()
+
+
+@pytest.fixture(scope="module")
+def renderers():
+    cache = {}
+
+    def get(scene_name, lights_name):
+        key = (scene_name, lights_name)
+        if key not in cache:
+            cache[key] = make_renderer(S.scene(scene_name), S.lights(lights_name))
+        return cache[key]
+    yield get
+    for r in cache.values():
+        r.close()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_golden_cases(case, renderers):
+    """Every committed reference case: vs the oracle (ids, depth, colour) and vs the reference's own hashes."""
+    oa = S.case_args(case)
+    r = renderers(case["scene"], case["lights"])
+    got = gpu_draw(r, oa)
+    want = orc.oracle_draw(S.scene(case["scene"]), S.lights(case["lights"]), oa)
+    assert_parity(got, want, case["name"])
+    # the implementation is in fact bit-exact: its output hashes equal the reference's
+    assert orc.fnv(got[1]) == case["depth_fnv"]
+    assert orc.fnv(got[0]) == case["frame_fnv"]
+    assert orc.fnv(r.depth_to_u8(case["width"], case["height"])) == case["depth_u8_fnv"]
+    assert np.array_equal(r.light_trans_dirs().view(np.uint32).ravel(),
+                          np.array([int(b, 16) for b in case["trans_dir_bits"]], np.uint32))
+
+
+@pytest.mark.parametrize("seed,n_tris,size,cw", [(1, 8, (16, 16), False), (2, 40, (64, 48), False), (3, 120, (257, 129), True),
+                                                 (4, 200, (97, 131), False), (5, 60, (1, 50), True), (6, 30, (33, 1), False),
+                                                 (7, 150, (128, 128), True), (8, 90, (200, 150), False), (9, 1, (31, 17), False),
+                                                 (10, 3000, (320, 200), False), (11, 20000, (512, 512), True)])
+def test_random_soups(seed, n_tris, size, cw):
+    scene = S.random_soup(seed, n_tris)
+    lights = S.random_lights(seed, 1 + seed % 5)
+    oa = orc.make_args(size[0], size[1], scale=0.9, disp=(0.05, -0.03, 0.2), angles=(0.1 * seed, 0.37 * seed, -0.2), wind_clockwise=cw)
+    r = make_renderer(scene, lights)
+    try:
+        assert_parity(gpu_draw(r, oa), orc.oracle_draw(scene, lights, oa, threads=4), "soup %d" % seed)
+    finally:
+        r.close()
+
+
+def test_tie_rule_duplicates():
+    """Coplanar identical triangles: the lower index (first drawn) wins every covered pixel."""
+    scene = S.random_soup(11, 8, with_uv=False)
+    lights = S.random_lights(3, 2)
+    oa = orc.make_args(160, 120)
+    r = make_renderer(scene, lights)
+    try:
+        got = gpu_draw(r, oa)
+        assert_parity(got, orc.oracle_draw(scene, lights, oa), "duplicates")
+        assert not (got[2] == 1).any()
+    finally:
+        r.close()
+
+
+def test_many_lights_and_missing_material():
+    scene = S.random_soup(21, 300)
+    scene.tris[::7, 9] = -1           # no material (untextured white)
+    scene.tris[::5, 6:9] = -1         # faces without uvs
+    lights = S.random_lights(5, 64)
+    lights[:, 3] = 16.0
+    oa = orc.make_args(300, 200, angles=(0.2, 0.4, 0.0))
+    r = make_renderer(scene, lights)
+    try:
+        assert_parity(gpu_draw(r, oa), orc.oracle_draw(scene, lights, oa, threads=4), "64 lights")
+    finally:
+        r.close()
+
+
+def test_small_triangles_dense_mesh():
+    """A finely tessellated grid: most triangles cover 0-1 samples (the tiny-triangle path)."""
+    n = 300
+    xs = np.linspace(-1.1, 1.1, n + 1, dtype=np.float32)
+    gx, gy = np.meshgrid(xs, xs)
+    rng = np.random.RandomState(0)
+    pos = np.stack([gx.ravel(), gy.ravel(), (0.3 * np.sin(3 * gx) * np.cos(2 * gy)).ravel().astype(np.float32)], 1).astype(np.float32)
+    pos[:, :2] += rng.rand(len(pos), 2).astype(np.float32) * 0.002
+    idx = np.arange((n + 1) * (n + 1)).reshape(n + 1, n + 1)
+    a, b, c, d = idx[:-1, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, :-1].ravel(), idx[1:, 1:].ravel()
+    v = np.concatenate([np.stack([a, b, c], 1), np.stack([c, b, d], 1)])
+    tris = np.zeros((len(v), 10), np.int32)
+    tris[:, 0:3] = v
+    tris[:, 3:6] = v % 97
+    tris[:, 6:9] = -1
+    nrm = rng.randn(97, 3).astype(np.float32)
+    scene = orc.Scene(pos, nrm, np.zeros((1, 2), np.float32), tris, [{"kd": (0.7, 0.6, 0.5), "texels": None}])
+    lights = S.lights("threepoint")
+    oa = orc.make_args(400, 300, angles=(0.3, 0.2, 0.1))
+    r = make_renderer(scene, lights)
+    try:
+        assert_parity(gpu_draw(r, oa), orc.oracle_draw(scene, lights, oa, threads=4), "dense grid")
+        st = r.stats()
+        assert st["triangles"] == len(tris)
+    finally:
+        r.close()
+
+
+def test_bands_equal_whole_frame(renderers):
+    """Sort-first screen bands (rast_set_band) stitch to exactly the whole frame, for G = 2, 3, 8."""
+    oa = orc.make_args(320, 243, angles=(0.2, 0.9, 0.1))
+    r = renderers("suzanne", "threepoint")
+    whole = gpu_draw(r, oa)
+    want = orc.oracle_draw(S.scene("suzanne"), S.lights("threepoint"), oa)
+    assert_parity(whole, want, "whole")
+    H = oa.image_height
+    try:
+        for G in (2, 3, 8):
+            f, d, t = np.zeros_like(whole[0]), np.zeros_like(whole[1]), np.zeros_like(whole[2])
+            for g in range(G):
+                y0, y1 = H * g // G, H * (g + 1) // G
+                r.set_band(y0, y1)
+                bf, bd = r.draw_frame(to_api_args(oa))
+                bt = r.triangle_ids(oa.image_width, y1 - y0)
+                assert bf.shape == (3, y1 - y0, oa.image_width)
+                f[:, y0:y1], d[y0:y1], t[y0:y1] = bf, bd, bt
+            assert np.array_equal(f, whole[0]) and np.array_equal(d.view(np.uint32), whole[1].view(np.uint32)) and np.array_equal(t, whole[2])
+    finally:
+        r.set_band(0, 0)
+
+
+def test_batched_spin_frames_equal_single_frames(renderers):
+    """rast_draw_frames (frames batched through the kernels together) == one rast_draw_frame per pose,
+    and each equals the oracle; the spin schedule is a pure function of k."""
+    r = renderers("suzanne", "threepoint")
+    n, W, H = 37, 200, 150
+    poses = [api.Args(W, H, tait_bryan_angles=(0.0, api.spin_angle(0.0, k, n), 0.0)) for k in range(n)]
+    frames, depths = r.draw_frames(poses, want_depth=True)
+    for k in (0, 1, 17, 36):
+        f1, d1 = r.draw_frame(poses[k])
+        assert np.array_equal(frames[k], f1) and np.array_equal(depths[k].view(np.uint32), d1.view(np.uint32))
+        oa = orc.make_args(W, H, angles=(0.0, float(orc.oracle().orc_spin_angle(0.0, k, n)), 0.0))
+        wf, wd, _ = orc.oracle_draw(S.scene("suzanne"), S.lights("threepoint"), oa)
+        assert np.array_equal(frames[k], wf) and ulp_distance(depths[k], wd).max() <= 1
+    frames2, _ = r.draw_frames(poses)
+    assert np.array_equal(frames, frames2)
+
+
+def test_draw_frame_function_mirrors_reference_signature():
+    """api.draw_frame(vertices, faces, normals, uvs, lights, materials, args, frame, depth)."""
+    sc = S.scene("plane")
+    lights = orc.lights_array(S.lights("normalmap"))
+    a = api.Args(96, 64, tait_bryan_angles=(0.9, 0.3, 0.0))
+    frame, depth = np.zeros((3, 64, 96), np.uint8), np.ones((64, 96), np.float32)
+    api.draw_frame(sc.positions, sc.tris, sc.normals, sc.uvs, lights, sc.materials, a, frame, depth)
+    z = np.load(S.GOLDEN + "/small_frames.npz")
+    assert np.array_equal(frame, z["plane_96x64_frame"])
+    assert np.array_equal(depth.view(np.uint32), z["plane_96x64_depth"].view(np.uint32))
+    assert np.abs(np.linalg.norm(lights[:, 7:10], axis=1) - 1).max() < 1e-6
+
+
+def test_idempotent_and_deterministic(renderers):
+    r = renderers("suzanne", "threepoint")
+    a = api.Args(640, 480, tait_bryan_angles=(0.3, 1.0, 0.2), displacement=(0.0, 0.0, 2.2))
+    f0, d0 = r.draw_frame(a)
+    t0 = r.triangle_ids(640, 480)
+    for _ in range(3):
+        f, d = r.draw_frame(a)
+        assert np.array_equal(f, f0) and np.array_equal(d.view(np.uint32), d0.view(np.uint32)) and np.array_equal(r.triangle_ids(640, 480), t0)
+
+
+def test_nonfinite_vertices_do_not_crash(renderers):
+    """--scale 4 puts a vertex on w = 0 (inf/NaN raster coordinates).  Unpinned corner: the
+    device follows the same IEEE operations as the oracle, so results are compared but only reported."""
+    r = renderers("suzanne", "threepoint")
+    oa = orc.make_args(640, 480, scale=4.0)
+    got = gpu_draw(r, oa)
+    got2 = gpu_draw(r, oa)
+    assert all(np.array_equal(a, b) for a, b in zip(got[::2], got2[::2]))  # deterministic
+    want = orc.oracle_draw(S.scene("suzanne"), S.lights("threepoint"), oa, threads=4)
+    mism = int((got[2] != want[2]).sum())
+    print("scale 4 (w=0): %d / %d pixels with a different winner" % (mism, want[2].size))
+
+
+def test_errors():
+    r = api.Renderer(0)
+    try:
+        with pytest.raises(api.RastError):
+            r.draw_frame(api.Args(64, 64))          # no mesh uploaded
+        sc = S.scene("square")
+        bad = sc.tris.copy()
+        bad[0, 0] = 99
+        with pytest.raises(api.RastError, match="out of range"):
+            r.upload_mesh(sc.positions, bad, sc.normals, sc.uvs)
+        r.upload_mesh(sc.positions, sc.tris, sc.normals, sc.uvs)
+        r.upload_materials(sc.materials)
+        r.set_lights(S.lights("threepoint"))
+        with pytest.raises(api.RastError):
+            r.draw_frame(api.Args(0, 64))
+        f, d = r.draw_frame(api.Args(64, 64))
+        assert f.any()
+    finally:
+        r.close()
