@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 frame path.
+
+Default workload (BASELINE.json configs[1]): Suzanne (968 triangles, textured, threepoint.csv) at
+1920x1080, the 720-frame spin sequence ry_k = k * 2*pi/720.  One "step" = every rank renders one
+720-frame sequence (weak scaling: with N ranks a step is N revolutions, frame k on rank k mod N; no
+data-path collective -- frames stay on the GPU that rendered them).
+
+  python bench.py --gpus N --steps K --warmup W          # this framework (CUDA, through the C ABI)
+  python bench.py --impl reference --gpus N ...          # the reference's own CPU path, timed beside it
+
+Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM and outputs written to
+HBM; `e2e` = the same through the host-buffer entry point (parameters H2D, frames + depth D2H inside the
+timed region).  `roofline` is for the dominant kernel, from CUDA events on the launching stream;
+`cpu_baseline` is the reference (oracle/_ref, else the oracle port) on this box's host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames_per_s_suzanne_1080p_spin"
+UNIT = "frames/s"
+
+
+# ------------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------------
+def load_suzanne():
+    """Suzanne as the reference's loader reads it (arrays committed in tests/golden/scenes.npz), with the
+    texture normalised like Material's constructor (material.h:22): (t - min) / (max - min) in fp32."""
+    from PIL import Image
+    z = np.load(os.path.join(ROOT, "tests", "golden", "scenes.npz"))
+    img = np.asarray(Image.open(os.path.join(ROOT, "tests", "data", "SuzanneTex.png")).convert("RGB"), np.uint8)
+    t = np.ascontiguousarray(img.transpose(2, 0, 1).astype(np.float32))
+    m, M = np.float32(t.min()), np.float32(t.max())
+    if not (m == 0 and M == 1):
+        t = ((t - m) / (M - m) * np.float32(1.0) + np.float32(0.0)).astype(np.float32)
+    lights = np.loadtxt(os.path.join(ROOT, "tests", "data", "threepoint.csv"), delimiter=",", dtype=np.float32).reshape(-1, 7)
+    return dict(pos=z["suzanne_pos"], nrm=z["suzanne_nrm"], uv=z["suzanne_uv"], tris=z["suzanne_tris"],
+                materials=[dict(kd=(0.64, 0.64, 0.64), texels=t)], lights=lights)
+
+
+def make_workload(name):
+    """-> dict(scene arrays, lights, width, height, frames_per_step, label)"""
+    from rasteriser_b200 import synth
+    s = load_suzanne()
+    if name == "spin1080p":
+        s.update(width=1920, height=1080, frames=720, label="Suzanne.obj + threepoint.csv, 1920x1080, -f, 720-frame spin sequence")
+    elif name == "suzanne640":
+        s.update(width=640, height=480, frames=1, label="Suzanne.obj + threepoint.csv, 640x480, single frame")
+    elif name in ("tess4k", "tess4k_64lights"):
+        n = 91 if name == "tess4k" else 227
+        s["pos"], s["nrm"], s["uv"], s["tris"] = synth.tessellate(s["pos"], s["nrm"], s["uv"], s["tris"], n)
+        if name == "tess4k_64lights":
+            s["lights"] = synth.random_lights(64)
+        s.update(width=3840, height=2160, frames=1, label="Suzanne tessellated %dx%d (%d triangles), 3840x2160, %d lights" % (n, n, len(s["tris"]), len(s["lights"])))
+    elif name == "overdraw8k":
+        s["pos"], s["nrm"], s["uv"], s["tris"] = synth.overdraw_scene(200000, 7680, 4320)
+        s["materials"] = [dict(kd=(0.8, 0.8, 0.8), texels=None)]
+        s.update(width=7680, height=4320, frames=1, label="200k random triangles R=80px, 7680x4320, depth complexity ~50")
+    else:
+        raise SystemExit("unknown workload " + name)
+    s["name"] = name
+    return s
+
+
+def spin_args(api, wl, rank, world, flat=True):
+    """The poses this rank renders in one step: frame k of the global sequence goes to rank k mod world.
+    n_frames single-frame workloads render the same pose `frames` times."""
+    n = wl["frames"]
+    out = []
+    for i in range(n):
+        k = i * world + rank
+        ry = api.spin_angle(0.0, k % 720, 720) if n > 1 else 0.0
+        out.append(api.Args(wl["width"], wl["height"], flat=flat, tait_bryan_angles=(0.0, ry, 0.0)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_runner(wl):
+    """Returns (kind, render(pose_args_list) -> seconds, threads).  kind = "reference" when the reference's
+    own sources were compiled here (oracle/_ref/libref.so), else "port" (oracle/liboracle.so).  Frames are
+    independent, so they are spread over all host threads (one frame per thread at a time); the reference's
+    per-frame code itself is single-threaded."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    from concurrent.futures import ThreadPoolExecutor
+    threads = os.cpu_count() or 1
+    W, H = wl["width"], wl["height"]
+    ref = orc.ref()
+    scene = orc.Scene(wl["pos"], wl["nrm"], wl["uv"], wl["tris"], wl["materials"])
+    l7 = np.asarray(wl["lights"], np.float32)
+    if ref is not None:
+        import tempfile
+        from PIL import Image
+        tmp = tempfile.mkdtemp()
+        paths, kd = [], []
+        for i, m in enumerate(wl["materials"]):
+            kd += list(m["kd"])
+            if m.get("texels") is None:
+                paths.append(None)
+            else:
+                p = os.path.join(tmp, "tex%d.ppm" % i)
+                Image.fromarray(np.round(m["texels"] * 255).astype(np.uint8).transpose(1, 2, 0)).save(p)
+                paths.append(p.encode())
+        arr = (C.c_char_p * max(1, len(paths)))(*paths)
+        kd = np.array(kd, np.float32)
+        h = ref.ref_scene_create(orc.ptr(scene.positions), len(scene.positions), orc.ptr(scene.normals), len(scene.normals), orc.ptr(scene.uvs), len(scene.uvs),
+                                 orc.ptr(scene.tris), len(scene.tris), orc.ptr(kd), arr, len(wl["materials"]))
+        kind = "reference"
+
+        def one(a):
+            f, d = np.empty((3, H, W), np.uint8), np.empty((H, W), np.float32)
+            l10 = orc.lights_array(l7)
+            oa = orc.make_args(W, H, a.scale, a.displacement, a.tait_bryan_angles, a.wind_clockwise, a.flat)
+            ref.ref_scene_draw(h, orc.ptr(l10), len(l10), W, H, oa.scale, oa.displacement, oa.tait_bryan_angles, oa.wind_clockwise, oa.flat, orc.ptr(f), orc.ptr(d))
+    else:
+        kind = "port"
+
+        def one(a):
+            oa = orc.make_args(W, H, a.scale, a.displacement, a.tait_bryan_angles, a.wind_clockwise, a.flat)
+            orc.oracle_draw(scene, l7, oa)
+
+    def render(poses):
+        t0 = time.perf_counter()
+        if len(poses) == 1 or threads == 1:
+            for a in poses:
+                one(a)
+        else:
+            with ThreadPoolExecutor(threads) as ex:
+                list(ex.map(one, poses))
+        return time.perf_counter() - t0
+
+    return kind, render, threads
+
+
+def run_reference_arm(opts, wl):
+    from rasteriser_b200 import api
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    kind, render, threads = cpu_reference_runner(wl)
+    full = spin_args(api, wl, 0, 1)
+    n_sample = min(len(full), max(threads * 2, 8))
+    sample = [full[(i * len(full)) // n_sample] for i in range(n_sample)]
+    for _ in range(opts.warmup):
+        render(sample[:threads])
+    t = 0.0
+    for _ in range(opts.steps):
+        t += render(sample)
+    fps = n_sample * opts.steps / t
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": opts.gpus, "steps": opts.steps, "warmup": opts.warmup,
+            "ms_per_step": 1e3 * t / opts.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["label"], "frames_per_step": n_sample, "sample": "%d evenly spaced poses of the 720-frame sequence per step" % n_sample},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": kind,
+                             "sample": "%d poses x %d steps of the 1080p spin sequence, frames spread over %d host threads" % (n_sample, opts.steps, threads)},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(wl, visible_tris, P):
+    """per frame, per pass."""
+    V, Nn, T = len(wl["pos"]), len(wl["nrm"]), len(wl["tris"])
+    return {"vertex": 28 * V + 24 * Nn, "setup+raster": 12 * T + 16 * V + 16 * P, "shade": 15 * P + 136 * visible_tris}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="spin1080p")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--frames", type=int, default=0, help="override frames per step (profiling runs)")
+    opts = ap.parse_args()
+
+    wl = make_workload(opts.workload)
+    if opts.frames:
+        wl["frames"] = opts.frames
+    if opts.impl == "reference":
+        run_reference_arm(opts, wl)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from rasteriser_b200 import api
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    r = api.Renderer(local)
+    r.upload_mesh(wl["pos"], wl["tris"], wl["nrm"], wl["uv"])
+    r.upload_materials(wl["materials"])
+    r.set_lights(wl["lights"])
+    stream = torch.cuda.Stream(dev)  # the kernels and the timing events share this stream
+    torch.cuda.set_stream(stream)
+    r.set_stream(stream.cuda_stream)
+
+    W, H, n = wl["width"], wl["height"], wl["frames"]
+    P = W * H
+    poses = spin_args(api, wl, rank, world)
+    arr = (api.RastArgs * n)(*[a.to_rast() for a in poses])
+    frames_dev = torch.empty((n, 3, H, W), dtype=torch.uint8, device=dev)
+    depths_dev = torch.empty((n, H, W), dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_device():
+        r.draw_frames_device(arr, frames_dev.data_ptr(), depths_dev.data_ptr())
+
+    # ---- value: device-resident ----
+    for _ in range(max(3, opts.warmup)):
+        step_device()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = r.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(opts.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = r.launch_count() - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    clk = clocks.stop() if rank == 0 else None
+    fps = world * n * opts.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers through the public host entry point ----
+    e2e = None
+    if not opts.no_e2e:
+        lib = api._lib.load()
+        chunk = min(n, 120)  # frames per host call: bounds the pinned staging memory (120 x 14.5 MB at 1080p)
+        fb, db = lib.rast_host_alloc(chunk * 3 * P), lib.rast_host_alloc(chunk * P * 4)
+        if not fb or not db:
+            raise SystemExit("bench.py: pinned host allocation failed")
+        frames_host = np.ctypeslib.as_array(C.cast(fb, C.POINTER(C.c_uint8)), (chunk, 3, H, W))
+        depths_host = np.ctypeslib.as_array(C.cast(db, C.POINTER(C.c_float)), (chunk, H, W))
+        chunks = [(api.RastArgs * len(poses[i:i + chunk]))(*[a.to_rast() for a in poses[i:i + chunk]]) for i in range(0, n, chunk)]
+
+        def step_host():
+            for c in chunks:  # each call returns when its frames are complete in host memory
+                r.draw_frames(c, frames_host[:len(c)], depths_host[:len(c)])
+
+        step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(opts.steps):
+            step_host()
+        barrier()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n * opts.steps / float(t.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(n * 144 + len(chunks) * len(wl["lights"]) * 32), "d2h_bytes_per_step": int(n * 7 * P),
+               "note": "rast_draw_frames with pinned host outputs, %d frames per call: RGB8 + f32 depth of every frame copied D2H inside the timed region (wall clock, max over ranks)" % chunk}
+        checksum = int(frames_host[len(chunks[-1]) // 2].astype(np.uint64).sum())
+        lib.rast_host_free(fb)
+        lib.rast_host_free(db)
+    else:
+        checksum = int(frames_dev[n // 2].sum().item())
+
+    # ---- per-pass kernel durations (CUDA events around each launch, same stream) ----
+    r.set_profiling(True)
+    pass_ms = {k: 0.0 for k in api.RAST_PASS_NAMES}
+    prof_steps = 2
+    for _ in range(prof_steps):
+        step_device()
+        r.sync()
+        for k, v in r.pass_ms().items():
+            pass_ms[k] += v
+    r.set_profiling(False)
+    r.draw_frames_device(arr[n - 1:n] if n > 1 else arr, frames_dev.data_ptr(), depths_dev.data_ptr())
+    r.sync()
+    st = r.stats()
+    tri_ids = r.triangle_ids(W, H)
+    visible_tris = int(len(np.unique(tri_ids[tri_ids != api.NO_TRIANGLE])))
+    batches_per_step = (n + 31) // 32
+    launches_per_pass = prof_steps * batches_per_step
+    ab = algorithmic_bytes(wl, visible_tris, P)
+    dominant = max(("vertex", "setup", "raster", "shade", "clear"), key=lambda k: pass_ms[k])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    frames_per_launch = n / batches_per_step
+    bytes_key = {"vertex": "vertex", "setup": "setup+raster", "raster": "setup+raster", "shade": "shade", "clear": None}[dominant]
+    alg = (8 * P if dominant == "clear" else ab[bytes_key]) * frames_per_launch
+    avg_ms = pass_ms[dominant] / launches_per_pass
+    achieved = alg / (avg_ms * 1e-3) / 1e9
+    total_alg = sum(ab.values())
+    roofline = {"bound": "hbm", "kernel": {"vertex": "k_vertex", "setup": "k_setup", "raster": "k_raster_chunks", "shade": "k_resolve_shade", "clear": "k_clear"}[dominant],
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms, "frames_per_launch": frames_per_launch,
+                "pass_ms_per_step": {k: v / prof_steps for k, v in pass_ms.items()},
+                "whole_frame_algorithmic_bytes": total_alg, "whole_frame_achieved_GBs": total_alg * n * world * opts.steps / (ms_total * 1e-3) / 1e9}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not opts.no_cpu_baseline:
+        kind, render, threads = cpu_reference_runner(wl)
+        n_sample = min(n, max(threads * 2, 8))
+        sample = [poses[(i * n) // n_sample] for i in range(n_sample)]
+        render(sample[:min(threads, n_sample)])
+        reps, tcpu = 0, 0.0
+        while tcpu < 10.0 and reps < 50:
+            tcpu += render(sample)
+            reps += 1
+        cpu = {"value": n_sample * reps / tcpu, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": "%d evenly spaced poses of the sequence x %d repetitions, frames spread over %d host threads (each frame single-threaded like the reference)" % (n_sample, reps, threads)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": opts.steps, "warmup": max(3, opts.warmup),
+                "ms_per_step": ms_total / opts.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["label"], "frames_per_step_per_gpu": n, "image": [W, H], "triangles": len(wl["tris"]),
+                           "partition": "frame k of the global sequence on rank k mod N; no collective", "l2": "working set per 32-frame batch ~1 GB >> 126 MB L2 (inputs/outputs larger than L2)",
+                           "outputs": "RGB8 planes + f32 depth per frame, written to HBM"},
+                "mtris_per_s": fps * len(wl["tris"]) / 1e6, "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+                "stats_last_frame": st, "checksum": checksum}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    r.close()
+
+
+if __name__ == "__main__":
+    main()

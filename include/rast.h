@@ -87,10 +87,12 @@ void rast_destroy(rast_ctx *ctx);
 const char *rast_last_error(const rast_ctx *ctx); /* ctx may be NULL: error of the last failed rast_create */
 const char *rast_version(void);
 
-/* Launch on this cudaStream_t (as void*) instead of the context's own stream; NULL restores it.
- * Lets a host that owns streams (e.g. torch.cuda.current_stream().cuda_stream) time and order
- * the kernels itself. */
+/* Launch on this cudaStream_t (passed as void*; NULL is the legacy default stream) instead of the
+ * context's own non-blocking stream.  Lets a host that owns streams (e.g.
+ * torch.cuda.current_stream().cuda_stream) time and order the kernels itself.
+ * rast_use_own_stream switches back. */
 int rast_set_stream(rast_ctx *ctx, void *cuda_stream);
+int rast_use_own_stream(rast_ctx *ctx);
 
 /* ---- scene upload (once; replaces handing the std::vectors to draw_frame each call) -------- */
 /* positions xyz[n_positions], normals xyz[n_normals], uvs uv[n_uvs]; tris = 10 x int32 per

@@ -38,6 +38,7 @@ SYMBOLS = {
     "rast_last_error": (C.c_char_p, [C.c_void_p]),
     "rast_version": (C.c_char_p, []),
     "rast_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rast_use_own_stream": (C.c_int, [C.c_void_p]),
     "rast_upload_mesh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]),
     "rast_upload_materials": (C.c_int, [C.c_void_p, C.POINTER(RastMaterial), C.c_uint32]),
     "rast_set_lights": (C.c_int, [C.c_void_p, C.POINTER(RastLight), C.c_uint32]),

@@ -138,7 +138,11 @@ class Renderer:
         self._band = (int(y0), int(y1)) if y1 > y0 else None
 
     def set_stream(self, cuda_stream):
-        self._check(self._lib.rast_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None), "rast_set_stream")
+        """Launch on this cudaStream_t handle (int; 0 = the legacy default stream)."""
+        self._check(self._lib.rast_set_stream(self._h, C.c_void_p(int(cuda_stream))), "rast_set_stream")
+
+    def use_own_stream(self):
+        self._check(self._lib.rast_use_own_stream(self._h), "rast_use_own_stream")
 
     # ---- drawing ----
     def draw_frame(self, args, frame=None, depth=None, want_depth=True):
@@ -155,7 +159,7 @@ class Renderer:
     def draw_frames(self, args_list, frames=None, depths=None, want_depth=False):
         """Several frames of the uploaded scene in one call (host outputs)."""
         n = len(args_list)
-        arr = (RastArgs * n)(*[_as_rast_args(a) for a in args_list])
+        arr = args_list if isinstance(args_list, C.Array) else (RastArgs * n)(*[_as_rast_args(a) for a in args_list])
         rows = self._band_rows(arr[0].image_height)
         if frames is None:
             frames = np.empty((n, 3, rows, arr[0].image_width), np.uint8)

@@ -43,10 +43,14 @@ struct Scene {
     const float *nrm;         // xyz [Nn]
     const float2 *uv;         // [Nuv]
     const int *vidx0, *vidx1, *vidx2; // vertex indices, SoA [T] (coalesced in the per-triangle pass)
-    const int4 *attr;         // [2T]: (n0,n1,n2,material), (t0,t1,t2,-) -- touched only for visible triangles
+    const int4 *tri_rec;      // [3T]: (v0,v1,v2,n0) (n1,n2,t0,t1) (t2,material,-,-): one 48-byte record per
+                              // triangle, read only by the shade pass for winning triangles.  Absent (-1)
+                              // normal / uv / material indices are remapped on upload to a sentinel entry
+                              // appended to each array (zero normal, uv (0,0), white untextured material),
+                              // so the shade pass needs no index checks
     const MaterialDev *mats;
     const float *texels;
-    uint32_t V, Nn, Nuv, M;
+    uint32_t V, Nn, Nuv, M;   // Nn, Nuv, M count the appended sentinel entry
     uint64_t T;
 };
 
@@ -60,6 +64,8 @@ struct Batch {
     const FrameParams *frames;
     uint32_t n_frames;
     float4 *rv;               // raster vertices (x, y, ndc z, 1/w) [n_frames][V]  (drawing.cpp:216,247)
+    float4 *cn;               // camera-space normals [n_frames][Nn] (drawing.cpp:219,236) or nullptr: then the
+                              // shade pass transforms the three normals of each winning triangle itself
     unsigned long long *vis;  // visibility buffer [n_frames][band_pixels]
     uint2 *queue;             // work items (triangle, cx | cy<<12 | frame<<24)
     uint32_t queue_cap;
@@ -185,22 +191,29 @@ __global__ void k_clear(unsigned long long *vis, size_t n, unsigned long long *c
 // transform_point + z_divide + ndc_to_raster (geometry.cpp:44-74, drawing.cpp:241-247) fused: one
 // thread per vertex, 12 B in, one float4 out.
 __global__ void __launch_bounds__(256) k_vertex(Scene sc, View vw, Batch bt) {
-    __shared__ float cam[16];
+    __shared__ float cam[16], nm[16];
     const uint32_t f = blockIdx.y;
     if (threadIdx.x < 16) cam[threadIdx.x] = bt.frames[f].camera[threadIdx.x];
+    else if (threadIdx.x < 32) nm[threadIdx.x - 16] = bt.frames[f].normal_m[threadIdx.x - 16];
     __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= sc.V) return;
     using namespace exact;
-    const float x = sc.pos[3 * (size_t)i], y = sc.pos[3 * (size_t)i + 1], z = sc.pos[3 * (size_t)i + 2];
-    const float4 clip = mat_vec(cam, x, y, z, 1.f);
-    const float nx = div(clip.x, clip.w), ny = div(clip.y, clip.w), nz = div(clip.z, clip.w), nw = div(1.f, clip.w);
-    float4 r;
-    r.x = mul(mul(0.5f, add(nx, 1.0f)), (float)(int)vw.W);   // remap_ndc(x, width)
-    r.y = mul(mul(0.5f, add(-ny, 1.0f)), (float)(int)vw.H);  // remap_ndc(-y, height)
-    r.z = nz;
-    r.w = nw;
-    bt.rv[(size_t)f * sc.V + i] = r;
+    if (i < sc.V) {
+        const float x = sc.pos[3 * (size_t)i], y = sc.pos[3 * (size_t)i + 1], z = sc.pos[3 * (size_t)i + 2];
+        const float4 clip = mat_vec(cam, x, y, z, 1.f);
+        const float nx = div(clip.x, clip.w), ny = div(clip.y, clip.w), nz = div(clip.z, clip.w), nw = div(1.f, clip.w);
+        float4 r;
+        r.x = mul(mul(0.5f, add(nx, 1.0f)), (float)(int)vw.W);   // remap_ndc(x, width)
+        r.y = mul(mul(0.5f, add(-ny, 1.0f)), (float)(int)vw.H);  // remap_ndc(-y, height)
+        r.z = nz;
+        r.w = nw;
+        bt.rv[(size_t)f * sc.V + i] = r;
+    } else if (bt.cn != nullptr && i - sc.V < sc.Nn) {
+        // transform_normals (geometry.cpp:97-108): transpose(inverse(modelview)) * (n, 0), xyz kept, not normalised
+        const uint32_t j = i - sc.V;
+        const float4 t = mat_vec(nm, sc.nrm[3 * (size_t)j], sc.nrm[3 * (size_t)j + 1], sc.nrm[3 * (size_t)j + 2], 0.f);
+        bt.cn[(size_t)f * sc.Nn + j] = make_float4(t.x, t.y, t.z, 0.f);
+    }
 }
 
 // ---- K2: triangle setup, cull, classification -----------------------------------------------
@@ -249,72 +262,130 @@ __global__ void __launch_bounds__(256) k_setup(Scene sc, View vw, Batch bt) {
 }
 
 // ---- K3: chunk rasteriser -------------------------------------------------------------------
-// One warp per work item; lanes own 2x2 pixel quads of a 16x8 block, so the per-pixel
-// differences (p - a) and half of the products of edge() are shared inside the quad.  A ballot
-// skips blocks no lane may cover.  update_pixel's coverage + depth part (drawing.cpp:108-121).
-__global__ void __launch_bounds__(256) k_raster_chunks(Scene sc, View vw, Batch bt) {
+// update_pixel's coverage + depth part (drawing.cpp:108-121) for the queued work items.
+// A warp takes 32 items at a time: each lane fetches ONE item (queue entry -> indices -> vertices, the
+// three dependent loads overlap across the 32 lanes), computes its triangle setup and stages it in
+// shared memory; then the whole warp walks the 32 staged items one after another.  Lanes own 2x2
+// pixel quads of a 16x8 block, so the per-pixel differences (p - a) and half of the products of
+// edge() are shared inside the quad; a ballot skips blocks no lane may cover.
+constexpr int RASTER_WARPS = 8;
+constexpr int STAGE_FIELDS = 21;
+
+struct StagedTris {
+    uint32_t w[STAGE_FIELDS][32]; // [field][slot]: conflict-free lane-per-slot writes, broadcast reads
+};
+
+__global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_chunks(Scene sc, View vw, Batch bt) {
+    __shared__ StagedTris stage_all[RASTER_WARPS];
+    StagedTris &stg = stage_all[threadIdx.x >> 5];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t count = (uint32_t)min(bt.counters[0], (unsigned long long)bt.queue_cap);
     const uint32_t qx = (lane & 7u) * 2u, qy = (lane >> 3) * 2u;
     for (;;) {
-        uint32_t e = 0;
-        if (lane == 0) e = (uint32_t)min(atomicAdd(&bt.counters[1], 1ull), 0xFFFFFFFFull);
-        e = __shfl_sync(0xFFFFFFFFu, e, 0);
-        if (e >= count) break;
-        const uint2 item = bt.queue[e];
-        const uint32_t tri = item.x;
-        if (tri == INVALID_TRI) continue;
-        const uint32_t cx = item.y & 0xFFFu, cy = (item.y >> 12) & 0xFFFu, f = item.y >> 24;
-        const float4 *rv = bt.rv + (size_t)f * sc.V;
-        const float4 v0 = rv[sc.vidx0[tri]], v1 = rv[sc.vidx1[tri]], v2 = rv[sc.vidx2[tri]];
-        const BBox bb = bounding_box(v0, v1, v2, vw);
-        TriSetup s;
-        tri_setup(s, v0, v1, v2);
-        unsigned long long *vis = bt.vis + (size_t)f * vw.band_pixels;
+        uint32_t base = 0;
+        if (lane == 0) base = (uint32_t)min(atomicAdd(&bt.counters[1], 32ull), 0xFFFFFFFFull);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= count) break;
+        const uint32_t n_items = min(32u, count - base);
 
-        const uint32_t rx0 = bb.x0 + cx * CHUNK, ry0 = bb.y0 + cy * CHUNK;
-        const uint32_t rx1 = min(bb.x1, rx0 + CHUNK - 1u), ry1 = min(bb.y1, ry0 + CHUNK - 1u);
-        for (uint32_t by = ry0; by <= ry1; by += 8u) {
-            for (uint32_t bx = rx0; bx <= rx1; bx += 16u) {
+        // ---- stage: lane = item ----
+        {
+            uint32_t tri = INVALID_TRI, rect0 = 0, rect1 = 0, f = 0;
+            TriSetup s = {};
+            if (lane < n_items) {
+                const uint2 item = bt.queue[base + lane];
+                tri = item.x;
+                if (tri != INVALID_TRI) {
+                    const uint32_t cx = item.y & 0xFFFu, cy = (item.y >> 12) & 0xFFFu;
+                    f = item.y >> 24;
+                    const float4 *rv = bt.rv + (size_t)f * sc.V;
+                    const float4 v0 = rv[sc.vidx0[tri]], v1 = rv[sc.vidx1[tri]], v2 = rv[sc.vidx2[tri]];
+                    const BBox bb = bounding_box(v0, v1, v2, vw);
+                    tri_setup(s, v0, v1, v2);
+                    const uint32_t rx0 = bb.x0 + cx * CHUNK, ry0 = bb.y0 + cy * CHUNK;
+                    const uint32_t rx1 = min(bb.x1, rx0 + CHUNK - 1u), ry1 = min(bb.y1, ry0 + CHUNK - 1u);
+                    rect0 = rx0 | (ry0 << 16);
+                    rect1 = rx1 | (ry1 << 16);
+                }
+            }
+            const float fl[16] = {s.x0, s.y0, s.x1, s.y1, s.x2, s.y2, s.z0, s.z1, s.z2, s.d12x, s.d12y, s.d20x, s.d20y, s.d01x, s.d01y, s.area};
+#pragma unroll
+            for (int k = 0; k < 16; ++k) stg.w[k][lane] = __float_as_uint(fl[k]);
+            stg.w[16][lane] = s.flip | (s.literal ? 1u : 0u);
+            stg.w[17][lane] = rect0;
+            stg.w[18][lane] = rect1;
+            stg.w[19][lane] = tri;
+            stg.w[20][lane] = f;
+        }
+        __syncwarp();
+
+        // ---- rasterise: warp = item, lane = 2x2 quad ----
+        for (uint32_t it = 0; it < n_items; ++it) {
+            const uint32_t tri = stg.w[19][it];
+            if (tri == INVALID_TRI) continue;
+            TriSetup s;
+            s.x0 = __uint_as_float(stg.w[0][it]); s.y0 = __uint_as_float(stg.w[1][it]);
+            s.x1 = __uint_as_float(stg.w[2][it]); s.y1 = __uint_as_float(stg.w[3][it]);
+            s.x2 = __uint_as_float(stg.w[4][it]); s.y2 = __uint_as_float(stg.w[5][it]);
+            s.z0 = __uint_as_float(stg.w[6][it]); s.z1 = __uint_as_float(stg.w[7][it]); s.z2 = __uint_as_float(stg.w[8][it]);
+            s.d12x = __uint_as_float(stg.w[9][it]); s.d12y = __uint_as_float(stg.w[10][it]);
+            s.d20x = __uint_as_float(stg.w[11][it]); s.d20y = __uint_as_float(stg.w[12][it]);
+            s.d01x = __uint_as_float(stg.w[13][it]); s.d01y = __uint_as_float(stg.w[14][it]);
+            s.area = __uint_as_float(stg.w[15][it]);
+            const uint32_t fw = stg.w[16][it];
+            s.flip = fw & 0x80000000u;
+            s.literal = (fw & 1u) != 0u;
+            const uint32_t rect0 = stg.w[17][it], rect1 = stg.w[18][it];
+            const uint32_t rx0 = rect0 & 0xFFFFu, ry0 = rect0 >> 16, rx1 = rect1 & 0xFFFFu, ry1 = rect1 >> 16;
+            unsigned long long *vis = bt.vis + (size_t)stg.w[20][it] * vw.band_pixels;
+
+            for (uint32_t by = ry0; by <= ry1; by += 8u) {
                 using namespace exact;
-                const uint32_t x = bx + qx, y = by + qy;
-                const float pxa = (float)x, pxb = (float)(x + 1u), pya = (float)y, pyb = (float)(y + 1u);
+                const uint32_t y = by + qy;
+                const float pya = (float)y, pyb = (float)(y + 1u);
                 // edge k at pixel (i,j): mul(dkx, py_j - yk) - mul(dky, px_i - xk)
                 const float a0a = mul(s.d12x, sub(pya, s.y1)), a0b = mul(s.d12x, sub(pyb, s.y1));
                 const float a1a = mul(s.d20x, sub(pya, s.y2)), a1b = mul(s.d20x, sub(pyb, s.y2));
                 const float a2a = mul(s.d01x, sub(pya, s.y0)), a2b = mul(s.d01x, sub(pyb, s.y0));
-                const float c0a = mul(s.d12y, sub(pxa, s.x1)), c0b = mul(s.d12y, sub(pxb, s.x1));
-                const float c1a = mul(s.d20y, sub(pxa, s.x2)), c1b = mul(s.d20y, sub(pxb, s.x2));
-                const float c2a = mul(s.d01y, sub(pxa, s.x0)), c2b = mul(s.d01y, sub(pxb, s.x0));
-                float e0[4], e1[4], e2[4]; // (xa,ya) (xb,ya) (xa,yb) (xb,yb)
-                e0[0] = sub(a0a, c0a); e0[1] = sub(a0a, c0b); e0[2] = sub(a0b, c0a); e0[3] = sub(a0b, c0b);
-                e1[0] = sub(a1a, c1a); e1[1] = sub(a1a, c1b); e1[2] = sub(a1b, c1a); e1[3] = sub(a1b, c1b);
-                e2[0] = sub(a2a, c2a); e2[1] = sub(a2a, c2b); e2[2] = sub(a2b, c2a); e2[3] = sub(a2b, c2b);
-                uint32_t mask = 0;
+                const uint32_t ymask = (y <= ry1 ? 3u : 0u) | (y + 1u <= ry1 ? 12u : 0u);
+                for (uint32_t bx = rx0; bx <= rx1; bx += 16u) {
+                    const uint32_t x = bx + qx;
+                    const float pxa = (float)x, pxb = (float)(x + 1u);
+                    const float c0a = mul(s.d12y, sub(pxa, s.x1)), c0b = mul(s.d12y, sub(pxb, s.x1));
+                    const float c1a = mul(s.d20y, sub(pxa, s.x2)), c1b = mul(s.d20y, sub(pxb, s.x2));
+                    const float c2a = mul(s.d01y, sub(pxa, s.x0)), c2b = mul(s.d01y, sub(pxb, s.x0));
+                    float e0[4], e1[4], e2[4]; // (xa,ya) (xb,ya) (xa,yb) (xb,yb)
+                    e0[0] = sub(a0a, c0a); e0[1] = sub(a0a, c0b); e0[2] = sub(a0b, c0a); e0[3] = sub(a0b, c0b);
+                    e1[0] = sub(a1a, c1a); e1[1] = sub(a1a, c1b); e1[2] = sub(a1b, c1a); e1[3] = sub(a1b, c1b);
+                    e2[0] = sub(a2a, c2a); e2[1] = sub(a2a, c2b); e2[2] = sub(a2b, c2a); e2[3] = sub(a2b, c2b);
+                    const uint32_t inrect = ymask & ((x <= rx1 ? 5u : 0u) | (x + 1u <= rx1 ? 10u : 0u));
+                    uint32_t mask = 0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const bool in_rect = (x + (k & 1)) <= rx1 && (y + (k >> 1)) <= ry1;
-                    if (in_rect && candidate(s, e0[k], e1[k], e2[k])) mask |= 1u << k;
-                }
-                if (!__any_sync(0xFFFFFFFFu, mask != 0u)) continue;
+                    for (int k = 0; k < 4; ++k)
+                        if (candidate(s, e0[k], e1[k], e2[k])) mask |= 1u << k;
+                    mask &= inrect;
+                    if (!__any_sync(0xFFFFFFFFu, mask != 0u)) continue;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (mask & (1u << k)) {
-                        float b0, b1, b2, z;
-                        if (fragment(s, e0[k], e1[k], e2[k], b0, b1, b2, z)) {
-                            const unsigned long long key = ((unsigned long long)depth_key(z) << 32) | tri;
-                            atomicMin(vis + (size_t)(y + (k >> 1) - vw.y0) * vw.W + (x + (k & 1)), key);
+                    for (int k = 0; k < 4; ++k) {
+                        if (mask & (1u << k)) {
+                            float b0, b1, b2, z;
+                            if (fragment(s, e0[k], e1[k], e2[k], b0, b1, b2, z)) {
+                                const unsigned long long key = ((unsigned long long)depth_key(z) << 32) | tri;
+                                atomicMin(vis + (size_t)(y + (k >> 1) - vw.y0) * vw.W + (x + (k & 1)), key);
+                            }
                         }
                     }
                 }
             }
         }
+        __syncwarp();
     }
 }
 
 // ---- K4: resolve + deferred shading ---------------------------------------------------------
-// CImg::_linear_atXY (CImg.h:13475-13492) on one channel plane
-__device__ __forceinline__ float linear_at(const float *plane, int w, int h, float fx, float fy) {
+// Material::sample on a textured material (material.cpp:19-21): three CImg::_linear_atXY lookups
+// (CImg.h:13475-13492) at the same position; the position arithmetic is shared between the channels.
+__device__ __forceinline__ void sample_texture(const float *tex, int w, int h, float fx, float fy, float &r, float &g, float &b) {
     using namespace exact;
     const float hx = (float)(w - 1), hy = (float)(h - 1);
     const float nfx = fx < 0.f ? 0.f : (fx > hx ? hx : fx); // cimg::cut (CImg.h:5184-5186)
@@ -322,78 +393,106 @@ __device__ __forceinline__ float linear_at(const float *plane, int w, int h, flo
     const uint32_t x = to_uint(nfx), y = to_uint(nfy);
     const float dx = sub(nfx, (float)x), dy = sub(nfy, (float)y);
     const uint32_t nx = dx > 0.f ? x + 1u : x, ny = dy > 0.f ? y + 1u : y;
-    const float Icc = plane[x + (size_t)y * w], Inc = plane[nx + (size_t)y * w];
-    const float Icn = plane[x + (size_t)ny * w], Inn = plane[nx + (size_t)ny * w];
-    const float t1 = sub(sub(add(Icc, Inn), Icn), Inc);
-    const float t2 = add(sub(Inc, Icc), mul(dy, t1));
-    return add(add(Icc, mul(dx, t2)), mul(dy, sub(Icn, Icc)));
+    const uint32_t occ = x + y * (uint32_t)w, onc = nx + y * (uint32_t)w, ocn = x + ny * (uint32_t)w, onn = nx + ny * (uint32_t)w;
+    const uint32_t plane = (uint32_t)w * (uint32_t)h;
+    float out[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float *p = tex + (size_t)c * plane;
+        const float Icc = p[occ], Inc = p[onc], Icn = p[ocn], Inn = p[onn];
+        const float t1 = sub(sub(add(Icc, Inn), Icn), Inc);
+        const float t2 = add(sub(Inc, Icc), mul(dy, t1));
+        out[c] = add(add(Icc, mul(dx, t2)), mul(dy, sub(Icn, Icc)));
+    }
+    r = out[0]; g = out[1]; b = out[2];
 }
 
 struct Shaded { uint32_t r, g, b; float depth; };
 
+constexpr uint32_t PARAM_LIGHTS = 64;
+
+// The first PARAM_LIGHTS lights travel as a kernel parameter (constant bank: uniform loads, no staging, no
+// barrier): (-trans_dir.xyz, intensity*colour.r) (intensity*colour.g, intensity*colour.b).
+struct LightTable {
+    uint32_t n;          // all lights
+    uint32_t pad[3];
+    float4 a[PARAM_LIGHTS];
+    float2 c[PARAM_LIGHTS];
+};
+
 // The shading half of update_pixel (drawing.cpp:121-146) for the winning triangle of one pixel.
-__device__ __forceinline__ Shaded shade_pixel(unsigned long long key, uint32_t x, uint32_t y, const Scene &sc, const float4 *rv,
-                                              const FrameParams &fp, const LightDev *lights, uint32_t n_lights) {
+template <bool PRE_NORMALS>
+__device__ __forceinline__ Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t y, const Scene &sc, const float4 *__restrict__ rv,
+                                              const float4 *__restrict__ cn, const float *__restrict__ normal_m, bool wind_clockwise,
+                                              const LightTable &lt, const LightDev *__restrict__ lights) {
     using namespace exact;
     Shaded out;
-    if (key == VIS_EMPTY) { out.r = out.g = out.b = 0u; out.depth = 1.0f; return out; }
-    const uint32_t tri = (uint32_t)key;
-    const float4 v0 = rv[sc.vidx0[tri]], v1 = rv[sc.vidx1[tri]], v2 = rv[sc.vidx2[tri]];
-    TriSetup s;
-    tri_setup(s, v0, v1, v2);
-    float e0, e1, e2;
-    edges(s, (float)x, (float)y, e0, e1, e2);
-    const float b0 = div(e0, s.area), b1 = div(e1, s.area), b2 = div(e2, s.area);
-    out.depth = add(add(mul(v0.z, b0), mul(v1.z, b1)), mul(v2.z, b2)); // same bits as the raster pass
+    const int4 *rec = sc.tri_rec + 3 * (size_t)tri;
+    const int4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
+    const float4 v0 = rv[r0.x], v1 = rv[r0.y], v2 = rv[r0.z];
+
+    // vertex normals in camera space (transform_direction, geometry.cpp:35-42,97-108)
+    float4 n0, n1, n2;
+    if (PRE_NORMALS) {
+        n0 = cn[r0.w]; n1 = cn[r1.x]; n2 = cn[r1.y];
+    } else {
+        const float *m0 = sc.nrm + 3 * (size_t)r0.w, *m1 = sc.nrm + 3 * (size_t)r1.x, *m2 = sc.nrm + 3 * (size_t)r1.y;
+        float nm[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) nm[k] = __ldg(normal_m + k);
+        n0 = mat_vec(nm, __ldg(m0), __ldg(m0 + 1), __ldg(m0 + 2), 0.f);
+        n1 = mat_vec(nm, __ldg(m1), __ldg(m1 + 1), __ldg(m1 + 2), 0.f);
+        n2 = mat_vec(nm, __ldg(m2), __ldg(m2 + 1), __ldg(m2 + 2), 0.f);
+    }
+    const MaterialDev *mp = sc.mats + r2.y;
+    const float4 mk = __ldg(reinterpret_cast<const float4 *>(mp));      // kd.rgb, has_texture
+    const int4 mt = __ldg(reinterpret_cast<const int4 *>(mp) + 1);      // tex_w, tex_h, texel_offset (lo, hi)
+
+    // barycentric + depth, the same operations as the raster pass => the same bits (drawing.cpp:41-49,115-116)
+    const float px = (float)x, py = (float)y;
+    const float area = sub(mul(sub(v1.x, v0.x), sub(v2.y, v0.y)), mul(sub(v1.y, v0.y), sub(v2.x, v0.x)));
+    const float e0 = sub(mul(sub(v2.x, v1.x), sub(py, v1.y)), mul(sub(v2.y, v1.y), sub(px, v1.x)));
+    const float e1 = sub(mul(sub(v0.x, v2.x), sub(py, v2.y)), mul(sub(v0.y, v2.y), sub(px, v2.x)));
+    const float e2 = sub(mul(sub(v1.x, v0.x), sub(py, v0.y)), mul(sub(v1.y, v0.y), sub(px, v0.x)));
+    const float b0 = div(e0, area), b1 = div(e1, area), b2 = div(e2, area);
+    out.depth = add(add(mul(v0.z, b0), mul(v1.z, b1)), mul(v2.z, b2));
 
     // interpolation_coords + camera-space depth (drawing.cpp:125-128)
     const float i0 = mul(v0.w, b0), i1 = mul(v1.w, b1), i2 = mul(v2.w, b2);
     const float d = div(1.f, add(add(i0, i1), i2));
 
-    const int4 an = sc.attr[2 * (size_t)tri], at = sc.attr[2 * (size_t)tri + 1];
-    // transform_direction on the three vertex normals (geometry.cpp:35-42,97-108), done lazily here
-    float3 n[3];
-    const int nidx[3] = {an.x, an.y, an.z};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        float mx = 0.f, my = 0.f, mz = 0.f;
-        if (nidx[k] >= 0) { mx = sc.nrm[3 * (size_t)nidx[k]]; my = sc.nrm[3 * (size_t)nidx[k] + 1]; mz = sc.nrm[3 * (size_t)nidx[k] + 2]; }
-        const float4 t = mat_vec(fp.normal_m, mx, my, mz, 0.f);
-        n[k] = make_float3(t.x, t.y, t.z);
-    }
     // perspective_interpolate + normalize (drawing.cpp:64-75,131-132)
-    const float mx = mul(d, add(add(mul(i0, n[0].x), mul(i1, n[1].x)), mul(i2, n[2].x)));
-    const float my = mul(d, add(add(mul(i0, n[0].y), mul(i1, n[1].y)), mul(i2, n[2].y)));
-    const float mz = mul(d, add(add(mul(i0, n[0].z), mul(i1, n[1].z)), mul(i2, n[2].z)));
+    const float mx = mul(d, add(add(mul(i0, n0.x), mul(i1, n1.x)), mul(i2, n2.x)));
+    const float my = mul(d, add(add(mul(i0, n0.y), mul(i1, n1.y)), mul(i2, n2.y)));
+    const float mz = mul(d, add(add(mul(i0, n0.z), mul(i1, n1.z)), mul(i2, n2.z)));
     const float inv = div(1.f, fsqrt(add(add(mul(mx, mx), mul(my, my)), mul(mz, mz))));
     float nx = mul(mx, inv), ny = mul(my, inv), nz = mul(mz, inv);
-    if (fp.wind_clockwise) { nx = -nx; ny = -ny; nz = -nz; }
+    if (wind_clockwise) { nx = -nx; ny = -ny; nz = -nz; }
 
-    // Material::sample (material.cpp:11-26); material -1 = untextured white (unpinned corner)
-    float ar = 1.f, ag = 1.f, ab = 1.f;
-    if (an.w >= 0 && (uint32_t)an.w < sc.M) {
-        const MaterialDev m = sc.mats[an.w];
-        if (m.has_texture) {
-            float2 uv[3];
-            const int tidx[3] = {at.x, at.y, at.z};
-#pragma unroll
-            for (int k = 0; k < 3; ++k) uv[k] = tidx[k] >= 0 ? sc.uv[tidx[k]] : make_float2(0.f, 0.f);
-            const float u = mul(d, add(add(mul(i0, uv[0].x), mul(i1, uv[1].x)), mul(i2, uv[2].x))); // drawing.cpp:135
-            const float v = mul(d, add(add(mul(i0, uv[0].y), mul(i1, uv[1].y)), mul(i2, uv[2].y)));
-            const float fx = mul(u, (float)m.tex_w), fy = mul(sub(1.f, v), (float)m.tex_h);
-            const float *tex = sc.texels + m.texel_offset;
-            const size_t plane = (size_t)m.tex_w * m.tex_h;
-            ar = linear_at(tex, m.tex_w, m.tex_h, fx, fy);
-            ag = linear_at(tex + plane, m.tex_w, m.tex_h, fx, fy);
-            ab = linear_at(tex + 2 * plane, m.tex_w, m.tex_h, fx, fy);
-        } else {
-            ar = m.kd[0]; ag = m.kd[1]; ab = m.kd[2];
-        }
+    // Material::sample (material.cpp:11-26)
+    float ar = mk.x, ag = mk.y, ab = mk.z;
+    if (__float_as_int(mk.w) != 0) {
+        const float2 uv0 = __ldg(sc.uv + r1.z), uv1 = __ldg(sc.uv + r1.w), uv2 = __ldg(sc.uv + r2.x);
+        const float u = mul(d, add(add(mul(i0, uv0.x), mul(i1, uv1.x)), mul(i2, uv2.x))); // drawing.cpp:135
+        const float v = mul(d, add(add(mul(i0, uv0.y), mul(i1, uv1.y)), mul(i2, uv2.y)));
+        const long long toff = ((long long)(uint32_t)mt.z) | ((long long)mt.w << 32);
+        sample_texture(sc.texels + toff, mt.x, mt.y, mul(u, (float)mt.x), mul(sub(1.f, v), (float)mt.y), ar, ag, ab);
     }
 
     // shade / light_contribution (shading.cpp:20-34)
     float sr = 0.f, sg = 0.f, sb = 0.f;
-    for (uint32_t l = 0; l < n_lights; ++l) {
+    const uint32_t n_p = lt.n < PARAM_LIGHTS ? lt.n : PARAM_LIGHTS;
+#pragma unroll 1
+    for (uint32_t l = 0; l < n_p; ++l) {
+        const float4 a = lt.a[l];
+        const float2 c = lt.c[l];
+        const float k = glm_max(0.f, add(add(mul(nx, a.x), mul(ny, a.y)), mul(nz, a.z)));
+        sr = add(sr, mul(mul(mul(a.w, ar), k), 0.318309886183790671537767526745028724f));
+        sg = add(sg, mul(mul(mul(c.x, ag), k), 0.318309886183790671537767526745028724f));
+        sb = add(sb, mul(mul(mul(c.y, ab), k), 0.318309886183790671537767526745028724f));
+    }
+#pragma unroll 1
+    for (uint32_t l = n_p; l < lt.n; ++l) { // beyond the parameter table: straight from global memory
         const LightDev L = lights[l];
         const float k = glm_max(0.f, add(add(mul(nx, L.ntx), mul(ny, L.nty)), mul(nz, L.ntz)));
         sr = add(sr, mul(mul(mul(L.icr, ar), k), 0.318309886183790671537767526745028724f));
@@ -406,61 +505,68 @@ __device__ __forceinline__ Shaded shade_pixel(unsigned long long key, uint32_t x
     return out;
 }
 
-// One thread per 4 consecutive pixels: keys in as 2 x 16 B, colour out as one uchar4 per plane
-// and depth as one float4 (CImg planar layout, CImg.h:11715-11721).  VEC requires
-// band_pixels % 4 == 0 and 16-byte aligned outputs; otherwise the scalar variant runs.
-template <bool VEC>
-__global__ void __launch_bounds__(256) k_resolve_shade(Scene sc, View vw, Batch bt, const LightDev *lights, uint32_t n_lights,
-                                                       uint8_t *rgb, float *depth) {
-    __shared__ FrameParams fp;
-    __shared__ LightDev sl[64];
-    const uint32_t f = blockIdx.y;
-    for (uint32_t i = threadIdx.x; i < sizeof(FrameParams) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(&fp)[i] = reinterpret_cast<const uint32_t *>(&bt.frames[f])[i];
-    const uint32_t nl_s = n_lights <= 64u ? n_lights : 0u;
-    for (uint32_t i = threadIdx.x; i < nl_s * (sizeof(LightDev) / 4); i += blockDim.x) reinterpret_cast<uint32_t *>(sl)[i] = reinterpret_cast<const uint32_t *>(lights)[i];
-    __syncthreads();
-    const LightDev *lp = nl_s ? sl : lights;
+// Grid: x = chunks of SHADE_THREADS * PX pixels along a row, y = row of the band, z = frame of the batch,
+// so no thread divides to find its pixel.  PX = 1: a warp reads 256 B of keys and writes one full 32-byte
+// sector per colour plane plus 128 B of depth.  PX = 4 (W % 4 == 0, 16-byte aligned outputs): keys in as
+// 2 x 16 B, colour out as one uchar4 per plane, depth as one float4 (CImg planar layout, CImg.h:11715-11721).
+constexpr int SHADE_THREADS = 128;
 
+template <int PX, bool PRE_NORMALS>
+__global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View vw, Batch bt, const __grid_constant__ LightTable lt,
+                                                                 const LightDev *__restrict__ lights, uint8_t *__restrict__ rgb, float *__restrict__ depth) {
+    const uint32_t x0 = (blockIdx.x * SHADE_THREADS + threadIdx.x) * PX;
+    if (x0 >= vw.W) return;
+    const uint32_t row = blockIdx.y, f = blockIdx.z;
     const uint32_t P = vw.band_pixels;
-    const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i4 >= P) return;
-    const unsigned long long *vis = bt.vis + (size_t)f * P;
-    const float4 *rv = bt.rv + (size_t)f * sc.V;
-    uint8_t *out_r = rgb + (size_t)f * 3 * P, *out_g = out_r + P, *out_b = out_g + P;
-    float *out_d = depth ? depth + (size_t)f * P : nullptr;
+    const size_t i0 = (size_t)f * P + (size_t)row * vw.W + x0;          // into vis / depth
+    const size_t o0 = (size_t)f * 3 * P + (size_t)row * vw.W + x0;      // into the R plane of frame f
+    const unsigned long long *vis = bt.vis + i0;
 
-    unsigned long long keys[4];
-    if (VEC) {
-        const ulonglong2 k01 = *reinterpret_cast<const ulonglong2 *>(vis + i4), k23 = *reinterpret_cast<const ulonglong2 *>(vis + i4 + 2);
-        keys[0] = k01.x; keys[1] = k01.y; keys[2] = k23.x; keys[3] = k23.y;
+    unsigned long long keys[PX];
+    if (PX == 4) {
+        const ulonglong2 k01 = *reinterpret_cast<const ulonglong2 *>(vis), k23 = *reinterpret_cast<const ulonglong2 *>(vis + 2);
+        keys[0] = k01.x; keys[PX > 1 ? 1 : 0] = k01.y; keys[PX > 2 ? 2 : 0] = k23.x; keys[PX > 3 ? 3 : 0] = k23.y;
     } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) keys[k] = (i4 + k < P) ? vis[i4 + k] : VIS_EMPTY;
+        keys[0] = *vis;
     }
-    Shaded px[4];
-    uint32_t x = (uint32_t)(i4 % vw.W), y = vw.y0 + (uint32_t)(i4 / vw.W);
+    bool any = false;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        px[k] = shade_pixel(keys[k], x, y, sc, rv, fp, lp, n_lights);
-        if (++x == vw.W) { x = 0; ++y; }
+    for (int k = 0; k < PX; ++k) any |= keys[k] != VIS_EMPTY;
+
+    Shaded px[PX];
+#pragma unroll
+    for (int k = 0; k < PX; ++k) { px[k].r = px[k].g = px[k].b = 0u; px[k].depth = 1.0f; } // renderer.cpp:85-86
+    if (any) {
+        const float4 *rv = bt.rv + (size_t)f * sc.V;
+        const float4 *cn = PRE_NORMALS ? bt.cn + (size_t)f * sc.Nn : nullptr;
+        const FrameParams *fp = bt.frames + f;
+        const bool cw = __ldg(&fp->wind_clockwise) != 0u;
+#pragma unroll
+        for (int k = 0; k < PX; ++k)
+            if (keys[k] != VIS_EMPTY) px[k] = shade_pixel<PRE_NORMALS>((uint32_t)keys[k], x0 + k, vw.y0 + row, sc, rv, cn, fp->normal_m, cw, lt, lights);
     }
-    if (VEC) {
-        *reinterpret_cast<uchar4 *>(out_r + i4) = make_uchar4(px[0].r, px[1].r, px[2].r, px[3].r);
-        *reinterpret_cast<uchar4 *>(out_g + i4) = make_uchar4(px[0].g, px[1].g, px[2].g, px[3].g);
-        *reinterpret_cast<uchar4 *>(out_b + i4) = make_uchar4(px[0].b, px[1].b, px[2].b, px[3].b);
-        if (out_d) *reinterpret_cast<float4 *>(out_d + i4) = make_float4(px[0].depth, px[1].depth, px[2].depth, px[3].depth);
+    if (PX == 4) {
+        *reinterpret_cast<uchar4 *>(rgb + o0) = make_uchar4(px[0].r, px[PX > 1 ? 1 : 0].r, px[PX > 2 ? 2 : 0].r, px[PX > 3 ? 3 : 0].r);
+        *reinterpret_cast<uchar4 *>(rgb + o0 + P) = make_uchar4(px[0].g, px[PX > 1 ? 1 : 0].g, px[PX > 2 ? 2 : 0].g, px[PX > 3 ? 3 : 0].g);
+        *reinterpret_cast<uchar4 *>(rgb + o0 + 2 * (size_t)P) = make_uchar4(px[0].b, px[PX > 1 ? 1 : 0].b, px[PX > 2 ? 2 : 0].b, px[PX > 3 ? 3 : 0].b);
+        if (depth) *reinterpret_cast<float4 *>(depth + i0) = make_float4(px[0].depth, px[PX > 1 ? 1 : 0].depth, px[PX > 2 ? 2 : 0].depth, px[PX > 3 ? 3 : 0].depth);
     } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i4 + k < P) {
-                out_r[i4 + k] = (uint8_t)px[k].r; out_g[i4 + k] = (uint8_t)px[k].g; out_b[i4 + k] = (uint8_t)px[k].b;
-                if (out_d) out_d[i4 + k] = px[k].depth;
-            }
-        }
+        rgb[o0] = (uint8_t)px[0].r; rgb[o0 + P] = (uint8_t)px[0].g; rgb[o0 + 2 * (size_t)P] = (uint8_t)px[0].b;
+        if (depth) depth[i0] = px[0].depth;
     }
 }
 
 // ---- auxiliary kernels ----------------------------------------------------------------------
+// tri_rec[3t+2].z holds the caller's material index; .y becomes the index the shade pass uses:
+// materials[face.material] (drawing.cpp:173), with -1 / out of range mapped to the sentinel.
+__global__ void k_resolve_materials(int4 *tri_rec, uint64_t n_tris, uint32_t n_materials) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tris) return;
+    int4 r = tri_rec[3 * t + 2];
+    r.y = (r.z < 0 || (uint32_t)r.z >= n_materials) ? (int)n_materials : r.z;
+    tri_rec[3 * t + 2] = r;
+}
+
 __global__ void k_extract_tri_ids(const unsigned long long *vis, uint32_t *ids, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) ids[i] = (vis[i] == VIS_EMPTY) ? INVALID_TRI : (uint32_t)vis[i];

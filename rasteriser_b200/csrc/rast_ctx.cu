@@ -70,13 +70,18 @@ struct rast_ctx {
     rk::Scene scene{};
     DeviceBuffer d_pos, d_nrm, d_uv, d_vidx, d_attr, d_mats, d_texels;
     bool have_mesh = false;
+    bool mesh_materials_dirty = false; // material indices in d_attr still have to be clamped against n_materials
+    uint32_t n_materials = 0;
+    bool pre_normals = false;
+    int shade_px = 1; // pixels per thread of the shade pass (1 or 4)
+    rk::LightTable light_table{}; // first PARAM_LIGHTS lights, passed to the shade kernel by value
     std::vector<rast_light> lights;
 
     // view
     uint32_t band_y0 = 0, band_y1 = 0; // 0,0 = whole frame
 
     // per-call / per-batch buffers
-    DeviceBuffer d_frames, d_lights, d_rv, d_vis, d_queue, d_counters, d_aux;
+    DeviceBuffer d_frames, d_lights, d_rv, d_cn, d_vis, d_queue, d_counters, d_aux;
     DeviceBuffer d_rgb[2], d_depth[2];
     PinnedBuffer h_frames, h_lights, h_status;
     cudaEvent_t ev_params = nullptr, ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
@@ -156,6 +161,7 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     bt.frames = ctx->d_frames.as<rk::FrameParams>() + first;
     bt.n_frames = count;
     bt.rv = ctx->d_rv.as<float4>();
+    bt.cn = ctx->pre_normals ? ctx->d_cn.as<float4>() : nullptr;
     bt.vis = ctx->d_vis.as<unsigned long long>();
     bt.queue = ctx->d_queue.as<uint2>();
     bt.queue_cap = ctx->queue_cap;
@@ -168,19 +174,25 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     if (prof) cudaEventRecord(ctx->ev_pass[0], st);
     rk::k_clear<<<grid_for((n_vis + 1) / 2, 256), 256, 0, st>>>(bt.vis, n_vis, bt.counters);
     if (prof) cudaEventRecord(ctx->ev_pass[1], st);
-    if (sc.V) rk::k_vertex<<<dim3(grid_for(sc.V, 256), count), 256, 0, st>>>(sc, vw, bt);
+    if (sc.V) rk::k_vertex<<<dim3(grid_for((size_t)sc.V + (bt.cn ? sc.Nn : 0u), 256), count), 256, 0, st>>>(sc, vw, bt);
     if (prof) cudaEventRecord(ctx->ev_pass[2], st);
     if (sc.T && vw.band_pixels) rk::k_setup<<<dim3(grid_for(sc.T, 256), count), 256, 0, st>>>(sc, vw, bt);
     if (prof) cudaEventRecord(ctx->ev_pass[3], st);
-    if (sc.T && vw.band_pixels) rk::k_raster_chunks<<<ctx->raster_grid, 256, 0, st>>>(sc, vw, bt);
+    if (sc.T && vw.band_pixels) rk::k_raster_chunks<<<ctx->raster_grid, rk::RASTER_WARPS * 32, 0, st>>>(sc, vw, bt);
     if (prof) cudaEventRecord(ctx->ev_pass[4], st);
     if (vw.band_pixels) {
-        const bool vec = (vw.band_pixels % 4u == 0u) && (((uintptr_t)rgb_dev & 15u) == 0u) && (((uintptr_t)depth_dev & 15u) == 0u);
-        const dim3 grid(grid_for(((size_t)vw.band_pixels + 3) / 4, 256), count);
+        const bool vec = ctx->shade_px == 4 && (vw.W % 4u == 0u) && (((uintptr_t)rgb_dev & 15u) == 0u) && (((uintptr_t)depth_dev & 15u) == 0u);
         const rk::LightDev *lights = ctx->d_lights.as<rk::LightDev>();
-        const uint32_t nl = (uint32_t)ctx->lights.size();
-        if (vec) rk::k_resolve_shade<true><<<grid, 256, 0, st>>>(sc, vw, bt, lights, nl, rgb_dev, depth_dev);
-        else rk::k_resolve_shade<false><<<grid, 256, 0, st>>>(sc, vw, bt, lights, nl, rgb_dev, depth_dev);
+        const uint32_t rows = vw.y1 - vw.y0;
+        const dim3 grid(grid_for(vw.W, rk::SHADE_THREADS * (vec ? 4 : 1)), rows, count);
+        const rk::LightTable &lt = ctx->light_table;
+        if (vec) {
+            if (bt.cn) rk::k_resolve_shade<4, true><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev);
+            else rk::k_resolve_shade<4, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev);
+        } else {
+            if (bt.cn) rk::k_resolve_shade<1, true><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev);
+            else rk::k_resolve_shade<1, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev);
+        }
     }
     if (prof) cudaEventRecord(ctx->ev_pass[5], st);
     ctx->launches += 1 + (sc.V ? 1 : 0) + ((sc.T && vw.band_pixels) ? 2 : 0) + (vw.band_pixels ? 1 : 0);
@@ -202,11 +214,23 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
     if (!args || n == 0) return fail(ctx, RAST_EINVAL, "rast_draw: no frames");
     if (!ctx->have_mesh) return fail(ctx, RAST_ESTATE, "rast_draw: rast_upload_mesh has not been called");
     const uint32_t W = args[0].image_width, H = args[0].image_height;
-    if (W == 0 || H == 0 || W > 131072u || H > 131072u) return fail(ctx, RAST_EINVAL, "rast_draw: image size out of range");
+    if (W == 0 || H == 0 || W > 65535u || H > 65535u) return fail(ctx, RAST_EINVAL, "rast_draw: image size out of range");
     if ((uint64_t)W * H > 0xFFFFFFFFull) return fail(ctx, RAST_EINVAL, "rast_draw: more than 2^32 pixels");
     for (uint32_t i = 1; i < n; ++i)
         if (args[i].image_width != W || args[i].image_height != H) return fail(ctx, RAST_EINVAL, "rast_draw_frames: all frames must share one image size");
     RAST_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->scene.mats == nullptr) { // no materials uploaded: everything uses the white sentinel
+        int rc = rast_upload_materials(ctx, nullptr, 0);
+        if (rc != RAST_OK) return rc;
+    }
+    if (ctx->mesh_materials_dirty) {
+        // resolve material indices against the uploaded table; -1 / out of range -> sentinel (index n_materials)
+        if (ctx->scene.T) {
+            rk::k_resolve_materials<<<grid_for(ctx->scene.T, 256), 256, 0, ctx->stream>>>(ctx->d_attr.as<int4>(), ctx->scene.T, ctx->n_materials);
+            ctx->launches++;
+        }
+        ctx->mesh_materials_dirty = false;
+    }
     const rk::View vw = make_view(ctx, W, H);
     const size_t P = vw.band_pixels;
     if (P == 0) return RAST_OK; // empty band: nothing to render or copy
@@ -227,6 +251,10 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
     RAST_CUDA(ctx, ctx->d_frames.reserve((size_t)n * sizeof(rk::FrameParams)));
     RAST_CUDA(ctx, ctx->d_lights.reserve((ctx->lights.size() + 1) * sizeof(rk::LightDev)));
     RAST_CUDA(ctx, ctx->d_rv.reserve((size_t)nb * ctx->scene.V * sizeof(float4)));
+    // camera-space normals are precomputed per frame when there are few of them relative to the image;
+    // for huge meshes the shade pass transforms only the normals of winning triangles instead
+    ctx->pre_normals = (size_t)ctx->scene.Nn * 8 <= P;
+    if (ctx->pre_normals) RAST_CUDA(ctx, ctx->d_cn.reserve((size_t)nb * ctx->scene.Nn * sizeof(float4)));
     RAST_CUDA(ctx, ctx->d_vis.reserve((size_t)nb * P * 8));
     RAST_CUDA(ctx, ctx->d_queue.reserve((size_t)ctx->queue_cap * sizeof(uint2)));
     RAST_CUDA(ctx, ctx->d_counters.reserve(64));
@@ -253,7 +281,12 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
             hl[l].icg = L.intensity * L.colour[1];
             hl[l].icb = L.intensity * L.colour[2];
             hl[l].pad0 = hl[l].pad1 = 0.f;
+            if (l < rk::PARAM_LIGHTS) {
+                ctx->light_table.a[l] = make_float4(hl[l].ntx, hl[l].nty, hl[l].ntz, hl[l].icr);
+                ctx->light_table.c[l] = make_float2(hl[l].icg, hl[l].icb);
+            }
         }
+        ctx->light_table.n = (uint32_t)ctx->lights.size();
     }
     RAST_CUDA(ctx, cudaMemcpyAsync(ctx->d_frames.p, hp, (size_t)n * sizeof(rk::FrameParams), cudaMemcpyHostToDevice, ctx->stream));
     if (!ctx->lights.empty())
@@ -349,7 +382,7 @@ int rast_create(int device, rast_ctx **out) {
     if (ok) {
         int sms = 0, per_sm = 0;
         ok = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
-        ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rk::k_raster_chunks, 256, 0) == cudaSuccess;
+        ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rk::k_raster_chunks, rk::RASTER_WARPS * 32, 0) == cudaSuccess;
         ctx->raster_grid = (unsigned)(sms > 0 ? sms : 148) * (unsigned)(per_sm > 0 ? per_sm : 1);
     }
     if (!ok) {
@@ -358,6 +391,7 @@ int rast_create(int device, rast_ctx **out) {
         return RAST_ECUDA;
     }
     ctx->stream = ctx->own_stream;
+    if (const char *e = getenv("RAST_SHADE_PX")) ctx->shade_px = atoi(e) == 4 ? 4 : 1;
     *out = ctx;
     return RAST_OK;
 }
@@ -368,7 +402,7 @@ void rast_destroy(rast_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     DeviceBuffer *dev[] = {&ctx->d_pos, &ctx->d_nrm, &ctx->d_uv, &ctx->d_vidx, &ctx->d_attr, &ctx->d_mats, &ctx->d_texels, &ctx->d_frames, &ctx->d_lights,
-                           &ctx->d_rv, &ctx->d_vis, &ctx->d_queue, &ctx->d_counters, &ctx->d_aux, &ctx->d_rgb[0], &ctx->d_rgb[1], &ctx->d_depth[0], &ctx->d_depth[1]};
+                           &ctx->d_rv, &ctx->d_cn, &ctx->d_vis, &ctx->d_queue, &ctx->d_counters, &ctx->d_aux, &ctx->d_rgb[0], &ctx->d_rgb[1], &ctx->d_depth[0], &ctx->d_depth[1]};
     for (DeviceBuffer *b : dev) b->release();
     ctx->h_frames.release();
     ctx->h_lights.release();
@@ -391,7 +425,15 @@ int rast_set_stream(rast_ctx *ctx, void *cuda_stream) {
     if (!ctx) return RAST_EINVAL;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    return RAST_OK;
+}
+
+int rast_use_own_stream(rast_ctx *ctx) {
+    if (!ctx) return RAST_EINVAL;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stream = ctx->own_stream;
     return RAST_OK;
 }
 
@@ -403,35 +445,43 @@ int rast_upload_mesh(rast_ctx *ctx, const float *positions, uint32_t n_positions
     // Out-of-range indices are undefined behaviour in the reference (vector operator[], drawing.cpp:167-173);
     // here they are rejected up front.  -1 marks an absent normal / uv / material (face.h:6-13).
     std::vector<int> vidx;
-    std::vector<int4> attr;
+    std::vector<int4> rec;
     try {
         vidx.resize((size_t)n_tris * 3);
-        attr.resize((size_t)n_tris * 2);
+        rec.resize((size_t)n_tris * 3);
     } catch (...) { return fail(ctx, RAST_ENOMEM, "rast_upload_mesh: out of host memory"); }
+    // absent (-1) normals / uvs point at a sentinel entry appended after the real ones; the material index is
+    // resolved against the sentinel in rast_upload_materials' table at draw time (kept raw here, remapped below)
     for (uint64_t t = 0; t < n_tris; ++t) {
         const int32_t *f = tris + 10 * t;
+        int n[3], uvi[3];
         for (int k = 0; k < 3; ++k) {
             if (f[k] < 0 || (uint32_t)f[k] >= n_positions) return fail(ctx, RAST_EINVAL, "rast_upload_mesh: vertex index out of range");
             if (f[3 + k] >= 0 && (uint32_t)f[3 + k] >= n_normals) return fail(ctx, RAST_EINVAL, "rast_upload_mesh: normal index out of range");
             if (f[6 + k] >= 0 && (uint32_t)f[6 + k] >= n_uvs) return fail(ctx, RAST_EINVAL, "rast_upload_mesh: uv index out of range");
             vidx[(size_t)k * n_tris + t] = f[k];
+            n[k] = f[3 + k] >= 0 ? f[3 + k] : (int)n_normals;
+            uvi[k] = f[6 + k] >= 0 ? f[6 + k] : (int)n_uvs;
         }
-        attr[2 * t] = make_int4(f[3], f[4], f[5], f[9]);
-        attr[2 * t + 1] = make_int4(f[6], f[7], f[8], 0);
+        rec[3 * t] = make_int4(f[0], f[1], f[2], n[0]);
+        rec[3 * t + 1] = make_int4(n[1], n[2], uvi[0], uvi[1]);
+        rec[3 * t + 2] = make_int4(uvi[2], f[9], f[9], 0); // .z keeps the caller's material index, .y is resolved at draw time
     }
     RAST_CUDA(ctx, cudaSetDevice(ctx->device));
     RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     RAST_CUDA(ctx, ctx->d_pos.reserve((size_t)n_positions * 12));
-    RAST_CUDA(ctx, ctx->d_nrm.reserve((size_t)n_normals * 12));
-    RAST_CUDA(ctx, ctx->d_uv.reserve((size_t)n_uvs * 8));
+    RAST_CUDA(ctx, ctx->d_nrm.reserve(((size_t)n_normals + 1) * 12));
+    RAST_CUDA(ctx, ctx->d_uv.reserve(((size_t)n_uvs + 1) * 8));
+    RAST_CUDA(ctx, cudaMemset(ctx->d_nrm.as<float>() + (size_t)n_normals * 3, 0, 12)); // sentinel: zero normal
+    RAST_CUDA(ctx, cudaMemset(ctx->d_uv.as<float>() + (size_t)n_uvs * 2, 0, 8));       // sentinel: uv (0,0)
     RAST_CUDA(ctx, ctx->d_vidx.reserve(vidx.size() * 4));
-    RAST_CUDA(ctx, ctx->d_attr.reserve(attr.size() * 16));
+    RAST_CUDA(ctx, ctx->d_attr.reserve(rec.size() * 16));
     if (n_positions) RAST_CUDA(ctx, cudaMemcpy(ctx->d_pos.p, positions, (size_t)n_positions * 12, cudaMemcpyHostToDevice));
     if (n_normals) RAST_CUDA(ctx, cudaMemcpy(ctx->d_nrm.p, normals, (size_t)n_normals * 12, cudaMemcpyHostToDevice));
     if (n_uvs) RAST_CUDA(ctx, cudaMemcpy(ctx->d_uv.p, uvs, (size_t)n_uvs * 8, cudaMemcpyHostToDevice));
     if (n_tris) {
         RAST_CUDA(ctx, cudaMemcpy(ctx->d_vidx.p, vidx.data(), vidx.size() * 4, cudaMemcpyHostToDevice));
-        RAST_CUDA(ctx, cudaMemcpy(ctx->d_attr.p, attr.data(), attr.size() * 16, cudaMemcpyHostToDevice));
+        RAST_CUDA(ctx, cudaMemcpy(ctx->d_attr.p, rec.data(), rec.size() * 16, cudaMemcpyHostToDevice));
     }
     rk::Scene &s = ctx->scene;
     s.pos = ctx->d_pos.as<float>();
@@ -440,11 +490,12 @@ int rast_upload_mesh(rast_ctx *ctx, const float *positions, uint32_t n_positions
     s.vidx0 = ctx->d_vidx.as<int>();
     s.vidx1 = s.vidx0 + n_tris;
     s.vidx2 = s.vidx1 + n_tris;
-    s.attr = ctx->d_attr.as<int4>();
+    s.tri_rec = ctx->d_attr.as<int4>();
     s.V = n_positions;
-    s.Nn = n_normals;
-    s.Nuv = n_uvs;
+    s.Nn = n_normals + 1;
+    s.Nuv = n_uvs + 1;
     s.T = n_tris;
+    ctx->mesh_materials_dirty = true;
     ctx->have_mesh = true;
     ctx->have_frame = false;
     return RAST_OK;
@@ -453,8 +504,13 @@ int rast_upload_mesh(rast_ctx *ctx, const float *positions, uint32_t n_positions
 int rast_upload_materials(rast_ctx *ctx, const rast_material *materials, uint32_t n_materials) {
     if (!ctx) return RAST_EINVAL;
     if (n_materials && !materials) return fail(ctx, RAST_EINVAL, "rast_upload_materials: null array");
-    std::vector<rk::MaterialDev> md(n_materials);
+    std::vector<rk::MaterialDev> md((size_t)n_materials + 1);
     size_t texel_total = 0;
+    {   // sentinel for material index -1 / out of range: untextured white (renderer.cpp:49)
+        rk::MaterialDev &d = md[n_materials];
+        d.kd[0] = d.kd[1] = d.kd[2] = 1.f;
+        d.has_texture = 0; d.tex_w = d.tex_h = 0; d.texel_offset = 0;
+    }
     for (uint32_t i = 0; i < n_materials; ++i) {
         const rast_material &m = materials[i];
         md[i].kd[0] = m.kd[0]; md[i].kd[1] = m.kd[1]; md[i].kd[2] = m.kd[2];
@@ -469,16 +525,18 @@ int rast_upload_materials(rast_ctx *ctx, const rast_material *materials, uint32_
     }
     RAST_CUDA(ctx, cudaSetDevice(ctx->device));
     RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    RAST_CUDA(ctx, ctx->d_mats.reserve((size_t)n_materials * sizeof(rk::MaterialDev)));
+    RAST_CUDA(ctx, ctx->d_mats.reserve(md.size() * sizeof(rk::MaterialDev)));
     RAST_CUDA(ctx, ctx->d_texels.reserve(texel_total * 4));
-    if (n_materials) RAST_CUDA(ctx, cudaMemcpy(ctx->d_mats.p, md.data(), md.size() * sizeof(rk::MaterialDev), cudaMemcpyHostToDevice));
+    RAST_CUDA(ctx, cudaMemcpy(ctx->d_mats.p, md.data(), md.size() * sizeof(rk::MaterialDev), cudaMemcpyHostToDevice));
     for (uint32_t i = 0; i < n_materials; ++i)
         if (materials[i].has_texture)
             RAST_CUDA(ctx, cudaMemcpy(ctx->d_texels.as<float>() + md[i].texel_offset, materials[i].texels,
                                       (size_t)3 * materials[i].tex_w * materials[i].tex_h * 4, cudaMemcpyHostToDevice));
     ctx->scene.mats = ctx->d_mats.as<rk::MaterialDev>();
     ctx->scene.texels = ctx->d_texels.as<float>();
-    ctx->scene.M = n_materials;
+    ctx->scene.M = n_materials + 1;
+    ctx->n_materials = n_materials;
+    ctx->mesh_materials_dirty = true;
     return RAST_OK;
 }
 

@@ -156,7 +156,7 @@ def test_batched_spin_frames_equal_single_frames(renderers):
 def test_draw_frame_function_mirrors_reference_signature():
     """api.draw_frame(vertices, faces, normals, uvs, lights, materials, args, frame, depth)."""
     sc = S.scene("plane")
-    lights = orc.lights_array(S.lights("normalmap"))
+    lights = orc.lights_array(S.lights("threepoint"))
     a = api.Args(96, 64, tait_bryan_angles=(0.9, 0.3, 0.0))
     frame, depth = np.zeros((3, 64, 96), np.uint8), np.ones((64, 96), np.float32)
     api.draw_frame(sc.positions, sc.tris, sc.normals, sc.uvs, lights, sc.materials, a, frame, depth)
