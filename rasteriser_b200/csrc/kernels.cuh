@@ -85,12 +85,14 @@ __device__ __forceinline__ uint32_t depth_key(float z) {
 struct TriSetup {
     float x0, y0, x1, y1, x2, y2;
     float z0, z1, z2;
-    float d12x, d12y, d20x, d20y, d01x, d01y; // the pixel-invariant differences of edge() (drawing.cpp:38)
-    float area;                               // edge(v2; v0, v1) (drawing.cpp:46)
-    uint32_t flip;                            // sign bit of area
+    float d12x, d12y, d20x, d20y, d01x, d01y; // the pixel-invariant differences of edge() (drawing.cpp:38), times sign(area)
+    float area;                               // |edge(v2; v0, v1)| (drawing.cpp:46)
     bool literal;                             // area is 0, inf or NaN: no sign shortcut
 };
 
+// The six differences and the area are multiplied by sign(area).  Negation is exact and every IEEE
+// operation is sign-symmetric, so each edge value becomes exactly sign(area) * e_k and each quotient
+// e_k / area keeps its bits; what changes is that "inside" now simply reads e_k >= 0.
 __device__ __forceinline__ void tri_setup(TriSetup &s, const float4 &v0, const float4 &v1, const float4 &v2) {
     s.x0 = v0.x; s.y0 = v0.y; s.z0 = v0.z;
     s.x1 = v1.x; s.y1 = v1.y; s.z1 = v1.z;
@@ -99,8 +101,11 @@ __device__ __forceinline__ void tri_setup(TriSetup &s, const float4 &v0, const f
     s.d20x = exact::sub(v0.x, v2.x); s.d20y = exact::sub(v0.y, v2.y);
     s.d01x = exact::sub(v1.x, v0.x); s.d01y = exact::sub(v1.y, v0.y);
     s.area = exact::sub(exact::mul(s.d01x, exact::sub(v2.y, v0.y)), exact::mul(s.d01y, exact::sub(v2.x, v0.x)));
-    s.flip = __float_as_uint(s.area) & 0x80000000u;
     s.literal = !(fabsf(s.area) > 0.f && fabsf(s.area) < __int_as_float(0x7f800000));
+    if (!s.literal && s.area < 0.f) {
+        s.d12x = -s.d12x; s.d12y = -s.d12y; s.d20x = -s.d20x; s.d20y = -s.d20y; s.d01x = -s.d01x; s.d01y = -s.d01y;
+        s.area = -s.area;
+    }
 }
 
 // signed_area_2d (geometry.cpp:76-83), left to right
@@ -141,17 +146,14 @@ __device__ __forceinline__ void edges(const TriSetup &s, float px, float py, flo
     e2 = sub(mul(s.d01x, sub(py, s.y0)), mul(s.d01y, sub(px, s.x0)));
 }
 
-// Cheap superset of the inside test.  The reference tests e_i/area >= 0 (drawing.cpp:46-48,111).
-// For finite non-zero area the quotient is >= 0 (counting -0) iff e_i has area's sign, is zero, or
-// the quotient underflows to -0; underflow needs |e_i| <= 2^-150 * |area| < 2^-22.  So
-// "(e_i with area's sign folded in) >= -2^-22 for all i" never rejects a pixel the exact test
-// accepts; survivors take the literal divisions (needed for depth anyway).
+// Cheap superset of the inside test.  The reference tests e_k/area >= 0 (drawing.cpp:46-48,111).
+// For finite non-zero area the quotient is >= 0 (counting -0) iff e_k has area's sign, is zero, or
+// the quotient underflows to -0; underflow needs |e_k| <= 2^-150 * |area| < 2^-22.  With the setup's
+// sign folding that is "e_k >= -2^-22 for all k": it never rejects a pixel the exact test accepts
+// (fminf drops a NaN operand, which only widens the superset); survivors take the literal divisions,
+// which the depth needs anyway.
 __device__ __forceinline__ bool candidate(const TriSetup &s, float e0, float e1, float e2) {
-    if (s.literal) return true;
-    const float t0 = __uint_as_float(__float_as_uint(e0) ^ s.flip);
-    const float t1 = __uint_as_float(__float_as_uint(e1) ^ s.flip);
-    const float t2 = __uint_as_float(__float_as_uint(e2) ^ s.flip);
-    return (t0 >= -EDGE_SLACK) && (t1 >= -EDGE_SLACK) && (t2 >= -EDGE_SLACK);
+    return s.literal || fminf(fminf(e0, e1), e2) >= -EDGE_SLACK;
 }
 
 // barycentric + inside + depth (drawing.cpp:41-49,111,115-119).  True iff the fragment is inside
@@ -177,9 +179,10 @@ __device__ __forceinline__ void test_and_commit(const TriSetup &s, uint32_t x, u
 
 // ---- K0: clear ------------------------------------------------------------------------------
 // renderer.cpp:85-86 / :107-108 (frame = 0, depth = 1.0f) become "no triangle" in the visibility buffer.
-__global__ void k_clear(unsigned long long *vis, size_t n, unsigned long long *counters) {
+// Only needed for slots that are not known to be empty: the shade pass hands every key it consumes
+// back as VIS_EMPTY, so in steady state the buffer is already clear when the next batch starts.
+__global__ void k_clear(unsigned long long *vis, size_t n) {
     const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
-    if (blockIdx.x == 0 && threadIdx.x < 4) counters[threadIdx.x] = 0ull;
     if (i + 1 < n) {
         *reinterpret_cast<ulonglong2 *>(vis + i) = make_ulonglong2(VIS_EMPTY, VIS_EMPTY);
     } else if (i < n) {
@@ -193,6 +196,7 @@ __global__ void k_clear(unsigned long long *vis, size_t n, unsigned long long *c
 __global__ void __launch_bounds__(256) k_vertex(Scene sc, View vw, Batch bt) {
     __shared__ float cam[16], nm[16];
     const uint32_t f = blockIdx.y;
+    if (blockIdx.x == 0 && f == 0 && threadIdx.x >= 32 && threadIdx.x < 36) bt.counters[threadIdx.x - 32] = 0ull; // work queue reset
     if (threadIdx.x < 16) cam[threadIdx.x] = bt.frames[f].camera[threadIdx.x];
     else if (threadIdx.x < 32) nm[threadIdx.x - 16] = bt.frames[f].normal_m[threadIdx.x - 16];
     __syncthreads();
@@ -292,6 +296,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_chunks(Scene sc, V
         {
             uint32_t tri = INVALID_TRI, rect0 = 0, rect1 = 0, f = 0;
             TriSetup s = {};
+            s.literal = true;
             if (lane < n_items) {
                 const uint2 item = bt.queue[base + lane];
                 tri = item.x;
@@ -311,7 +316,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_chunks(Scene sc, V
             const float fl[16] = {s.x0, s.y0, s.x1, s.y1, s.x2, s.y2, s.z0, s.z1, s.z2, s.d12x, s.d12y, s.d20x, s.d20y, s.d01x, s.d01y, s.area};
 #pragma unroll
             for (int k = 0; k < 16; ++k) stg.w[k][lane] = __float_as_uint(fl[k]);
-            stg.w[16][lane] = s.flip | (s.literal ? 1u : 0u);
+            stg.w[16][lane] = s.literal ? 1u : 0u;
             stg.w[17][lane] = rect0;
             stg.w[18][lane] = rect1;
             stg.w[19][lane] = tri;
@@ -332,9 +337,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_chunks(Scene sc, V
             s.d20x = __uint_as_float(stg.w[11][it]); s.d20y = __uint_as_float(stg.w[12][it]);
             s.d01x = __uint_as_float(stg.w[13][it]); s.d01y = __uint_as_float(stg.w[14][it]);
             s.area = __uint_as_float(stg.w[15][it]);
-            const uint32_t fw = stg.w[16][it];
-            s.flip = fw & 0x80000000u;
-            s.literal = (fw & 1u) != 0u;
+            s.literal = stg.w[16][it] != 0u;
             const uint32_t rect0 = stg.w[17][it], rect1 = stg.w[18][it];
             const uint32_t rx0 = rect0 & 0xFFFFu, ry0 = rect0 >> 16, rx1 = rect1 & 0xFFFFu, ry1 = rect1 >> 16;
             unsigned long long *vis = bt.vis + (size_t)stg.w[20][it] * vw.band_pixels;
@@ -427,8 +430,9 @@ __device__ __forceinline__ Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t
                                               const LightTable &lt, const LightDev *__restrict__ lights) {
     using namespace exact;
     Shaded out;
-    const int4 *rec = sc.tri_rec + 3 * (size_t)tri;
-    const int4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
+    const uint4 *rec = reinterpret_cast<const uint4 *>(sc.tri_rec) + 3 * (size_t)tri; // indices are non-negative after upload
+    const uint4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
+    const uint2 r2 = __ldg(reinterpret_cast<const uint2 *>(rec + 2));
     const float4 v0 = rv[r0.x], v1 = rv[r0.y], v2 = rv[r0.z];
 
     // vertex normals in camera space (transform_direction, geometry.cpp:35-42,97-108)
@@ -505,54 +509,90 @@ __device__ __forceinline__ Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t
     return out;
 }
 
-// Grid: x = chunks of SHADE_THREADS * PX pixels along a row, y = row of the band, z = frame of the batch,
-// so no thread divides to find its pixel.  PX = 1: a warp reads 256 B of keys and writes one full 32-byte
-// sector per colour plane plus 128 B of depth.  PX = 4 (W % 4 == 0, 16-byte aligned outputs): keys in as
-// 2 x 16 B, colour out as one uchar4 per plane, depth as one float4 (CImg planar layout, CImg.h:11715-11721).
+// Grid: x = segments of SHADE_THREADS * PX * SHADE_GROUPS pixels along a row, y = row of the band,
+// z = frame of the batch -- no thread divides to find its pixel.  A thread owns SHADE_GROUPS groups of PX
+// adjacent pixels, the groups SHADE_THREADS * PX pixels apart.  Phase 1 issues the key loads of ALL its
+// groups and keeps one coverage bit per pixel: with most of a frame background, a warp that fetched only
+// 256 B of keys and then waited for DRAM left the memory system idle (measured: long-scoreboard bound at
+// 40 warps/SM).  Phase 2 walks the groups; a covered group re-reads its keys (L1 hits) and shades.
+// PX = 4 (W % 4 == 0, 16-byte aligned outputs): keys in as 2 x 16 B, colour out as one uchar4 per plane,
+// depth as one float4 (CImg planar layout, CImg.h:11715-11721).  PX = 1: scalar loads/stores, any W.
 constexpr int SHADE_THREADS = 128;
+constexpr int SHADE_GROUPS = 4;
+
+template <int PX>
+__device__ __forceinline__ void load_keys(const unsigned long long *p, unsigned long long (&keys)[PX]) {
+    if (PX == 4) {
+        const ulonglong2 k01 = *reinterpret_cast<const ulonglong2 *>(p), k23 = *reinterpret_cast<const ulonglong2 *>(p + 2);
+        keys[0] = k01.x; keys[PX > 1 ? 1 : 0] = k01.y; keys[PX > 2 ? 2 : 0] = k23.x; keys[PX > 3 ? 3 : 0] = k23.y;
+    } else {
+        keys[0] = *p;
+    }
+}
 
 template <int PX, bool PRE_NORMALS>
 __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View vw, Batch bt, const __grid_constant__ LightTable lt,
-                                                                 const LightDev *__restrict__ lights, uint8_t *__restrict__ rgb, float *__restrict__ depth) {
-    const uint32_t x0 = (blockIdx.x * SHADE_THREADS + threadIdx.x) * PX;
-    if (x0 >= vw.W) return;
+                                                                 const LightDev *__restrict__ lights, uint8_t *__restrict__ rgb, float *__restrict__ depth,
+                                                                 uint32_t keep_frame) {
+    constexpr uint32_t STRIDE = SHADE_THREADS * PX;
+    const uint32_t xb = blockIdx.x * (STRIDE * SHADE_GROUPS) + threadIdx.x * PX;
     const uint32_t row = blockIdx.y, f = blockIdx.z;
     const uint32_t P = vw.band_pixels;
-    const size_t i0 = (size_t)f * P + (size_t)row * vw.W + x0;          // into vis / depth
-    const size_t o0 = (size_t)f * 3 * P + (size_t)row * vw.W + x0;      // into the R plane of frame f
-    const unsigned long long *vis = bt.vis + i0;
+    const size_t i0 = (size_t)f * P + (size_t)row * vw.W + xb;          // into vis / depth
+    const size_t o0 = (size_t)f * 3 * P + (size_t)row * vw.W + xb;      // into the R plane of frame f
+    unsigned long long *vis = bt.vis + i0;
+    const bool reset = f != keep_frame; // hand the keys back as VIS_EMPTY (the next batch then needs no clear pass)
 
-    unsigned long long keys[PX];
-    if (PX == 4) {
-        const ulonglong2 k01 = *reinterpret_cast<const ulonglong2 *>(vis), k23 = *reinterpret_cast<const ulonglong2 *>(vis + 2);
-        keys[0] = k01.x; keys[PX > 1 ? 1 : 0] = k01.y; keys[PX > 2 ? 2 : 0] = k23.x; keys[PX > 3 ? 3 : 0] = k23.y;
-    } else {
-        keys[0] = *vis;
-    }
-    bool any = false;
+    // phase 1: all key loads in flight at once; one coverage bit per pixel
+    uint32_t covered = 0;
 #pragma unroll
-    for (int k = 0; k < PX; ++k) any |= keys[k] != VIS_EMPTY;
+    for (int g = 0; g < SHADE_GROUPS; ++g) {
+        if (xb + g * STRIDE < vw.W) {
+            unsigned long long keys[PX];
+            load_keys<PX>(vis + g * STRIDE, keys);
+#pragma unroll
+            for (int k = 0; k < PX; ++k) covered |= (keys[k] != VIS_EMPTY ? 1u : 0u) << (g * PX + k);
+        }
+    }
 
-    Shaded px[PX];
+    // phase 2
+    const float4 *rv = bt.rv + (size_t)f * sc.V;
+    const float4 *cn = PRE_NORMALS ? bt.cn + (size_t)f * sc.Nn : nullptr;
+    const FrameParams *fp = bt.frames + f;
+#pragma unroll 1
+    for (uint32_t g = 0; g < SHADE_GROUPS; ++g) {
+        const uint32_t x0 = xb + g * STRIDE;
+        if (x0 >= vw.W) break;
+        Shaded px[PX];
 #pragma unroll
-    for (int k = 0; k < PX; ++k) { px[k].r = px[k].g = px[k].b = 0u; px[k].depth = 1.0f; } // renderer.cpp:85-86
-    if (any) {
-        const float4 *rv = bt.rv + (size_t)f * sc.V;
-        const float4 *cn = PRE_NORMALS ? bt.cn + (size_t)f * sc.Nn : nullptr;
-        const FrameParams *fp = bt.frames + f;
-        const bool cw = __ldg(&fp->wind_clockwise) != 0u;
+        for (int k = 0; k < PX; ++k) { px[k].r = px[k].g = px[k].b = 0u; px[k].depth = 1.0f; } // renderer.cpp:85-86
+        const uint32_t cov = (covered >> (g * PX)) & ((1u << PX) - 1u);
+        if (cov) {
+            unsigned long long keys[PX];
+            load_keys<PX>(vis + g * STRIDE, keys);
+            const bool cw = __ldg(&fp->wind_clockwise) != 0u;
 #pragma unroll
-        for (int k = 0; k < PX; ++k)
-            if (keys[k] != VIS_EMPTY) px[k] = shade_pixel<PRE_NORMALS>((uint32_t)keys[k], x0 + k, vw.y0 + row, sc, rv, cn, fp->normal_m, cw, lt, lights);
-    }
-    if (PX == 4) {
-        *reinterpret_cast<uchar4 *>(rgb + o0) = make_uchar4(px[0].r, px[PX > 1 ? 1 : 0].r, px[PX > 2 ? 2 : 0].r, px[PX > 3 ? 3 : 0].r);
-        *reinterpret_cast<uchar4 *>(rgb + o0 + P) = make_uchar4(px[0].g, px[PX > 1 ? 1 : 0].g, px[PX > 2 ? 2 : 0].g, px[PX > 3 ? 3 : 0].g);
-        *reinterpret_cast<uchar4 *>(rgb + o0 + 2 * (size_t)P) = make_uchar4(px[0].b, px[PX > 1 ? 1 : 0].b, px[PX > 2 ? 2 : 0].b, px[PX > 3 ? 3 : 0].b);
-        if (depth) *reinterpret_cast<float4 *>(depth + i0) = make_float4(px[0].depth, px[PX > 1 ? 1 : 0].depth, px[PX > 2 ? 2 : 0].depth, px[PX > 3 ? 3 : 0].depth);
-    } else {
-        rgb[o0] = (uint8_t)px[0].r; rgb[o0 + P] = (uint8_t)px[0].g; rgb[o0 + 2 * (size_t)P] = (uint8_t)px[0].b;
-        if (depth) depth[i0] = px[0].depth;
+            for (int k = 0; k < PX; ++k)
+                if (cov & (1u << k)) px[k] = shade_pixel<PRE_NORMALS>((uint32_t)keys[k], x0 + k, vw.y0 + row, sc, rv, cn, fp->normal_m, cw, lt, lights);
+            if (reset) {
+                if (PX == 4) {
+                    *reinterpret_cast<ulonglong2 *>(vis + g * STRIDE) = make_ulonglong2(VIS_EMPTY, VIS_EMPTY);
+                    *reinterpret_cast<ulonglong2 *>(vis + g * STRIDE + 2) = make_ulonglong2(VIS_EMPTY, VIS_EMPTY);
+                } else {
+                    vis[g * STRIDE] = VIS_EMPTY;
+                }
+            }
+        }
+        const size_t o = o0 + g * STRIDE, i = i0 + g * STRIDE;
+        if (PX == 4) {
+            *reinterpret_cast<uchar4 *>(rgb + o) = make_uchar4(px[0].r, px[PX > 1 ? 1 : 0].r, px[PX > 2 ? 2 : 0].r, px[PX > 3 ? 3 : 0].r);
+            *reinterpret_cast<uchar4 *>(rgb + o + P) = make_uchar4(px[0].g, px[PX > 1 ? 1 : 0].g, px[PX > 2 ? 2 : 0].g, px[PX > 3 ? 3 : 0].g);
+            *reinterpret_cast<uchar4 *>(rgb + o + 2 * (size_t)P) = make_uchar4(px[0].b, px[PX > 1 ? 1 : 0].b, px[PX > 2 ? 2 : 0].b, px[PX > 3 ? 3 : 0].b);
+            if (depth) *reinterpret_cast<float4 *>(depth + i) = make_float4(px[0].depth, px[PX > 1 ? 1 : 0].depth, px[PX > 2 ? 2 : 0].depth, px[PX > 3 ? 3 : 0].depth);
+        } else {
+            rgb[o] = (uint8_t)px[0].r; rgb[o + P] = (uint8_t)px[0].g; rgb[o + 2 * (size_t)P] = (uint8_t)px[0].b;
+            if (depth) depth[i] = px[0].depth;
+        }
     }
 }
 

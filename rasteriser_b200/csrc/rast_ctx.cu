@@ -73,7 +73,7 @@ struct rast_ctx {
     bool mesh_materials_dirty = false; // material indices in d_attr still have to be clamped against n_materials
     uint32_t n_materials = 0;
     bool pre_normals = false;
-    int shade_px = 1; // pixels per thread of the shade pass (1 or 4)
+    int shade_px = 1; // adjacent pixels per group in the shade pass: 1 measured faster than 4 (uchar4/float4 stores) on B200
     rk::LightTable light_table{}; // first PARAM_LIGHTS lights, passed to the shade kernel by value
     std::vector<rast_light> lights;
 
@@ -87,6 +87,10 @@ struct rast_ctx {
     cudaEvent_t ev_params = nullptr, ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     bool copied_pending[2] = {false, false};
     uint32_t queue_cap = QUEUE_MIN;
+    // visibility-buffer bookkeeping: slots [0, vis_clean_slots) of band size vis_clean_pixels hold VIS_EMPTY,
+    // except vis_dirty_slot (the last frame of the previous call, kept for inspection)
+    uint32_t vis_clean_slots = 0, vis_clean_pixels = 0;
+    int vis_dirty_slot = -1;
 
     // most recent frame (for rast_read_triangle_ids / rast_depth_to_u8 / stats)
     rk::View last_view{};
@@ -156,7 +160,7 @@ uint32_t batch_capacity(const rast_ctx *ctx, const rk::View &vw) {
 }
 
 // Launch the five passes for frames [first, first+count) of the uploaded parameter block.
-int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count, uint8_t *rgb_dev, float *depth_dev) {
+int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count, uint8_t *rgb_dev, float *depth_dev, uint32_t keep_frame) {
     rk::Batch bt;
     bt.frames = ctx->d_frames.as<rk::FrameParams>() + first;
     bt.n_frames = count;
@@ -172,7 +176,22 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     const size_t n_vis = (size_t)count * vw.band_pixels;
 
     if (prof) cudaEventRecord(ctx->ev_pass[0], st);
-    rk::k_clear<<<grid_for((n_vis + 1) / 2, 256), 256, 0, st>>>(bt.vis, n_vis, bt.counters);
+    // Visibility slots known to be empty (handed back by the previous shade pass) are not cleared again.
+    uint32_t n_clear_launches = 0;
+    if (ctx->vis_clean_pixels != vw.band_pixels) { ctx->vis_clean_slots = 0; ctx->vis_dirty_slot = -1; }
+    if (ctx->vis_dirty_slot >= 0 && (uint32_t)ctx->vis_dirty_slot < ctx->vis_clean_slots) { // only one dirty slot is tracked: settle it now
+        rk::k_clear<<<grid_for(((size_t)vw.band_pixels + 1) / 2, 256), 256, 0, st>>>(bt.vis + (size_t)ctx->vis_dirty_slot * vw.band_pixels, vw.band_pixels);
+        ctx->vis_dirty_slot = -1;
+        n_clear_launches++;
+    }
+    if (count > ctx->vis_clean_slots) {
+        const size_t from = (size_t)ctx->vis_clean_slots * vw.band_pixels;
+        rk::k_clear<<<grid_for((n_vis - from + 1) / 2, 256), 256, 0, st>>>(bt.vis + from, n_vis - from);
+        if (ctx->vis_dirty_slot >= (int)ctx->vis_clean_slots) ctx->vis_dirty_slot = -1;
+        ctx->vis_clean_slots = count;
+        n_clear_launches++;
+    }
+    ctx->vis_clean_pixels = vw.band_pixels;
     if (prof) cudaEventRecord(ctx->ev_pass[1], st);
     if (sc.V) rk::k_vertex<<<dim3(grid_for((size_t)sc.V + (bt.cn ? sc.Nn : 0u), 256), count), 256, 0, st>>>(sc, vw, bt);
     if (prof) cudaEventRecord(ctx->ev_pass[2], st);
@@ -184,18 +203,19 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
         const bool vec = ctx->shade_px == 4 && (vw.W % 4u == 0u) && (((uintptr_t)rgb_dev & 15u) == 0u) && (((uintptr_t)depth_dev & 15u) == 0u);
         const rk::LightDev *lights = ctx->d_lights.as<rk::LightDev>();
         const uint32_t rows = vw.y1 - vw.y0;
-        const dim3 grid(grid_for(vw.W, rk::SHADE_THREADS * (vec ? 4 : 1)), rows, count);
+        const dim3 grid(grid_for(vw.W, rk::SHADE_THREADS * rk::SHADE_GROUPS * (vec ? 4 : 1)), rows, count);
         const rk::LightTable &lt = ctx->light_table;
         if (vec) {
-            if (bt.cn) rk::k_resolve_shade<4, true><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev);
-            else rk::k_resolve_shade<4, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev);
+            if (bt.cn) rk::k_resolve_shade<4, true><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
+            else rk::k_resolve_shade<4, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
         } else {
-            if (bt.cn) rk::k_resolve_shade<1, true><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev);
-            else rk::k_resolve_shade<1, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev);
+            if (bt.cn) rk::k_resolve_shade<1, true><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
+            else rk::k_resolve_shade<1, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
         }
     }
     if (prof) cudaEventRecord(ctx->ev_pass[5], st);
-    ctx->launches += 1 + (sc.V ? 1 : 0) + ((sc.T && vw.band_pixels) ? 2 : 0) + (vw.band_pixels ? 1 : 0);
+    ctx->launches += n_clear_launches + (sc.V ? 1 : 0) + ((sc.T && vw.band_pixels) ? 2 : 0) + (vw.band_pixels ? 1 : 0);
+    if (keep_frame < count) ctx->vis_dirty_slot = (int)keep_frame; // that slot still holds its keys (rast_read_triangle_ids)
     RAST_CUDA(ctx, cudaGetLastError());
     if (prof) {
         RAST_CUDA(ctx, cudaEventSynchronize(ctx->ev_pass[5]));
@@ -255,6 +275,7 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
     // for huge meshes the shade pass transforms only the normals of winning triangles instead
     ctx->pre_normals = (size_t)ctx->scene.Nn * 8 <= P;
     if (ctx->pre_normals) RAST_CUDA(ctx, ctx->d_cn.reserve((size_t)nb * ctx->scene.Nn * sizeof(float4)));
+    if ((size_t)nb * P * 8 > ctx->d_vis.bytes) { ctx->vis_clean_slots = 0; ctx->vis_dirty_slot = -1; }
     RAST_CUDA(ctx, ctx->d_vis.reserve((size_t)nb * P * 8));
     RAST_CUDA(ctx, ctx->d_queue.reserve((size_t)ctx->queue_cap * sizeof(uint2)));
     RAST_CUDA(ctx, ctx->d_counters.reserve(64));
@@ -317,7 +338,9 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
             RAST_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0));
             ctx->copied_pending[slot] = false;
         }
-        int rc = launch_batch(ctx, vw, first, count, rgb_dst, depth_dst);
+        // the last frame of the call keeps its visibility keys for rast_read_triangle_ids / rast_get_stats
+        const uint32_t keep_frame = (first + count == n) ? count - 1 : 0xFFFFFFFFu;
+        int rc = launch_batch(ctx, vw, first, count, rgb_dst, depth_dst, keep_frame);
         if (rc != RAST_OK) return rc;
 
         ctx->last_view = vw;
