@@ -36,18 +36,13 @@ UNIT = "frames/s"
 # workloads
 # ------------------------------------------------------------------------------------------------
 def load_suzanne():
-    """Suzanne as the reference's loader reads it (arrays committed in tests/golden/scenes.npz), with the
-    texture normalised like Material's constructor (material.h:22): (t - min) / (max - min) in fp32."""
-    from PIL import Image
-    z = np.load(os.path.join(ROOT, "tests", "golden", "scenes.npz"))
-    img = np.asarray(Image.open(os.path.join(ROOT, "tests", "data", "SuzanneTex.png")).convert("RGB"), np.uint8)
-    t = np.ascontiguousarray(img.transpose(2, 0, 1).astype(np.float32))
-    m, M = np.float32(t.min()), np.float32(t.max())
-    if not (m == 0 and M == 1):
-        t = ((t - m) / (M - m) * np.float32(1.0) + np.float32(0.0)).astype(np.float32)
-    lights = np.loadtxt(os.path.join(ROOT, "tests", "data", "threepoint.csv"), delimiter=",", dtype=np.float32).reshape(-1, 7)
-    return dict(pos=z["suzanne_pos"], nrm=z["suzanne_nrm"], uv=z["suzanne_uv"], tris=z["suzanne_tris"],
-                materials=[dict(kd=(0.64, 0.64, 0.64), texels=t)], lights=lights)
+    """Suzanne + threepoint.csv through the product's own C++ loaders (rasteriser_b200/host/loaders.cpp:
+    OBJ / MTL parsing with tinyobjloader's semantics, PNG texture decode + normalize(0,1))."""
+    from rasteriser_b200 import hostio
+    data = os.path.join(ROOT, "tests", "data")
+    m, _ = hostio.load_obj(os.path.join(data, "Suzanne.obj"), data + "/")
+    m["lights"] = hostio.load_lights(os.path.join(data, "threepoint.csv"))
+    return m
 
 
 def make_workload(name):

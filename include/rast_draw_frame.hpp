@@ -1,0 +1,106 @@
+// rast_draw_frame.hpp -- C++ shim with the reference's draw_frame signature on top of the C ABI.
+//
+// The reference's only entry into the frame path is (headers/drawing.h:16-18):
+//
+//   void draw_frame(const std::vector<glm::vec3>& model_vertices, const std::vector<Triangle>& faces,
+//                   const std::vector<glm::vec3>& model_vertnormals, const std::vector<glm::vec2>& vertuvs,
+//                   std::vector<Light>& lights, const std::vector<Material>& materials, const Args& arguments,
+//                   cimg_library::CImg<unsigned char>* frame_buffer, cimg_library::CImg<float>* depth_buffer);
+//
+// rast::draw_frame below takes the same arguments in the same order, as templates, so it binds to the
+// reference's own types (glm::vec3 = 3 packed floats, struct Triangle = 10 ints, CImg<T>::data()) and to
+// this repository's host types alike.  Materials need an adapter because the reference's class keeps its
+// fields private: pass anything with kd / has_texture / tex_w / tex_h / texels members (host::MaterialData)
+// -- INTEGRATION.md shows the three accessor lines to add to headers/material.h.
+//
+// Semantics: the scene is uploaded on the first call (and again if the vectors change size or address),
+// the finished frame and depth overwrite the caller's buffers (the reference's callers always pass cleared
+// buffers: renderer.cpp:85-86,107-108), lights[i].trans_dir is written like Light::transform
+// (geometry.cpp:126).  Errors throw std::runtime_error on the C++ side of the ABI.
+#pragma once
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "rast.h"
+
+namespace rast {
+
+class Session {
+public:
+    explicit Session(int device = 0) {
+        if (rast_create(device, &ctx_) != RAST_OK) throw std::runtime_error(std::string("rast_create: ") + rast_last_error(nullptr));
+    }
+    ~Session() { rast_destroy(ctx_); }
+    Session(const Session &) = delete;
+    Session &operator=(const Session &) = delete;
+    rast_ctx *ctx() const { return ctx_; }
+    void check(int rc, const char *what) const {
+        if (rc != RAST_OK) throw std::runtime_error(std::string(what) + ": " + rast_last_error(ctx_));
+    }
+
+    template <class Vec3s, class Faces, class Vec2s, class Materials>
+    void upload(const Vec3s &vertices, const Faces &faces, const Vec3s &normals, const Vec2s &uvs, const Materials &materials) {
+        static_assert(sizeof(typename Vec3s::value_type) == 12 && sizeof(typename Vec2s::value_type) == 8, "vec3 / vec2 must be packed floats");
+        static_assert(sizeof(typename Faces::value_type) == 40, "Triangle must be 10 x int32 (headers/face.h:6-13)");
+        check(rast_upload_mesh(ctx_, reinterpret_cast<const float *>(vertices.data()), (uint32_t)vertices.size(),
+                               reinterpret_cast<const float *>(normals.data()), (uint32_t)normals.size(),
+                               reinterpret_cast<const float *>(uvs.data()), (uint32_t)uvs.size(),
+                               reinterpret_cast<const int32_t *>(faces.data()), (uint64_t)faces.size()), "rast_upload_mesh");
+        std::vector<rast_material> m(materials.size());
+        for (size_t i = 0; i < materials.size(); ++i) {
+            m[i].kd[0] = materials[i].kd[0]; m[i].kd[1] = materials[i].kd[1]; m[i].kd[2] = materials[i].kd[2];
+            m[i].has_texture = materials[i].has_texture ? 1 : 0;
+            m[i].tex_w = materials[i].tex_w; m[i].tex_h = materials[i].tex_h;
+            m[i].texels = materials[i].has_texture ? &materials[i].texels[0] : nullptr;
+        }
+        check(rast_upload_materials(ctx_, m.data(), (uint32_t)m.size()), "rast_upload_materials");
+        key_ = {vertices.data(), faces.data(), normals.data(), uvs.data(), materials.data(), vertices.size(), faces.size(), materials.size()};
+        uploaded_ = true;
+    }
+
+    template <class Vec3s, class Faces, class Vec2s, class Materials>
+    bool holds(const Vec3s &vertices, const Faces &faces, const Vec3s &normals, const Vec2s &uvs, const Materials &materials) const {
+        const Key k = {vertices.data(), faces.data(), normals.data(), uvs.data(), materials.data(), vertices.size(), faces.size(), materials.size()};
+        return uploaded_ && k.v == key_.v && k.f == key_.f && k.n == key_.n && k.u == key_.u && k.m == key_.m && k.nv == key_.nv && k.nf == key_.nf && k.nm == key_.nm;
+    }
+
+private:
+    struct Key { const void *v, *f, *n, *u, *m; size_t nv, nf, nm; };
+    rast_ctx *ctx_ = nullptr;
+    Key key_{};
+    bool uploaded_ = false;
+};
+
+template <class ArgsT> inline rast_args to_rast_args(const ArgsT &a) {
+    rast_args r;
+    r.image_width = a.image_width;
+    r.image_height = a.image_height;
+    r.aspect_ratio = a.aspect_ratio;
+    r.scale = a.scale;
+    for (int k = 0; k < 3; ++k) {
+        r.displacement[k] = a.displacement[k];
+        r.tait_bryan_angles[k] = a.tait_bryan_angles[k];
+    }
+    r.wind_clockwise = a.wind_clockwise ? 1 : 0;
+    r.flat = a.flat ? 1 : 0;
+    return r;
+}
+
+// Same argument order as the reference's draw_frame.  Lights: any vector whose elements are laid out as
+// struct Light (direction[3], intensity, colour[3], trans_dir[3] = 10 floats, headers/light.h:7-14).
+template <class Vec3s, class Faces, class Vec2s, class Lights, class Materials, class ArgsT, class FrameImage, class DepthImage>
+void draw_frame(Session &session, const Vec3s &model_vertices, const Faces &faces, const Vec3s &model_vertnormals, const Vec2s &vertuvs,
+                Lights &lights, const Materials &materials, const ArgsT &arguments, FrameImage *frame_buffer, DepthImage *depth_buffer) {
+    static_assert(sizeof(typename Lights::value_type) == sizeof(rast_light), "Light must be 10 packed floats");
+    if (!session.holds(model_vertices, faces, model_vertnormals, vertuvs, materials))
+        session.upload(model_vertices, faces, model_vertnormals, vertuvs, materials);
+    rast_light *l = reinterpret_cast<rast_light *>(lights.data());
+    session.check(rast_set_lights(session.ctx(), l, (uint32_t)lights.size()), "rast_set_lights");
+    const rast_args a = to_rast_args(arguments);
+    session.check(rast_draw_frame(session.ctx(), &a, frame_buffer->data(), depth_buffer ? depth_buffer->data() : nullptr, l), "rast_draw_frame");
+}
+
+} // namespace rast

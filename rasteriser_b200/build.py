@@ -14,6 +14,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "librast_b200.so")
 RENDERER = os.path.join(PKG, "renderer")
+HOST_LIB = os.path.join(PKG, "librast_host.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false",  # the reference's fp32 ops are never fused
@@ -49,22 +50,31 @@ def build_lib(force=False, verbose=False):
     return LIB
 
 
+HOST_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-fPIC"]
+
+
 def build_renderer(force=False):
+    """rasteriser_b200/renderer: the reference-compatible command line (host/main.cpp) on the C ABI."""
     host = os.path.join(PKG, "host")
-    main = os.path.join(host, "main.cpp")
-    if not os.path.exists(main):
-        return None
     deps = _sources(host, os.path.join(ROOT, "include")) + [LIB]
     if force or _stale(RENDERER, deps):
-        srcs = [os.path.join(host, f) for f in sorted(os.listdir(host)) if f.endswith(".cpp")]
-        cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", RENDERER] + srcs + \
-              ["-L", PKG, "-lrast_b200", "-Wl,-rpath,$ORIGIN", "-lz", "-lpthread"]
-        subprocess.check_call(cmd)
+        srcs = [os.path.join(host, f) for f in ("main.cpp", "args.cpp", "loaders.cpp", "png.cpp")]
+        subprocess.check_call(["g++"] + HOST_FLAGS + ["-o", RENDERER] + srcs + ["-L", PKG, "-lrast_b200", "-Wl,-rpath,$ORIGIN", "-lz", "-lpthread"])
     return RENDERER
+
+
+def build_host_lib(force=False):
+    """rasteriser_b200/librast_host.so: loaders, PNG codec and flag parser behind a C API (tests, bench)."""
+    host = os.path.join(PKG, "host")
+    if force or _stale(HOST_LIB, _sources(host)):
+        srcs = [os.path.join(host, f) for f in ("host_capi.cpp", "args.cpp", "loaders.cpp", "png.cpp")]
+        subprocess.check_call(["g++"] + HOST_FLAGS + ["-shared", "-o", HOST_LIB] + srcs + ["-lz"])
+    return HOST_LIB
 
 
 def build_all(force=False, verbose=False):
     build_lib(force, verbose)
+    build_host_lib(force)
     build_renderer(force)
 
 

@@ -1,0 +1,122 @@
+// main.cpp -- reference-compatible command line on the B200 frame path.
+//
+// Same flow as the reference's main (renderer.cpp:52-129): parse flags, load lights, load the model (or the
+// built-in square), allocate frame (RGB8, 0) and depth (f32, 1.0) buffers, draw, write frame.png and the
+// normalised depth.png.  What differs: draw_frame runs on the GPU through the rast_* ABI, and -s (spin)
+// -- an X11 window rotated by wall-clock time in the reference (renderer.cpp:94-126) -- is a headless,
+// deterministic sequence: frame k of N is rotated by ry + k * 2*pi/N; frames are rendered in
+// batches, optionally written as PNG, and the measured frame rate is printed.
+#include <chrono>
+#include <cstring>
+#include <cstdio>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "../../include/rast.h"
+#include "../../include/rast_draw_frame.hpp"
+#include "args.hpp"
+#include "image.hpp"
+#include "loaders.hpp"
+#include "png.hpp"
+
+using host::Args;
+using host::Image;
+
+namespace {
+
+struct Tri { int32_t i[10]; }; // struct Triangle (headers/face.h:6-13)
+struct Vec3 { float x, y, z; };
+struct Vec2 { float x, y; };
+
+template <class T, class U> std::vector<T> pack(const std::vector<U> &flat) {
+    std::vector<T> out(flat.size() * sizeof(U) / sizeof(T));
+    if (!out.empty()) memcpy(out.data(), flat.data(), out.size() * sizeof(T));
+    return out;
+}
+
+} // namespace
+
+int main(int argc, char **argv) {
+    Args arguments;
+    std::string message;
+    switch (host::parse_args(argc, argv, arguments, message)) {
+        case host::ParseResult::Help: std::cout << host::usage_text(argv[0]); return 0;
+        case host::ParseResult::Version: std::cout << argv[0] << "  version: " << rast_version() << std::endl; return 0;
+        case host::ParseResult::Error:
+            std::cerr << message << "\n\nBrief USAGE: \n   " << argv[0] << "  -l <lights.csv> [-o <model.obj>] ...\n\nFor complete USAGE and HELP type: \n   " << argv[0] << " --help\n" << std::endl;
+            return 1;
+        case host::ParseResult::Ok: break;
+    }
+    const bool verbose = !arguments.quiet;
+
+    host::Model model;
+    std::vector<host::Light> lights;
+    std::string err;
+    if (!host::load_lights(arguments.lights_file, lights, err)) { std::cerr << err << std::endl; return 1; } // renderer.cpp:75
+    if (!arguments.obj_file.empty()) {                                                                        // renderer.cpp:78-82
+        const bool ok = host::load_obj(arguments.obj_file, arguments.materials_directory, model, err, verbose);
+        if (!err.empty()) std::cerr << err << std::endl; // fileloader.cpp:95-97
+        if (!ok) return 1;
+    } else {
+        host::add_square(model);
+    }
+    const std::vector<Vec3> vertices = pack<Vec3>(model.positions), normals = pack<Vec3>(model.normals);
+    const std::vector<Vec2> uvs = pack<Vec2>(model.uvs);
+    const std::vector<Tri> faces = pack<Tri>(model.tris);
+
+    // renderer.cpp:85-86
+    Image<unsigned char> frame_buffer(arguments.image_width, arguments.image_height, 3, 0);
+    Image<float> depth_buffer(arguments.image_width, arguments.image_height, 1, 1.f);
+
+    try {
+        rast::Session session(arguments.device);
+        if (!arguments.spin) {
+            rast::draw_frame(session, vertices, faces, normals, uvs, lights, model.materials, arguments, &frame_buffer, &depth_buffer);
+            // renderer.cpp:92-93: frame.png, and depth.normalize(0,255) saved as 8-bit grey
+            err = host::png_write_planar(arguments.frame_out, frame_buffer.data(), arguments.image_width, arguments.image_height, 3);
+            if (!err.empty()) { std::cerr << err << std::endl; return 1; }
+            std::vector<unsigned char> depth8((size_t)arguments.image_width * arguments.image_height);
+            session.check(rast_depth_to_u8(session.ctx(), depth8.data()), "rast_depth_to_u8"); // normalize + uchar cast on the device
+            err = host::png_write(arguments.depth_out, depth8.data(), arguments.image_width, arguments.image_height, 1);
+            if (!err.empty()) { std::cerr << err << std::endl; return 1; }
+        } else {
+            // headless spin: N frames, ry_k = ry + k * 2*pi/N, rendered in batches through rast_draw_frames
+            session.upload(vertices, faces, normals, uvs, model.materials);
+            session.check(rast_set_lights(session.ctx(), reinterpret_cast<rast_light *>(lights.data()), (uint32_t)lights.size()), "rast_set_lights");
+            const unsigned n = arguments.frames ? arguments.frames : 1u;
+            const size_t P = (size_t)arguments.image_width * arguments.image_height;
+            const unsigned chunk = n < 64u ? n : 64u;
+            unsigned char *frames = static_cast<unsigned char *>(rast_host_alloc((uint64_t)chunk * 3 * P));
+            if (!frames) { std::cerr << "out of pinned host memory" << std::endl; return 1; }
+            std::vector<rast_args> poses(chunk);
+            const auto t0 = std::chrono::steady_clock::now();
+            for (unsigned first = 0; first < n; first += chunk) {
+                const unsigned count = n - first < chunk ? n - first : chunk;
+                for (unsigned i = 0; i < count; ++i) {
+                    poses[i] = rast::to_rast_args(arguments);
+                    poses[i].tait_bryan_angles[1] = rast_spin_angle(arguments.tait_bryan_angles[1], first + i, n);
+                }
+                session.check(rast_draw_frames(session.ctx(), poses.data(), count, frames, nullptr, 0), "rast_draw_frames");
+                if (!arguments.save_frames.empty()) {
+                    for (unsigned i = 0; i < count; ++i) {
+                        char name[4096];
+                        std::snprintf(name, sizeof name, arguments.save_frames.c_str(), first + i);
+                        err = host::png_write_planar(name, frames + (size_t)i * 3 * P, arguments.image_width, arguments.image_height, 3);
+                        if (!err.empty()) { std::cerr << err << std::endl; return 1; }
+                    }
+                }
+            }
+            const std::chrono::duration<float> dt = std::chrono::steady_clock::now() - t0;
+            if (verbose) std::cout << n << " frames in " << dt.count() << " s: " << std::to_string((float)n / dt.count()) << " frames/s" << std::endl; // renderer.cpp:120
+            // the last frame is left in frame.png so the run has a visible result
+            err = host::png_write_planar(arguments.frame_out, frames + (size_t)((n - 1) % chunk) * 3 * P, arguments.image_width, arguments.image_height, 3);
+            rast_host_free(frames);
+            if (!err.empty()) { std::cerr << err << std::endl; return 1; }
+        }
+    } catch (const std::exception &e) {
+        std::cerr << "Error: " << e.what() << std::endl;
+        return 1;
+    }
+    return 0;
+}

@@ -208,3 +208,33 @@ def test_errors():
         assert f.any()
     finally:
         r.close()
+
+
+def test_renderer_cli_writes_reference_images(tmp_path):
+    """The C++ command line (reference flags) end to end: frame.png / depth.png decode to the reference's images."""
+    import os
+    import subprocess
+    from PIL import Image
+    from rasteriser_b200 import build
+    exe = build.build_renderer()
+    case = [c for c in CASES if c["name"] == "suzanne_640x480_pose1"][0]
+    cmd = [exe, "-o", os.path.join(S.DATA, "Suzanne.obj"), "-l", os.path.join(S.DATA, "threepoint.csv"), "--mats-dir", S.DATA + "/",
+           "-x", "640", "-y", "480", "--scale", "1.25", "--dx", "0.1", "--dy", "-0.2", "--dz", "0.5", "--rx", "0.3", "--ry", "1.0", "--rz", "0.2"]
+    out = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "Loading 968 triangles..." in out.stdout and "Loaded model" in out.stdout and "Loaded texture" in out.stdout
+    frame = np.ascontiguousarray(np.asarray(Image.open(tmp_path / "frame.png")).transpose(2, 0, 1))
+    depth8 = np.ascontiguousarray(np.asarray(Image.open(tmp_path / "depth.png")))
+    assert orc.fnv(frame) == case["frame_fnv"]
+    assert orc.fnv(depth8) == case["depth_u8_fnv"]
+    # headless spin: 5 frames, last one saved; equals a single frame at the same angle
+    out = subprocess.run(cmd[:11] + ["-s", "--frames", "5", "--save-frames", "spin_%02u.png"], cwd=tmp_path, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "frames/s" in out.stdout and (tmp_path / "spin_04.png").exists()
+    oa = orc.make_args(640, 480, angles=(0.0, float(orc.oracle().orc_spin_angle(0.0, 4, 5)), 0.0))
+    wf, _, _ = orc.oracle_draw(S.scene("suzanne"), S.lights("threepoint"), oa)
+    got = np.ascontiguousarray(np.asarray(Image.open(tmp_path / "spin_04.png")).transpose(2, 0, 1))
+    assert np.array_equal(got, wf)
+    # errors: missing -l, unreadable model
+    assert subprocess.run([exe, "-o", "x.obj"], capture_output=True).returncode == 1
+    assert subprocess.run([exe, "-o", "/nonexistent.obj", "-l", os.path.join(S.DATA, "threepoint.csv")], capture_output=True).returncode == 1
