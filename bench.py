@@ -232,6 +232,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--frames", type=int, default=0, help="override frames per step (profiling runs)")
+    ap.add_argument("--gather", action="store_true", help="N>1 spin: also gather the finished RGB frames to rank 0 (NCCL) inside the timed region")
     opts = ap.parse_args()
 
     wl = make_workload(opts.workload)
@@ -261,12 +262,21 @@ def main():
     torch.cuda.set_stream(stream)
     r.set_stream(stream.cuda_stream)
 
+    from rasteriser_b200 import multi
     W, H, n = wl["width"], wl["height"], wl["frames"]
-    P = W * H
-    poses = spin_args(api, wl, rank, world)
+    # a single huge frame on N GPUs is split sort-first into row bands and gathered to rank 0 (strong scaling);
+    # a frame sequence is partitioned by frame with no communication (weak scaling)
+    band_mode = n == 1 and world > 1
+    rows = H
+    if band_mode:
+        y0, y1 = multi.band_of_rank(H, rank, world)
+        r.set_band(y0, y1)
+        rows = y1 - y0
+    P = W * rows
+    poses = spin_args(api, wl, rank, 1 if band_mode else world)
     arr = (api.RastArgs * n)(*[a.to_rast() for a in poses])
-    frames_dev = torch.empty((n, 3, H, W), dtype=torch.uint8, device=dev)
-    depths_dev = torch.empty((n, H, W), dtype=torch.float32, device=dev)
+    frames_dev = torch.empty((n, 3, rows, W), dtype=torch.uint8, device=dev)
+    depths_dev = torch.empty((n, rows, W), dtype=torch.float32, device=dev)
 
     def barrier():
         if world > 1:
@@ -275,6 +285,12 @@ def main():
 
     def step_device():
         r.draw_frames_device(arr, frames_dev.data_ptr(), depths_dev.data_ptr())
+        if band_mode:  # NCCL over NVLink: band slabs to rank 0, on the same stream as the kernels
+            multi.gather_bands(frames_dev[0], H)
+            multi.gather_bands(depths_dev[0], H)
+        elif opts.gather and world > 1:  # optional: finished RGB frames of the sequence to rank 0
+            for c in range(0, n, 120):
+                multi.gather_frames(frames_dev[c:c + 120], min(120, n - c) * world)
 
     # ---- value: device-resident ----
     for _ in range(max(3, opts.warmup)):
@@ -298,7 +314,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     clk = clocks.stop() if rank == 0 else None
-    fps = world * n * opts.steps / (ms_total * 1e-3)
+    fps = (1 if band_mode else world) * n * opts.steps / (ms_total * 1e-3)
 
     # ---- e2e: host buffers through the public host entry point ----
     e2e = None
@@ -308,8 +324,8 @@ def main():
         fb, db = lib.rast_host_alloc(chunk * 3 * P), lib.rast_host_alloc(chunk * P * 4)
         if not fb or not db:
             raise SystemExit("bench.py: pinned host allocation failed")
-        frames_host = np.ctypeslib.as_array(C.cast(fb, C.POINTER(C.c_uint8)), (chunk, 3, H, W))
-        depths_host = np.ctypeslib.as_array(C.cast(db, C.POINTER(C.c_float)), (chunk, H, W))
+        frames_host = np.ctypeslib.as_array(C.cast(fb, C.POINTER(C.c_uint8)), (chunk, 3, rows, W))
+        depths_host = np.ctypeslib.as_array(C.cast(db, C.POINTER(C.c_float)), (chunk, rows, W))
         chunks = [(api.RastArgs * len(poses[i:i + chunk]))(*[a.to_rast() for a in poses[i:i + chunk]]) for i in range(0, n, chunk)]
 
         def step_host():
@@ -326,7 +342,7 @@ def main():
         t = torch.tensor([wall], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n * opts.steps / float(t.item()), "unit": UNIT,
+        e2e = {"value": (1 if band_mode else world) * n * opts.steps / float(t.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(n * 144 + len(chunks) * len(wl["lights"]) * 32), "d2h_bytes_per_step": int(n * 7 * P),
                "note": "rast_draw_frames with pinned host outputs, %d frames per call: RGB8 + f32 depth of every frame copied D2H inside the timed region (wall clock, max over ranks)" % chunk}
         checksum = int(frames_host[len(chunks[-1]) // 2].astype(np.uint64).sum())
@@ -348,7 +364,7 @@ def main():
     r.draw_frames_device(arr[n - 1:n] if n > 1 else arr, frames_dev.data_ptr(), depths_dev.data_ptr())
     r.sync()
     st = r.stats()
-    tri_ids = r.triangle_ids(W, H)
+    tri_ids = r.triangle_ids(W, rows)
     visible_tris = int(len(np.unique(tri_ids[tri_ids != api.NO_TRIANGLE])))
     batches_per_step = (n + 31) // 32
     launches_per_pass = prof_steps * batches_per_step
@@ -389,9 +405,10 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": opts.steps, "warmup": max(3, opts.warmup),
-                "ms_per_step": ms_total / opts.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "ms_per_step": ms_total / opts.steps, "higher_is_better": True, "scaling": "strong" if band_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["label"], "frames_per_step_per_gpu": n, "image": [W, H], "triangles": len(wl["tris"]),
-                           "partition": "frame k of the global sequence on rank k mod N; no collective", "l2": "working set per 32-frame batch ~1 GB >> 126 MB L2 (inputs/outputs larger than L2)",
+                           "partition": ("sort-first row bands, band slabs gathered to rank 0 with NCCL inside the timed region" if band_mode else
+                                         "frame k of the global sequence on rank k mod N; no collective" + ("; RGB frames gathered to rank 0 with NCCL" if opts.gather and world > 1 else "")), "l2": "working set per 32-frame batch ~1 GB >> 126 MB L2 (inputs/outputs larger than L2)",
                            "outputs": "RGB8 planes + f32 depth per frame, written to HBM"},
                 "mtris_per_s": fps * len(wl["tris"]) / 1e6, "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
                 "stats_last_frame": st, "checksum": checksum}
