@@ -295,6 +295,7 @@ def main():
     # ---- value: device-resident ----
     for _ in range(max(3, opts.warmup)):
         step_device()
+        r.sync()  # lets the library see the previous call's queue statistics (it grows its work queue lazily)
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:

@@ -8,6 +8,9 @@
 
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
+#include <cooperative_groups/scan.h>
 
 #include "exact.cuh"
 
@@ -223,14 +226,9 @@ __global__ void __launch_bounds__(256) k_vertex(Scene sc, View vw, Batch bt) {
 // ---- K2: triangle setup, cull, classification -----------------------------------------------
 // draw_triangle up to the pixel loops (drawing.cpp:165-188).  Tiny bboxes are rasterised here;
 // larger ones are cut into CHUNK x CHUNK work items for k_raster_chunks.
-__global__ void __launch_bounds__(256) k_setup(Scene sc, View vw, Batch bt) {
-    const uint32_t f = blockIdx.y;
-    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= sc.T) return;
-    const float4 *rv = bt.rv + (size_t)f * sc.V;
-    const float4 v0 = rv[sc.vidx0[t]], v1 = rv[sc.vidx1[t]], v2 = rv[sc.vidx2[t]];
+constexpr int SETUP_TRIS = 4; // triangles per thread: all index and vertex loads of a thread are in flight together
 
-    const bool cw = bt.frames[f].wind_clockwise != 0u;
+__device__ __noinline__ void setup_triangle(uint32_t t, uint32_t f, float4 v0, float4 v1, float4 v2, bool cw, const View &vw, const Batch &bt) {
     const float a2 = signed_area_2d(v0, v1, v2);
     if (!((a2 > 0.f) != cw)) return; // back face (drawing.cpp:178-180)
 
@@ -243,8 +241,21 @@ __global__ void __launch_bounds__(256) k_setup(Scene sc, View vw, Batch bt) {
     if (!inline_raster) {
         const uint32_t ncx = (w + CHUNK - 1) / CHUNK, ncy = (h + CHUNK - 1) / CHUNK;
         const uint64_t n = (uint64_t)ncx * ncy;
-        // reserve n consecutive slots; the 64-bit count keeps growing past the capacity, so it cannot wrap
-        const uint64_t first = (n <= bt.queue_cap) ? atomicAdd(&bt.counters[0], (unsigned long long)n) : (uint64_t)bt.queue_cap;
+        // Reserve n consecutive slots.  One atomicAdd per warp, not per triangle: the lanes that reached this
+        // point sum their requests (exclusive scan over the coalesced group) and the last lane adds the total --
+        // per-lane atomics on this single counter serialised in L2 and were 29 % of the kernel (ncu, 8 M triangles).
+        // The 64-bit count keeps growing past the capacity, so it cannot wrap.
+        namespace cg = cooperative_groups;
+        const cg::coalesced_group grp = cg::coalesced_threads();
+        const unsigned long long want = n <= bt.queue_cap ? n : 0ull;
+        const unsigned long long before = cg::exclusive_scan(grp, want);
+        unsigned long long base = 0;
+        if (grp.thread_rank() == grp.size() - 1) base = atomicAdd(&bt.counters[0], before + want);
+        base = grp.shfl(base, grp.size() - 1);
+        // queued bbox area (also one atomic per warp): the raster pass derives its overdraw estimate from it
+        const unsigned long long area_sum = cg::reduce(grp, (unsigned long long)w * h, cg::plus<unsigned long long>());
+        if (grp.thread_rank() == 0) atomicAdd(&bt.counters[3], area_sum);
+        const uint64_t first = (n <= bt.queue_cap) ? base + before : (uint64_t)bt.queue_cap;
         if (first + n > bt.queue_cap) {
             // queue full: void any slots reserved below the capacity and walk the whole bbox in this
             // thread (correct, slow); the host sees the flag and grows the queue for later frames
@@ -254,14 +265,38 @@ __global__ void __launch_bounds__(256) k_setup(Scene sc, View vw, Batch bt) {
         } else {
             uint64_t k = first;
             for (uint32_t cy = 0; cy < ncy; ++cy)
-                for (uint32_t cx = 0; cx < ncx; ++cx) bt.queue[k++] = make_uint2((uint32_t)t, cx | (cy << 12) | (f << 24));
+                for (uint32_t cx = 0; cx < ncx; ++cx) bt.queue[k++] = make_uint2(t, cx | (cy << 12) | (f << 24));
         }
     }
     if (inline_raster) {
         TriSetup s;
         tri_setup(s, v0, v1, v2);
         for (uint32_t y = bb.y0; y <= bb.y1; ++y)
-            for (uint32_t x = bb.x0; x <= bb.x1; ++x) test_and_commit(s, x, y, (uint32_t)t, vis, vw);
+            for (uint32_t x = bb.x0; x <= bb.x1; ++x) test_and_commit(s, x, y, t, vis, vw);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_setup(const __grid_constant__ Scene sc, const __grid_constant__ View vw, const __grid_constant__ Batch bt) {
+    const uint32_t f = blockIdx.y;
+    const uint64_t t0 = (uint64_t)blockIdx.x * (256 * SETUP_TRIS) + threadIdx.x;
+    const float4 *rv = bt.rv + (size_t)f * sc.V;
+    // phase 1: the (coalesced) index loads of all this thread's triangles, then all the vertex gathers
+    int i0[SETUP_TRIS], i1[SETUP_TRIS], i2[SETUP_TRIS];
+#pragma unroll
+    for (int k = 0; k < SETUP_TRIS; ++k) {
+        const uint64_t t = t0 + (uint64_t)k * 256;
+        const bool in = t < sc.T;
+        i0[k] = in ? sc.vidx0[t] : 0; i1[k] = in ? sc.vidx1[t] : 0; i2[k] = in ? sc.vidx2[t] : 0;
+    }
+    float4 v0[SETUP_TRIS], v1[SETUP_TRIS], v2[SETUP_TRIS];
+#pragma unroll
+    for (int k = 0; k < SETUP_TRIS; ++k) { v0[k] = rv[i0[k]]; v1[k] = rv[i1[k]]; v2[k] = rv[i2[k]]; }
+    const bool cw = bt.frames[f].wind_clockwise != 0u;
+    // phase 2
+#pragma unroll
+    for (int k = 0; k < SETUP_TRIS; ++k) {
+        const uint64_t t = t0 + (uint64_t)k * 256;
+        if (t < sc.T) setup_triangle((uint32_t)t, f, v0[k], v1[k], v2[k], cw, vw, bt);
     }
 }
 
@@ -273,7 +308,8 @@ __global__ void __launch_bounds__(256) k_setup(Scene sc, View vw, Batch bt) {
 // pixel quads of a 16x8 block, so the per-pixel differences (p - a) and half of the products of
 // edge() are shared inside the quad; a ballot skips blocks no lane may cover.
 constexpr int RASTER_WARPS = 8;
-constexpr int STAGE_FIELDS = 21;
+constexpr int STAGE_FIELDS = 23;
+constexpr unsigned long long EARLY_Z_OVERDRAW = 6;
 
 struct StagedTris {
     uint32_t w[STAGE_FIELDS][32]; // [field][slot]: conflict-free lane-per-slot writes, broadcast reads
@@ -285,12 +321,19 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_chunks(Scene sc, V
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t count = (uint32_t)min(bt.counters[0], (unsigned long long)bt.queue_cap);
     const uint32_t qx = (lane & 7u) * 2u, qy = (lane >> 3) * 2u;
+    // items per grab: 32 when the queue is long (amortises the fetch latency), fewer when it is short so that
+    // a small frame still spreads over the whole grid instead of over count/32 warps
+    const uint32_t n_warps = gridDim.x * RASTER_WARPS;
+    const uint32_t take = max(1u, min(32u, count / n_warps));
+    // Early depth rejection pays only when fragments mostly lose: it is switched on when the queued bbox area
+    // exceeds EARLY_Z_OVERDRAW times the pixels of the batch (bboxes are about twice the covered area).
+    const bool early_z = bt.counters[3] > (unsigned long long)EARLY_Z_OVERDRAW * vw.band_pixels * bt.n_frames;
     for (;;) {
         uint32_t base = 0;
-        if (lane == 0) base = (uint32_t)min(atomicAdd(&bt.counters[1], 32ull), 0xFFFFFFFFull);
+        if (lane == 0) base = (uint32_t)min(atomicAdd(&bt.counters[1], (unsigned long long)take), 0xFFFFFFFFull);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= count) break;
-        const uint32_t n_items = min(32u, count - base);
+        const uint32_t n_items = min(take, count - base);
 
         // ---- stage: lane = item ----
         {
@@ -321,6 +364,12 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_chunks(Scene sc, V
             stg.w[18][lane] = rect1;
             stg.w[19][lane] = tri;
             stg.w[20][lane] = f;
+            // early depth rejection (see below): 1/area and an error margin, both only used to SKIP work
+            const float zmax = fmaxf(fmaxf(fabsf(s.z0), fabsf(s.z1)), fabsf(s.z2));
+            const float rcp = 1.0f / s.area;
+            const bool usable = !s.literal && rcp > 0.f && rcp < __int_as_float(0x7f800000) && zmax < __int_as_float(0x7f800000);
+            stg.w[21][lane] = __float_as_uint(usable ? rcp : 0.f);
+            stg.w[22][lane] = __float_as_uint(usable ? fmaf(zmax, 1.9073486328125e-06f /* 2^-19 */, 1e-37f) : __int_as_float(0x7f800000));
         }
         __syncwarp();
 
@@ -338,6 +387,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_chunks(Scene sc, V
             s.d01x = __uint_as_float(stg.w[13][it]); s.d01y = __uint_as_float(stg.w[14][it]);
             s.area = __uint_as_float(stg.w[15][it]);
             s.literal = stg.w[16][it] != 0u;
+            const float rcp_area = __uint_as_float(stg.w[21][it]), z_margin = __uint_as_float(stg.w[22][it]);
             const uint32_t rect0 = stg.w[17][it], rect1 = stg.w[18][it];
             const uint32_t rx0 = rect0 & 0xFFFFu, ry0 = rect0 >> 16, rx1 = rect1 & 0xFFFFu, ry1 = rect1 >> 16;
             unsigned long long *vis = bt.vis + (size_t)stg.w[20][it] * vw.band_pixels;
@@ -368,13 +418,31 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_chunks(Scene sc, V
                         if (candidate(s, e0[k], e1[k], e2[k])) mask |= 1u << k;
                     mask &= inrect;
                     if (!__any_sync(0xFFFFFFFFu, mask != 0u)) continue;
+                    // Early depth rejection.  z_est approximates the fragment depth to within z_margin
+                    // (|z_est - z| <= (2^-22 + 8 ulp) * max|z_k| < z_margin / 2 for a candidate pixel), and a stored depth
+                    // only ever decreases, so "z_est > stored + margin" proves the exact depth would lose the atomicMin:
+                    // the divisions and the atomic are skipped.  Stale reads and NaNs fall through to the exact path.
+                    unsigned long long *pix0 = vis + (size_t)(y - vw.y0) * vw.W + x;
+                    if (early_z) {
+                        uint32_t cur_hi[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) // all four loads in flight together (L2, bypassing L1)
+                            cur_hi[k] = (mask & (1u << k)) ? __ldcg(reinterpret_cast<const uint32_t *>(pix0 + (k >> 1) * (size_t)vw.W + (k & 1)) + 1) : 0xFFFFFFFFu;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float z_est = fmaf(s.z2, e2[k], fmaf(s.z1, e1[k], s.z0 * e0[k])) * rcp_area;
+                            const uint32_t cur_bits = (cur_hi[k] & 0x80000000u) ? (cur_hi[k] ^ 0x80000000u) : ~cur_hi[k]; // inverse of depth_key
+                            if (cur_hi[k] != 0xFFFFFFFFu && z_est > __uint_as_float(cur_bits) + z_margin) mask &= ~(1u << k);
+                        }
+                        if (!__any_sync(0xFFFFFFFFu, mask != 0u)) continue;
+                    }
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         if (mask & (1u << k)) {
                             float b0, b1, b2, z;
                             if (fragment(s, e0[k], e1[k], e2[k], b0, b1, b2, z)) {
                                 const unsigned long long key = ((unsigned long long)depth_key(z) << 32) | tri;
-                                atomicMin(vis + (size_t)(y + (k >> 1) - vw.y0) * vw.W + (x + (k & 1)), key);
+                                atomicMin(pix0 + (k >> 1) * (size_t)vw.W + (k & 1), key);
                             }
                         }
                     }

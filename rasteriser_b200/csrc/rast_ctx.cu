@@ -23,7 +23,7 @@ thread_local std::string g_create_error;
 
 constexpr uint32_t MAX_BATCH = 32;                 // frames in flight through one launch sequence (<= 256: 8-bit frame tag)
 constexpr size_t BATCH_BYTES_BUDGET = 6ull << 30;  // per-batch device scratch budget
-constexpr uint32_t QUEUE_MIN = 1u << 20;           // work items
+constexpr uint32_t QUEUE_MIN = 1u << 23;           // work items (8 B each); grows on demand when a frame overflows it
 
 struct DeviceBuffer {
     void *p = nullptr;
@@ -195,7 +195,7 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     if (prof) cudaEventRecord(ctx->ev_pass[1], st);
     if (sc.V) rk::k_vertex<<<dim3(grid_for((size_t)sc.V + (bt.cn ? sc.Nn : 0u), 256), count), 256, 0, st>>>(sc, vw, bt);
     if (prof) cudaEventRecord(ctx->ev_pass[2], st);
-    if (sc.T && vw.band_pixels) rk::k_setup<<<dim3(grid_for(sc.T, 256), count), 256, 0, st>>>(sc, vw, bt);
+    if (sc.T && vw.band_pixels) rk::k_setup<<<dim3(grid_for(sc.T, 256 * rk::SETUP_TRIS), count), 256, 0, st>>>(sc, vw, bt);
     if (prof) cudaEventRecord(ctx->ev_pass[3], st);
     if (sc.T && vw.band_pixels) rk::k_raster_chunks<<<ctx->raster_grid, rk::RASTER_WARPS * 32, 0, st>>>(sc, vw, bt);
     if (prof) cudaEventRecord(ctx->ev_pass[4], st);
