@@ -28,7 +28,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "frames_per_s_suzanne_1080p_spin"
+METRIC = "frames_per_s_suzanne_1080p_spin"  # the default workload; other --workload values rename it below
 UNIT = "frames/s"
 
 
@@ -236,6 +236,9 @@ def main():
     opts = ap.parse_args()
 
     wl = make_workload(opts.workload)
+    global METRIC
+    if opts.workload != "spin1080p":
+        METRIC = "frames_per_s_" + opts.workload
     if opts.frames:
         wl["frames"] = opts.frames
     if opts.impl == "reference":
