@@ -38,7 +38,7 @@ struct MaterialDev {          // material.h:11-25
     float kd[3];
     int has_texture;
     int tex_w, tex_h;
-    long long texel_offset;   // into Scene::texels, planar [3][h][w]
+    long long texel_offset;   // into Scene::texels, in texels
 };
 
 struct Scene {
@@ -52,7 +52,7 @@ struct Scene {
                               // appended to each array (zero normal, uv (0,0), white untextured material),
                               // so the shade pass needs no index checks
     const MaterialDev *mats;
-    const float *texels;
+    const float4 *texels;     // all textures, interleaved (r, g, b, -) per texel
     uint32_t V, Nn, Nuv, M;   // Nn, Nuv, M count the appended sentinel entry
     uint64_t T;
 };
@@ -455,8 +455,10 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_chunks(Scene sc, V
 
 // ---- K4: resolve + deferred shading ---------------------------------------------------------
 // Material::sample on a textured material (material.cpp:19-21): three CImg::_linear_atXY lookups
-// (CImg.h:13475-13492) at the same position; the position arithmetic is shared between the channels.
-__device__ __forceinline__ void sample_texture(const float *tex, int w, int h, float fx, float fy, float &r, float &g, float &b) {
+// (CImg.h:13475-13492) at the same position.  The position arithmetic is shared between the channels and
+// the texels are stored interleaved (r, g, b, -) on the device, so the four corners are four 16-byte loads
+// instead of twelve 4-byte ones; the per-channel arithmetic is CImg's, unchanged.
+__device__ __forceinline__ void sample_texture(const float4 *__restrict__ tex, int w, int h, float fx, float fy, float &r, float &g, float &b) {
     using namespace exact;
     const float hx = (float)(w - 1), hy = (float)(h - 1);
     const float nfx = fx < 0.f ? 0.f : (fx > hx ? hx : fx); // cimg::cut (CImg.h:5184-5186)
@@ -464,18 +466,12 @@ __device__ __forceinline__ void sample_texture(const float *tex, int w, int h, f
     const uint32_t x = to_uint(nfx), y = to_uint(nfy);
     const float dx = sub(nfx, (float)x), dy = sub(nfy, (float)y);
     const uint32_t nx = dx > 0.f ? x + 1u : x, ny = dy > 0.f ? y + 1u : y;
-    const uint32_t occ = x + y * (uint32_t)w, onc = nx + y * (uint32_t)w, ocn = x + ny * (uint32_t)w, onn = nx + ny * (uint32_t)w;
-    const uint32_t plane = (uint32_t)w * (uint32_t)h;
-    float out[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float *p = tex + (size_t)c * plane;
-        const float Icc = p[occ], Inc = p[onc], Icn = p[ocn], Inn = p[onn];
-        const float t1 = sub(sub(add(Icc, Inn), Icn), Inc);
-        const float t2 = add(sub(Inc, Icc), mul(dy, t1));
-        out[c] = add(add(Icc, mul(dx, t2)), mul(dy, sub(Icn, Icc)));
-    }
-    r = out[0]; g = out[1]; b = out[2];
+    const float4 cc = __ldg(tex + (x + y * (uint32_t)w)), nc = __ldg(tex + (nx + y * (uint32_t)w));
+    const float4 cn = __ldg(tex + (x + ny * (uint32_t)w)), nn = __ldg(tex + (nx + ny * (uint32_t)w));
+    // Icc + dx*(Inc - Icc + dy*(Icc + Inn - Icn - Inc)) + dy*(Icn - Icc)
+    r = add(add(cc.x, mul(dx, add(sub(nc.x, cc.x), mul(dy, sub(sub(add(cc.x, nn.x), cn.x), nc.x))))), mul(dy, sub(cn.x, cc.x)));
+    g = add(add(cc.y, mul(dx, add(sub(nc.y, cc.y), mul(dy, sub(sub(add(cc.y, nn.y), cn.y), nc.y))))), mul(dy, sub(cn.y, cc.y)));
+    b = add(add(cc.z, mul(dx, add(sub(nc.z, cc.z), mul(dy, sub(sub(add(cc.z, nn.z), cn.z), nc.z))))), mul(dy, sub(cn.z, cc.z)));
 }
 
 struct Shaded { uint32_t r, g, b; float depth; };
@@ -501,12 +497,12 @@ __device__ __forceinline__ Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t
     const uint4 *rec = reinterpret_cast<const uint4 *>(sc.tri_rec) + 3 * (size_t)tri; // indices are non-negative after upload
     const uint4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
     const uint2 r2 = __ldg(reinterpret_cast<const uint2 *>(rec + 2));
-    const float4 v0 = rv[r0.x], v1 = rv[r0.y], v2 = rv[r0.z];
+    const float4 v0 = __ldg(rv + r0.x), v1 = __ldg(rv + r0.y), v2 = __ldg(rv + r0.z); // written by k_vertex, read-only here
 
     // vertex normals in camera space (transform_direction, geometry.cpp:35-42,97-108)
     float4 n0, n1, n2;
     if (PRE_NORMALS) {
-        n0 = cn[r0.w]; n1 = cn[r1.x]; n2 = cn[r1.y];
+        n0 = __ldg(cn + r0.w); n1 = __ldg(cn + r1.x); n2 = __ldg(cn + r1.y);
     } else {
         const float *m0 = sc.nrm + 3 * (size_t)r0.w, *m1 = sc.nrm + 3 * (size_t)r1.x, *m2 = sc.nrm + 3 * (size_t)r1.y;
         float nm[16];
@@ -623,9 +619,13 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View 
         }
     }
 
-    // phase 2
-    const float4 *rv = bt.rv + (size_t)f * sc.V;
-    const float4 *cn = PRE_NORMALS ? bt.cn + (size_t)f * sc.Nn : nullptr;
+    // phase 2.  The per-frame base pointers are made opaque so that a gather is "base + index * 16" (one
+    // IMAD.WIDE) instead of a 64-bit add of the frame offset to every index followed by the address computation.
+    unsigned long long rv_base = (unsigned long long)(bt.rv + (size_t)f * sc.V);
+    unsigned long long cn_base = (unsigned long long)(PRE_NORMALS ? bt.cn + (size_t)f * sc.Nn : nullptr);
+    asm volatile("" : "+l"(rv_base), "+l"(cn_base));
+    const float4 *rv = reinterpret_cast<const float4 *>(rv_base);
+    const float4 *cn = reinterpret_cast<const float4 *>(cn_base);
     const FrameParams *fp = bt.frames + f;
 #pragma unroll 1
     for (uint32_t g = 0; g < SHADE_GROUPS; ++g) {

@@ -543,20 +543,25 @@ int rast_upload_materials(rast_ctx *ctx, const rast_material *materials, uint32_
         if (m.has_texture) {
             // CImg::linear_atXY throws on an empty image (CImg.h:13467-13470)
             if (!m.texels || m.tex_w <= 0 || m.tex_h <= 0) return fail(ctx, RAST_EINVAL, "rast_upload_materials: textured material without texels");
-            texel_total += (size_t)3 * m.tex_w * m.tex_h;
+            texel_total += (size_t)m.tex_w * m.tex_h;
         }
     }
     RAST_CUDA(ctx, cudaSetDevice(ctx->device));
     RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     RAST_CUDA(ctx, ctx->d_mats.reserve(md.size() * sizeof(rk::MaterialDev)));
-    RAST_CUDA(ctx, ctx->d_texels.reserve(texel_total * 4));
+    RAST_CUDA(ctx, ctx->d_texels.reserve(texel_total * sizeof(float4)));
     RAST_CUDA(ctx, cudaMemcpy(ctx->d_mats.p, md.data(), md.size() * sizeof(rk::MaterialDev), cudaMemcpyHostToDevice));
     for (uint32_t i = 0; i < n_materials; ++i)
-        if (materials[i].has_texture)
-            RAST_CUDA(ctx, cudaMemcpy(ctx->d_texels.as<float>() + md[i].texel_offset, materials[i].texels,
-                                      (size_t)3 * materials[i].tex_w * materials[i].tex_h * 4, cudaMemcpyHostToDevice));
+        if (materials[i].has_texture) { // planar [3][h][w] (CImg layout) -> interleaved float4 per texel
+            const size_t n = (size_t)materials[i].tex_w * materials[i].tex_h;
+            std::vector<float4> inter;
+            try { inter.resize(n); } catch (...) { return fail(ctx, RAST_ENOMEM, "rast_upload_materials: out of host memory"); }
+            const float *t = materials[i].texels;
+            for (size_t k = 0; k < n; ++k) inter[k] = make_float4(t[k], t[n + k], t[2 * n + k], 0.f);
+            RAST_CUDA(ctx, cudaMemcpy(ctx->d_texels.as<float4>() + md[i].texel_offset, inter.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
+        }
     ctx->scene.mats = ctx->d_mats.as<rk::MaterialDev>();
-    ctx->scene.texels = ctx->d_texels.as<float>();
+    ctx->scene.texels = ctx->d_texels.as<float4>();
     ctx->scene.M = n_materials + 1;
     ctx->n_materials = n_materials;
     ctx->mesh_materials_dirty = true;
