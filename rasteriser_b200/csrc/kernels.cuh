@@ -308,8 +308,25 @@ __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ Scene sc,
 // pixel quads of a 16x8 block, so the per-pixel differences (p - a) and half of the products of
 // edge() are shared inside the quad; a ballot skips blocks no lane may cover.
 constexpr int RASTER_WARPS = 8;
-constexpr int STAGE_FIELDS = 23;
+constexpr int STAGE_FIELDS = 24;
 constexpr unsigned long long EARLY_Z_OVERDRAW = 6;
+
+// Conservative rejection of one 16x8 block (pixel extent [xa,xb] x [ya,yb]) against one sign-folded edge.
+// E(p) = dx*(py-yk) - dy*(px-xk) is affine, so over the block it peaks at a corner pixel; the fp32
+// evaluation e(p) differs from E(p) by at most 3.01 ulp-units of (|dx|*|py-yk| + |dy|*|px-xk|) (two rounded
+// differences, two rounded products, one rounded subtraction) plus 2^-148 for underflow.  Hence
+//   e(p) <= max_corners e(c) + 2*err   for every pixel p of the block,
+// and if that bound is below the candidate threshold -2^-22 no pixel of the block can be a candidate.
+// 8 ulp-units (2^-21) are used for 2*err = 6.02; NaN / inf make the comparison false (no rejection).
+__device__ __forceinline__ bool block_outside_edge(float dx, float dy, float xk, float yk, float xa, float xb, float ya, float yb) {
+    using namespace exact;
+    const float ua = sub(ya, yk), ub = sub(yb, yk), va = sub(xa, xk), vb = sub(xb, xk);
+    const float pa = mul(dx, ua), pb = mul(dx, ub), qa = mul(dy, va), qb = mul(dy, vb);
+    const float emax = fmaxf(fmaxf(sub(pa, qa), sub(pa, qb)), fmaxf(sub(pb, qa), sub(pb, qb)));
+    const float spread = fabsf(dx) * fmaxf(fabsf(ua), fabsf(ub)) + fabsf(dy) * fmaxf(fabsf(va), fabsf(vb));
+    const float err = fmaf(spread, 4.76837158203125e-07f /* 2^-21 */, 7.17e-43f /* 2^-140 */);
+    return emax + err < -EDGE_SLACK;
+}
 
 struct StagedTris {
     uint32_t w[STAGE_FIELDS][32]; // [field][slot]: conflict-free lane-per-slot writes, broadcast reads
@@ -370,6 +387,21 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_chunks(Scene sc, V
             const bool usable = !s.literal && rcp > 0.f && rcp < __int_as_float(0x7f800000) && zmax < __int_as_float(0x7f800000);
             stg.w[21][lane] = __float_as_uint(usable ? rcp : 0.f);
             stg.w[22][lane] = __float_as_uint(usable ? fmaf(zmax, 1.9073486328125e-06f /* 2^-19 */, 1e-37f) : __int_as_float(0x7f800000));
+            // which of the chunk's 4 x 2 blocks can contain a candidate pixel at all (bit = strip * 2 + column)
+            uint32_t live = 0xFFu;
+            if (tri != INVALID_TRI && !s.literal) {
+                const uint32_t rx0 = rect0 & 0xFFFFu, ry0 = rect0 >> 16, rx1 = rect1 & 0xFFFFu, ry1 = rect1 >> 16;
+#pragma unroll
+                for (uint32_t b = 0; b < 8u; ++b) {
+                    const uint32_t bx0 = rx0 + (b & 1u) * 16u, by0 = ry0 + (b >> 1) * 8u;
+                    if (bx0 > rx1 || by0 > ry1) continue;
+                    const float xa = (float)bx0, xb = (float)min(bx0 + 15u, rx1), ya = (float)by0, yb = (float)min(by0 + 7u, ry1);
+                    if (block_outside_edge(s.d12x, s.d12y, s.x1, s.y1, xa, xb, ya, yb) || block_outside_edge(s.d20x, s.d20y, s.x2, s.y2, xa, xb, ya, yb) ||
+                        block_outside_edge(s.d01x, s.d01y, s.x0, s.y0, xa, xb, ya, yb))
+                        live &= ~(1u << b);
+                }
+            }
+            stg.w[23][lane] = live;
         }
         __syncwarp();
 
@@ -391,9 +423,12 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_chunks(Scene sc, V
             const uint32_t rect0 = stg.w[17][it], rect1 = stg.w[18][it];
             const uint32_t rx0 = rect0 & 0xFFFFu, ry0 = rect0 >> 16, rx1 = rect1 & 0xFFFFu, ry1 = rect1 >> 16;
             unsigned long long *vis = bt.vis + (size_t)stg.w[20][it] * vw.band_pixels;
+            const uint32_t live = stg.w[23][it];
+            if (live == 0u) continue;
 
-            for (uint32_t by = ry0; by <= ry1; by += 8u) {
+            for (uint32_t by = ry0, strip = 0; by <= ry1; by += 8u, ++strip) {
                 using namespace exact;
+                if (((live >> (strip * 2u)) & 3u) == 0u) continue;
                 const uint32_t y = by + qy;
                 const float pya = (float)y, pyb = (float)(y + 1u);
                 // edge k at pixel (i,j): mul(dkx, py_j - yk) - mul(dky, px_i - xk)
@@ -401,7 +436,8 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_chunks(Scene sc, V
                 const float a1a = mul(s.d20x, sub(pya, s.y2)), a1b = mul(s.d20x, sub(pyb, s.y2));
                 const float a2a = mul(s.d01x, sub(pya, s.y0)), a2b = mul(s.d01x, sub(pyb, s.y0));
                 const uint32_t ymask = (y <= ry1 ? 3u : 0u) | (y + 1u <= ry1 ? 12u : 0u);
-                for (uint32_t bx = rx0; bx <= rx1; bx += 16u) {
+                for (uint32_t bx = rx0, column = 0; bx <= rx1; bx += 16u, ++column) {
+                    if (((live >> (strip * 2u + column)) & 1u) == 0u) continue;
                     const uint32_t x = bx + qx;
                     const float pxa = (float)x, pxb = (float)(x + 1u);
                     const float c0a = mul(s.d12y, sub(pxa, s.x1)), c0b = mul(s.d12y, sub(pxb, s.x1));
