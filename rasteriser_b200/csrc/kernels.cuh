@@ -75,6 +75,20 @@ struct Batch {
     unsigned long long *counters; // [0] queue count (may exceed queue_cap), [1] queue cursor, [2] overflow flag
 };
 
+// Screen-tile bins of the binned raster schedule (k_plan_tiles / k_fill_tiles / k_raster_tiles).
+struct TileBins {
+    uint32_t *count;       // [n_frames * tiles] items per tile (filled by k_setup)
+    uint32_t *start;       // [n_frames * tiles] exclusive prefix of count (k_plan)
+    uint32_t *fill;        // [n_frames * tiles] running cursor (k_fill)
+    uint2 *list;           // queued triangles (triangle, frame) (k_setup)
+    uint32_t *items;       // triangle ids grouped by tile (k_fill)
+    uint32_t list_cap, items_cap;
+    uint32_t tiles_x, tiles_y; // tiles of one frame (band)
+};
+
+constexpr uint32_t TILE = 32; // screen tile edge of the binned schedule (= CHUNK: both use the same 4 x 2 block grid)
+enum { CNT_QUEUE = 0, CNT_CURSOR = 1, CNT_QUEUE_OVERFLOW = 2, CNT_BBOX_AREA = 3, CNT_LIST = 4, CNT_TILE_ITEMS = 5, CNT_TILE_MODE = 6, CNT_TILE_OVERFLOW = 7, CNT_COUNT = 8 }; // counters[] slots
+
 // ---- visibility key ------------------------------------------------------------------------
 // Order-preserving map of a finite float below 1.0 to u32.  -0 is canonicalised so that it ties
 // with +0 (the reference's strict '<' treats them as equal, drawing.cpp:119).
@@ -199,7 +213,7 @@ __global__ void k_clear(unsigned long long *vis, size_t n) {
 __global__ void __launch_bounds__(256) k_vertex(Scene sc, View vw, Batch bt) {
     __shared__ float cam[16], nm[16];
     const uint32_t f = blockIdx.y;
-    if (blockIdx.x == 0 && f == 0 && threadIdx.x >= 32 && threadIdx.x < 36) bt.counters[threadIdx.x - 32] = 0ull; // work queue reset
+    if (blockIdx.x == 0 && f == 0 && threadIdx.x >= 32 && threadIdx.x < 40) bt.counters[threadIdx.x - 32] = 0ull; // work queue / bin counters reset
     if (threadIdx.x < 16) cam[threadIdx.x] = bt.frames[f].camera[threadIdx.x];
     else if (threadIdx.x < 32) nm[threadIdx.x - 16] = bt.frames[f].normal_m[threadIdx.x - 16];
     __syncthreads();
@@ -228,7 +242,8 @@ __global__ void __launch_bounds__(256) k_vertex(Scene sc, View vw, Batch bt) {
 // larger ones are cut into CHUNK x CHUNK work items for k_raster_chunks.
 constexpr int SETUP_TRIS = 4; // triangles per thread: all index and vertex loads of a thread are in flight together
 
-__device__ __noinline__ void setup_triangle(uint32_t t, uint32_t f, float4 v0, float4 v1, float4 v2, bool cw, const View &vw, const Batch &bt) {
+template <bool BINS>
+__device__ __noinline__ void setup_triangle(uint32_t t, uint32_t f, float4 v0, float4 v1, float4 v2, bool cw, const View &vw, const Batch &bt, const TileBins &tb) {
     const float a2 = signed_area_2d(v0, v1, v2);
     if (!((a2 > 0.f) != cw)) return; // back face (drawing.cpp:178-180)
 
@@ -250,17 +265,27 @@ __device__ __noinline__ void setup_triangle(uint32_t t, uint32_t f, float4 v0, f
         const unsigned long long want = n <= bt.queue_cap ? n : 0ull;
         const unsigned long long before = cg::exclusive_scan(grp, want);
         unsigned long long base = 0;
-        if (grp.thread_rank() == grp.size() - 1) base = atomicAdd(&bt.counters[0], before + want);
+        if (grp.thread_rank() == grp.size() - 1) base = atomicAdd(&bt.counters[0 /*CNT_QUEUE*/], before + want);
         base = grp.shfl(base, grp.size() - 1);
         // queued bbox area (also one atomic per warp): the raster pass derives its overdraw estimate from it
         const unsigned long long area_sum = cg::reduce(grp, (unsigned long long)w * h, cg::plus<unsigned long long>());
-        if (grp.thread_rank() == 0) atomicAdd(&bt.counters[3], area_sum);
+        if (grp.thread_rank() == 0) atomicAdd(&bt.counters[3 /*CNT_BBOX_AREA*/], area_sum);
         const uint64_t first = (n <= bt.queue_cap) ? base + before : (uint64_t)bt.queue_cap;
+        if (BINS) { // binned schedule requested: remember the triangle and count it in every tile it touches
+            unsigned long long lbase = 0;
+            if (grp.thread_rank() == 0) lbase = atomicAdd(&bt.counters[CNT_LIST], (unsigned long long)grp.size());
+            const unsigned long long slot = grp.shfl(lbase, 0) + grp.thread_rank();
+            if (slot < tb.list_cap) tb.list[slot] = make_uint2(t, f);
+            const uint32_t tx0 = bb.x0 / TILE, tx1 = bb.x1 / TILE, ty0 = (bb.y0 - vw.y0) / TILE, ty1 = (bb.y1 - vw.y0) / TILE;
+            uint32_t *cnt = tb.count + (size_t)f * tb.tiles_x * tb.tiles_y;
+            for (uint32_t ty = ty0; ty <= ty1; ++ty)
+                for (uint32_t tx = tx0; tx <= tx1; ++tx) atomicAdd(&cnt[ty * tb.tiles_x + tx], 1u);
+        }
         if (first + n > bt.queue_cap) {
             // queue full: void any slots reserved below the capacity and walk the whole bbox in this
             // thread (correct, slow); the host sees the flag and grows the queue for later frames
             for (uint64_t k = first; k < bt.queue_cap; ++k) bt.queue[k] = make_uint2(INVALID_TRI, 0u);
-            bt.counters[2] = 1ull;
+            bt.counters[2 /*CNT_QUEUE_OVERFLOW*/] = 1ull;
             inline_raster = true;
         } else {
             uint64_t k = first;
@@ -276,7 +301,9 @@ __device__ __noinline__ void setup_triangle(uint32_t t, uint32_t f, float4 v0, f
     }
 }
 
-__global__ void __launch_bounds__(256) k_setup(const __grid_constant__ Scene sc, const __grid_constant__ View vw, const __grid_constant__ Batch bt) {
+template <bool BINS>
+__global__ void __launch_bounds__(256) k_setup(const __grid_constant__ Scene sc, const __grid_constant__ View vw, const __grid_constant__ Batch bt,
+                                               const __grid_constant__ TileBins tb) {
     const uint32_t f = blockIdx.y;
     const uint64_t t0 = (uint64_t)blockIdx.x * (256 * SETUP_TRIS) + threadIdx.x;
     const float4 *rv = bt.rv + (size_t)f * sc.V;
@@ -296,19 +323,27 @@ __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ Scene sc,
 #pragma unroll
     for (int k = 0; k < SETUP_TRIS; ++k) {
         const uint64_t t = t0 + (uint64_t)k * 256;
-        if (t < sc.T) setup_triangle((uint32_t)t, f, v0[k], v1[k], v2[k], cw, vw, bt);
+        if (t < sc.T) setup_triangle<BINS>((uint32_t)t, f, v0[k], v1[k], v2[k], cw, vw, bt, tb);
     }
 }
 
-// ---- K3: chunk rasteriser -------------------------------------------------------------------
-// update_pixel's coverage + depth part (drawing.cpp:108-121) for the queued work items.
-// A warp takes 32 items at a time: each lane fetches ONE item (queue entry -> indices -> vertices, the
-// three dependent loads overlap across the 32 lanes), computes its triangle setup and stages it in
-// shared memory; then the whole warp walks the 32 staged items one after another.  Lanes own 2x2
-// pixel quads of a 16x8 block, so the per-pixel differences (p - a) and half of the products of
-// edge() are shared inside the quad; a ballot skips blocks no lane may cover.
+// ---- K3: rasterisers --------------------------------------------------------------------------
+// update_pixel's coverage + depth part (drawing.cpp:108-121) for the queued triangles.  Two schedules share
+// one inner loop:
+//   * k_raster_chunks -- work items are <=32x32-pixel chunks of a triangle's bbox, taken from a flat queue in
+//     any order; fragments go to the visibility buffer with global atomicMin.  Best when few fragments
+//     compete per pixel.
+//   * k_raster_tiles  -- screen-tile binning: the items of one aligned 32x32 screen tile are processed by one
+//     CTA that keeps the tile's 1024 keys in shared memory (atomicMin + early depth rejection against shared
+//     memory) and merges them into the visibility buffer once.  Chosen by the host when the previous call
+//     showed high overdraw: the global early-z reads of the chunk schedule then miss L2 and dominate.
+// In both, a warp stages up to 32 items at a time: each lane fetches ONE item (indices -> vertices: the
+// dependent loads overlap across the lanes), computes its triangle setup, the conservative block mask and
+// the early-z constants, and writes them to shared memory; then the whole warp walks the staged items.
+// Lanes own 2x2 pixel quads of a 16x8 block, so the per-pixel differences (p - a) and half of the products
+// of edge() are shared inside the quad; a ballot skips blocks no lane may cover.
 constexpr int RASTER_WARPS = 8;
-constexpr int STAGE_FIELDS = 24;
+constexpr int STAGE_FIELDS = 25;
 constexpr unsigned long long EARLY_Z_OVERDRAW = 6;
 
 // Conservative rejection of one 16x8 block (pixel extent [xa,xb] x [ya,yb]) against one sign-folded edge.
@@ -332,31 +367,159 @@ struct StagedTris {
     uint32_t w[STAGE_FIELDS][32]; // [field][slot]: conflict-free lane-per-slot writes, broadcast reads
 };
 
+// Stage one item (this lane's) : triangle `tri` of frame `f`, to be rasterised inside the pixel rectangle
+// [rx0,rx1] x [ry0,ry1] (already intersected with its bbox) on the 4 x 2 block grid anchored at (ox, oy).
+__device__ __forceinline__ void stage_item(StagedTris &stg, uint32_t lane, uint32_t tri, uint32_t f, const float4 &v0, const float4 &v1, const float4 &v2,
+                                           uint32_t rx0, uint32_t ry0, uint32_t rx1, uint32_t ry1, uint32_t ox, uint32_t oy) {
+    TriSetup s = {};
+    s.literal = true;
+    if (tri != INVALID_TRI) tri_setup(s, v0, v1, v2);
+    const float fl[16] = {s.x0, s.y0, s.x1, s.y1, s.x2, s.y2, s.z0, s.z1, s.z2, s.d12x, s.d12y, s.d20x, s.d20y, s.d01x, s.d01y, s.area};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) stg.w[k][lane] = __float_as_uint(fl[k]);
+    stg.w[16][lane] = s.literal ? 1u : 0u;
+    stg.w[17][lane] = rx0 | (ry0 << 16);
+    stg.w[18][lane] = rx1 | (ry1 << 16);
+    stg.w[19][lane] = tri;
+    stg.w[20][lane] = f;
+    // early depth rejection (see raster_item): 1/area and an error margin, both only used to SKIP work
+    const float zmax = fmaxf(fmaxf(fabsf(s.z0), fabsf(s.z1)), fabsf(s.z2));
+    const float rcp = 1.0f / s.area;
+    const bool usable = !s.literal && rcp > 0.f && rcp < __int_as_float(0x7f800000) && zmax < __int_as_float(0x7f800000);
+    stg.w[21][lane] = __float_as_uint(usable ? rcp : 0.f);
+    stg.w[22][lane] = __float_as_uint(usable ? fmaf(zmax, 1.9073486328125e-06f /* 2^-19 */, 1e-37f) : __int_as_float(0x7f800000));
+    // which of the 4 x 2 blocks can contain a candidate pixel at all (bit = strip * 2 + column)
+    uint32_t live = 0u;
+    if (tri != INVALID_TRI) {
+#pragma unroll
+        for (uint32_t b = 0; b < 8u; ++b) {
+            const uint32_t bx0 = max(ox + (b & 1u) * 16u, rx0), by0 = max(oy + (b >> 1) * 8u, ry0);
+            const uint32_t bx1 = min(ox + (b & 1u) * 16u + 15u, rx1), by1 = min(oy + (b >> 1) * 8u + 7u, ry1);
+            if (bx0 > bx1 || by0 > by1) continue;
+            const float xa = (float)bx0, xb = (float)bx1, ya = (float)by0, yb = (float)by1;
+            if (!s.literal && (block_outside_edge(s.d12x, s.d12y, s.x1, s.y1, xa, xb, ya, yb) || block_outside_edge(s.d20x, s.d20y, s.x2, s.y2, xa, xb, ya, yb) ||
+                               block_outside_edge(s.d01x, s.d01y, s.x0, s.y0, xa, xb, ya, yb)))
+                continue;
+            live |= 1u << b;
+        }
+    }
+    stg.w[23][lane] = live;
+    stg.w[24][lane] = ox | (oy << 16);
+}
+
+// Rasterise staged item `it` with the whole warp.  TILE_MODE = false: keys go to the visibility buffer `vis`
+// (global atomicMin; early-z reads it through L2 when `early_z`).  TILE_MODE = true: keys go to the CTA's
+// shared-memory tile `tile_keys` (TILE x TILE, anchored at the item's block origin); early-z always on.
+template <bool TILE_MODE>
+__device__ __forceinline__ void raster_item(const StagedTris &stg, uint32_t it, uint32_t lane, const View &vw, unsigned long long *vis_all,
+                                            unsigned long long *tile_keys, bool early_z) {
+    using namespace exact;
+    const uint32_t tri = stg.w[19][it];
+    const uint32_t live = stg.w[23][it];
+    if (tri == INVALID_TRI || live == 0u) return;
+    const uint32_t qx = (lane & 7u) * 2u, qy = (lane >> 3) * 2u;
+    TriSetup s;
+    s.x0 = __uint_as_float(stg.w[0][it]); s.y0 = __uint_as_float(stg.w[1][it]);
+    s.x1 = __uint_as_float(stg.w[2][it]); s.y1 = __uint_as_float(stg.w[3][it]);
+    s.x2 = __uint_as_float(stg.w[4][it]); s.y2 = __uint_as_float(stg.w[5][it]);
+    s.z0 = __uint_as_float(stg.w[6][it]); s.z1 = __uint_as_float(stg.w[7][it]); s.z2 = __uint_as_float(stg.w[8][it]);
+    s.d12x = __uint_as_float(stg.w[9][it]); s.d12y = __uint_as_float(stg.w[10][it]);
+    s.d20x = __uint_as_float(stg.w[11][it]); s.d20y = __uint_as_float(stg.w[12][it]);
+    s.d01x = __uint_as_float(stg.w[13][it]); s.d01y = __uint_as_float(stg.w[14][it]);
+    s.area = __uint_as_float(stg.w[15][it]);
+    s.literal = stg.w[16][it] != 0u;
+    const float rcp_area = __uint_as_float(stg.w[21][it]), z_margin = __uint_as_float(stg.w[22][it]);
+    const uint32_t rect0 = stg.w[17][it], rect1 = stg.w[18][it], org = stg.w[24][it];
+    const uint32_t rx0 = rect0 & 0xFFFFu, ry0 = rect0 >> 16, rx1 = rect1 & 0xFFFFu, ry1 = rect1 >> 16, ox = org & 0xFFFFu, oy = org >> 16;
+    unsigned long long *vis = TILE_MODE ? nullptr : vis_all + (size_t)stg.w[20][it] * vw.band_pixels;
+
+#pragma unroll 1
+    for (uint32_t strip = 0; strip < 4u; ++strip) {
+        if (((live >> (strip * 2u)) & 3u) == 0u) continue;
+        const uint32_t y = oy + strip * 8u + qy;
+        const float pya = (float)y, pyb = (float)(y + 1u);
+        // edge k at pixel (i,j): mul(dkx, py_j - yk) - mul(dky, px_i - xk)
+        const float a0a = mul(s.d12x, sub(pya, s.y1)), a0b = mul(s.d12x, sub(pyb, s.y1));
+        const float a1a = mul(s.d20x, sub(pya, s.y2)), a1b = mul(s.d20x, sub(pyb, s.y2));
+        const float a2a = mul(s.d01x, sub(pya, s.y0)), a2b = mul(s.d01x, sub(pyb, s.y0));
+        const uint32_t ymask = ((y >= ry0 && y <= ry1) ? 3u : 0u) | ((y + 1u >= ry0 && y + 1u <= ry1) ? 12u : 0u);
+#pragma unroll 1
+        for (uint32_t column = 0; column < 2u; ++column) {
+            if (((live >> (strip * 2u + column)) & 1u) == 0u) continue;
+            const uint32_t x = ox + column * 16u + qx;
+            const float pxa = (float)x, pxb = (float)(x + 1u);
+            const float c0a = mul(s.d12y, sub(pxa, s.x1)), c0b = mul(s.d12y, sub(pxb, s.x1));
+            const float c1a = mul(s.d20y, sub(pxa, s.x2)), c1b = mul(s.d20y, sub(pxb, s.x2));
+            const float c2a = mul(s.d01y, sub(pxa, s.x0)), c2b = mul(s.d01y, sub(pxb, s.x0));
+            float e0[4], e1[4], e2[4]; // (xa,ya) (xb,ya) (xa,yb) (xb,yb)
+            e0[0] = sub(a0a, c0a); e0[1] = sub(a0a, c0b); e0[2] = sub(a0b, c0a); e0[3] = sub(a0b, c0b);
+            e1[0] = sub(a1a, c1a); e1[1] = sub(a1a, c1b); e1[2] = sub(a1b, c1a); e1[3] = sub(a1b, c1b);
+            e2[0] = sub(a2a, c2a); e2[1] = sub(a2a, c2b); e2[2] = sub(a2b, c2a); e2[3] = sub(a2b, c2b);
+            const uint32_t inrect = ymask & (((x >= rx0 && x <= rx1) ? 5u : 0u) | ((x + 1u >= rx0 && x + 1u <= rx1) ? 10u : 0u));
+            uint32_t mask = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (candidate(s, e0[k], e1[k], e2[k])) mask |= 1u << k;
+            mask &= inrect;
+            if (!__any_sync(0xFFFFFFFFu, mask != 0u)) continue;
+            // Early depth rejection.  z_est approximates the fragment depth to within z_margin
+            // (|z_est - z| <= (2^-22 + 8 ulp) * max|z_k| < z_margin / 2 for a candidate pixel), and a stored depth
+            // only ever decreases, so "z_est > stored + margin" proves the exact depth would lose the atomicMin:
+            // the divisions and the atomic are skipped.  Stale reads and NaNs fall through to the exact path.
+            unsigned long long *pix0 = TILE_MODE ? tile_keys + (strip * 8u + qy) * TILE + column * 16u + qx : vis + (size_t)(y - vw.y0) * vw.W + x;
+            const size_t row_stride = TILE_MODE ? (size_t)TILE : (size_t)vw.W;
+            if (TILE_MODE || early_z) {
+                uint32_t cur_hi[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { // all four reads in flight together (global: L2, bypassing L1)
+                    const uint32_t *hi = reinterpret_cast<const uint32_t *>(pix0 + (k >> 1) * row_stride + (k & 1)) + 1;
+                    cur_hi[k] = (mask & (1u << k)) ? (TILE_MODE ? *reinterpret_cast<const volatile uint32_t *>(hi) : __ldcg(hi)) : 0xFFFFFFFFu;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float z_est = fmaf(s.z2, e2[k], fmaf(s.z1, e1[k], s.z0 * e0[k])) * rcp_area;
+                    const uint32_t cur_bits = (cur_hi[k] & 0x80000000u) ? (cur_hi[k] ^ 0x80000000u) : ~cur_hi[k]; // inverse of depth_key
+                    if (cur_hi[k] != 0xFFFFFFFFu && z_est > __uint_as_float(cur_bits) + z_margin) mask &= ~(1u << k);
+                }
+                if (!__any_sync(0xFFFFFFFFu, mask != 0u)) continue;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (mask & (1u << k)) {
+                    float b0, b1, b2, z;
+                    if (fragment(s, e0[k], e1[k], e2[k], b0, b1, b2, z)) {
+                        const unsigned long long key = ((unsigned long long)depth_key(z) << 32) | tri;
+                        atomicMin(pix0 + (k >> 1) * row_stride + (k & 1), key);
+                    }
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_chunks(Scene sc, View vw, Batch bt) {
     __shared__ StagedTris stage_all[RASTER_WARPS];
+    if (bt.counters[CNT_TILE_MODE] != 0ull) return; // this batch is rasterised by k_raster_tiles
     StagedTris &stg = stage_all[threadIdx.x >> 5];
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t count = (uint32_t)min(bt.counters[0], (unsigned long long)bt.queue_cap);
-    const uint32_t qx = (lane & 7u) * 2u, qy = (lane >> 3) * 2u;
+    const uint32_t count = (uint32_t)min(bt.counters[CNT_QUEUE], (unsigned long long)bt.queue_cap);
     // items per grab: 32 when the queue is long (amortises the fetch latency), fewer when it is short so that
     // a small frame still spreads over the whole grid instead of over count/32 warps
     const uint32_t n_warps = gridDim.x * RASTER_WARPS;
     const uint32_t take = max(1u, min(32u, count / n_warps));
     // Early depth rejection pays only when fragments mostly lose: it is switched on when the queued bbox area
     // exceeds EARLY_Z_OVERDRAW times the pixels of the batch (bboxes are about twice the covered area).
-    const bool early_z = bt.counters[3] > (unsigned long long)EARLY_Z_OVERDRAW * vw.band_pixels * bt.n_frames;
+    const bool early_z = bt.counters[CNT_BBOX_AREA] > (unsigned long long)EARLY_Z_OVERDRAW * vw.band_pixels * bt.n_frames;
     for (;;) {
         uint32_t base = 0;
-        if (lane == 0) base = (uint32_t)min(atomicAdd(&bt.counters[1], (unsigned long long)take), 0xFFFFFFFFull);
+        if (lane == 0) base = (uint32_t)min(atomicAdd(&bt.counters[CNT_CURSOR], (unsigned long long)take), 0xFFFFFFFFull);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= count) break;
         const uint32_t n_items = min(take, count - base);
 
-        // ---- stage: lane = item ----
-        {
-            uint32_t tri = INVALID_TRI, rect0 = 0, rect1 = 0, f = 0;
-            TriSetup s = {};
-            s.literal = true;
+        {   // ---- stage: lane = item ----
+            uint32_t tri = INVALID_TRI, f = 0, rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;
             if (lane < n_items) {
                 const uint2 item = bt.queue[base + lane];
                 tri = item.x;
@@ -364,128 +527,110 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_chunks(Scene sc, V
                     const uint32_t cx = item.y & 0xFFFu, cy = (item.y >> 12) & 0xFFFu;
                     f = item.y >> 24;
                     const float4 *rv = bt.rv + (size_t)f * sc.V;
-                    const float4 v0 = rv[sc.vidx0[tri]], v1 = rv[sc.vidx1[tri]], v2 = rv[sc.vidx2[tri]];
+                    v0 = rv[sc.vidx0[tri]]; v1 = rv[sc.vidx1[tri]]; v2 = rv[sc.vidx2[tri]];
                     const BBox bb = bounding_box(v0, v1, v2, vw);
-                    tri_setup(s, v0, v1, v2);
-                    const uint32_t rx0 = bb.x0 + cx * CHUNK, ry0 = bb.y0 + cy * CHUNK;
-                    const uint32_t rx1 = min(bb.x1, rx0 + CHUNK - 1u), ry1 = min(bb.y1, ry0 + CHUNK - 1u);
-                    rect0 = rx0 | (ry0 << 16);
-                    rect1 = rx1 | (ry1 << 16);
+                    rx0 = bb.x0 + cx * CHUNK; ry0 = bb.y0 + cy * CHUNK;
+                    rx1 = min(bb.x1, rx0 + CHUNK - 1u); ry1 = min(bb.y1, ry0 + CHUNK - 1u);
                 }
             }
-            const float fl[16] = {s.x0, s.y0, s.x1, s.y1, s.x2, s.y2, s.z0, s.z1, s.z2, s.d12x, s.d12y, s.d20x, s.d20y, s.d01x, s.d01y, s.area};
-#pragma unroll
-            for (int k = 0; k < 16; ++k) stg.w[k][lane] = __float_as_uint(fl[k]);
-            stg.w[16][lane] = s.literal ? 1u : 0u;
-            stg.w[17][lane] = rect0;
-            stg.w[18][lane] = rect1;
-            stg.w[19][lane] = tri;
-            stg.w[20][lane] = f;
-            // early depth rejection (see below): 1/area and an error margin, both only used to SKIP work
-            const float zmax = fmaxf(fmaxf(fabsf(s.z0), fabsf(s.z1)), fabsf(s.z2));
-            const float rcp = 1.0f / s.area;
-            const bool usable = !s.literal && rcp > 0.f && rcp < __int_as_float(0x7f800000) && zmax < __int_as_float(0x7f800000);
-            stg.w[21][lane] = __float_as_uint(usable ? rcp : 0.f);
-            stg.w[22][lane] = __float_as_uint(usable ? fmaf(zmax, 1.9073486328125e-06f /* 2^-19 */, 1e-37f) : __int_as_float(0x7f800000));
-            // which of the chunk's 4 x 2 blocks can contain a candidate pixel at all (bit = strip * 2 + column)
-            uint32_t live = 0xFFu;
-            if (tri != INVALID_TRI && !s.literal) {
-                const uint32_t rx0 = rect0 & 0xFFFFu, ry0 = rect0 >> 16, rx1 = rect1 & 0xFFFFu, ry1 = rect1 >> 16;
-#pragma unroll
-                for (uint32_t b = 0; b < 8u; ++b) {
-                    const uint32_t bx0 = rx0 + (b & 1u) * 16u, by0 = ry0 + (b >> 1) * 8u;
-                    if (bx0 > rx1 || by0 > ry1) continue;
-                    const float xa = (float)bx0, xb = (float)min(bx0 + 15u, rx1), ya = (float)by0, yb = (float)min(by0 + 7u, ry1);
-                    if (block_outside_edge(s.d12x, s.d12y, s.x1, s.y1, xa, xb, ya, yb) || block_outside_edge(s.d20x, s.d20y, s.x2, s.y2, xa, xb, ya, yb) ||
-                        block_outside_edge(s.d01x, s.d01y, s.x0, s.y0, xa, xb, ya, yb))
-                        live &= ~(1u << b);
-                }
-            }
-            stg.w[23][lane] = live;
+            stage_item(stg, lane, tri, f, v0, v1, v2, rx0, ry0, rx1, ry1, rx0, ry0);
         }
         __syncwarp();
+        for (uint32_t it = 0; it < n_items; ++it) raster_item<false>(stg, it, lane, vw, bt.vis, nullptr, early_z);
+        __syncwarp();
+    }
+}
 
-        // ---- rasterise: warp = item, lane = 2x2 quad ----
-        for (uint32_t it = 0; it < n_items; ++it) {
-            const uint32_t tri = stg.w[19][it];
-            if (tri == INVALID_TRI) continue;
-            TriSetup s;
-            s.x0 = __uint_as_float(stg.w[0][it]); s.y0 = __uint_as_float(stg.w[1][it]);
-            s.x1 = __uint_as_float(stg.w[2][it]); s.y1 = __uint_as_float(stg.w[3][it]);
-            s.x2 = __uint_as_float(stg.w[4][it]); s.y2 = __uint_as_float(stg.w[5][it]);
-            s.z0 = __uint_as_float(stg.w[6][it]); s.z1 = __uint_as_float(stg.w[7][it]); s.z2 = __uint_as_float(stg.w[8][it]);
-            s.d12x = __uint_as_float(stg.w[9][it]); s.d12y = __uint_as_float(stg.w[10][it]);
-            s.d20x = __uint_as_float(stg.w[11][it]); s.d20y = __uint_as_float(stg.w[12][it]);
-            s.d01x = __uint_as_float(stg.w[13][it]); s.d01y = __uint_as_float(stg.w[14][it]);
-            s.area = __uint_as_float(stg.w[15][it]);
-            s.literal = stg.w[16][it] != 0u;
-            const float rcp_area = __uint_as_float(stg.w[21][it]), z_margin = __uint_as_float(stg.w[22][it]);
-            const uint32_t rect0 = stg.w[17][it], rect1 = stg.w[18][it];
-            const uint32_t rx0 = rect0 & 0xFFFFu, ry0 = rect0 >> 16, rx1 = rect1 & 0xFFFFu, ry1 = rect1 >> 16;
-            unsigned long long *vis = bt.vis + (size_t)stg.w[20][it] * vw.band_pixels;
-            const uint32_t live = stg.w[23][it];
-            if (live == 0u) continue;
+// ---- screen-tile binning ----------------------------------------------------------------------
+// Single CTA: decides whether this batch takes the binned schedule and, if so, turns the per-tile counts into
+// run offsets.  Falls back to the chunk schedule when the list or the item array would overflow.
+__global__ void __launch_bounds__(1024) k_plan_tiles(Batch bt, TileBins tb) {
+    __shared__ uint32_t partial[1024];
+    const uint32_t n = bt.n_frames * tb.tiles_x * tb.tiles_y;
+    const uint32_t per = (n + 1023u) / 1024u;
+    const uint32_t lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; ++i) { sum += tb.count[i]; tb.fill[i] = 0u; }
+    partial[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024u; d <<= 1) { // Hillis-Steele inclusive scan of the 1024 partial sums
+        const uint32_t v = threadIdx.x >= d ? partial[threadIdx.x - d] : 0u;
+        __syncthreads();
+        partial[threadIdx.x] += v;
+        __syncthreads();
+    }
+    const unsigned long long total = partial[1023];
+    const bool ok = bt.counters[CNT_LIST] <= tb.list_cap && total <= tb.items_cap;
+    uint32_t run = threadIdx.x ? partial[threadIdx.x - 1] : 0u;
+    for (uint32_t i = lo; i < hi; ++i) { tb.start[i] = run; run += tb.count[i]; }
+    if (threadIdx.x == 0) {
+        bt.counters[CNT_TILE_ITEMS] = total;
+        bt.counters[CNT_TILE_MODE] = ok ? 1ull : 0ull;
+        if (!ok) bt.counters[CNT_TILE_OVERFLOW] = 1ull;
+    }
+}
 
-            for (uint32_t by = ry0, strip = 0; by <= ry1; by += 8u, ++strip) {
-                using namespace exact;
-                if (((live >> (strip * 2u)) & 3u) == 0u) continue;
-                const uint32_t y = by + qy;
-                const float pya = (float)y, pyb = (float)(y + 1u);
-                // edge k at pixel (i,j): mul(dkx, py_j - yk) - mul(dky, px_i - xk)
-                const float a0a = mul(s.d12x, sub(pya, s.y1)), a0b = mul(s.d12x, sub(pyb, s.y1));
-                const float a1a = mul(s.d20x, sub(pya, s.y2)), a1b = mul(s.d20x, sub(pyb, s.y2));
-                const float a2a = mul(s.d01x, sub(pya, s.y0)), a2b = mul(s.d01x, sub(pyb, s.y0));
-                const uint32_t ymask = (y <= ry1 ? 3u : 0u) | (y + 1u <= ry1 ? 12u : 0u);
-                for (uint32_t bx = rx0, column = 0; bx <= rx1; bx += 16u, ++column) {
-                    if (((live >> (strip * 2u + column)) & 1u) == 0u) continue;
-                    const uint32_t x = bx + qx;
-                    const float pxa = (float)x, pxb = (float)(x + 1u);
-                    const float c0a = mul(s.d12y, sub(pxa, s.x1)), c0b = mul(s.d12y, sub(pxb, s.x1));
-                    const float c1a = mul(s.d20y, sub(pxa, s.x2)), c1b = mul(s.d20y, sub(pxb, s.x2));
-                    const float c2a = mul(s.d01y, sub(pxa, s.x0)), c2b = mul(s.d01y, sub(pxb, s.x0));
-                    float e0[4], e1[4], e2[4]; // (xa,ya) (xb,ya) (xa,yb) (xb,yb)
-                    e0[0] = sub(a0a, c0a); e0[1] = sub(a0a, c0b); e0[2] = sub(a0b, c0a); e0[3] = sub(a0b, c0b);
-                    e1[0] = sub(a1a, c1a); e1[1] = sub(a1a, c1b); e1[2] = sub(a1b, c1a); e1[3] = sub(a1b, c1b);
-                    e2[0] = sub(a2a, c2a); e2[1] = sub(a2a, c2b); e2[2] = sub(a2b, c2a); e2[3] = sub(a2b, c2b);
-                    const uint32_t inrect = ymask & ((x <= rx1 ? 5u : 0u) | (x + 1u <= rx1 ? 10u : 0u));
-                    uint32_t mask = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (candidate(s, e0[k], e1[k], e2[k])) mask |= 1u << k;
-                    mask &= inrect;
-                    if (!__any_sync(0xFFFFFFFFu, mask != 0u)) continue;
-                    // Early depth rejection.  z_est approximates the fragment depth to within z_margin
-                    // (|z_est - z| <= (2^-22 + 8 ulp) * max|z_k| < z_margin / 2 for a candidate pixel), and a stored depth
-                    // only ever decreases, so "z_est > stored + margin" proves the exact depth would lose the atomicMin:
-                    // the divisions and the atomic are skipped.  Stale reads and NaNs fall through to the exact path.
-                    unsigned long long *pix0 = vis + (size_t)(y - vw.y0) * vw.W + x;
-                    if (early_z) {
-                        uint32_t cur_hi[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) // all four loads in flight together (L2, bypassing L1)
-                            cur_hi[k] = (mask & (1u << k)) ? __ldcg(reinterpret_cast<const uint32_t *>(pix0 + (k >> 1) * (size_t)vw.W + (k & 1)) + 1) : 0xFFFFFFFFu;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float z_est = fmaf(s.z2, e2[k], fmaf(s.z1, e1[k], s.z0 * e0[k])) * rcp_area;
-                            const uint32_t cur_bits = (cur_hi[k] & 0x80000000u) ? (cur_hi[k] ^ 0x80000000u) : ~cur_hi[k]; // inverse of depth_key
-                            if (cur_hi[k] != 0xFFFFFFFFu && z_est > __uint_as_float(cur_bits) + z_margin) mask &= ~(1u << k);
-                        }
-                        if (!__any_sync(0xFFFFFFFFu, mask != 0u)) continue;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (mask & (1u << k)) {
-                            float b0, b1, b2, z;
-                            if (fragment(s, e0[k], e1[k], e2[k], b0, b1, b2, z)) {
-                                const unsigned long long key = ((unsigned long long)depth_key(z) << 32) | tri;
-                                atomicMin(pix0 + (k >> 1) * (size_t)vw.W + (k & 1), key);
-                            }
-                        }
-                    }
-                }
+// One thread per queued triangle: its id goes into the run of every tile its bbox touches.
+__global__ void __launch_bounds__(256) k_fill_tiles(Scene sc, View vw, Batch bt, TileBins tb) {
+    if (bt.counters[CNT_TILE_MODE] == 0ull) return;
+    const uint32_t n = (uint32_t)min(bt.counters[CNT_LIST], (unsigned long long)tb.list_cap);
+    const uint32_t tiles = tb.tiles_x * tb.tiles_y;
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const uint2 ent = tb.list[e];
+        const float4 *rv = bt.rv + (size_t)ent.y * sc.V;
+        const BBox bb = bounding_box(rv[sc.vidx0[ent.x]], rv[sc.vidx1[ent.x]], rv[sc.vidx2[ent.x]], vw);
+        const uint32_t tx0 = bb.x0 / TILE, tx1 = bb.x1 / TILE, ty0 = (bb.y0 - vw.y0) / TILE, ty1 = (bb.y1 - vw.y0) / TILE;
+        for (uint32_t ty = ty0; ty <= ty1; ++ty)
+            for (uint32_t tx = tx0; tx <= tx1; ++tx) {
+                const uint32_t g = ent.y * tiles + ty * tb.tiles_x + tx;
+                tb.items[tb.start[g] + atomicAdd(&tb.fill[g], 1u)] = ent.x;
             }
+    }
+}
+
+// One CTA per (tile, frame): the tile's keys live in shared memory until every triangle of the bin is done.
+__global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_tiles(Scene sc, View vw, Batch bt, TileBins tb) {
+    __shared__ StagedTris stage_all[RASTER_WARPS];
+    __shared__ unsigned long long tile_keys[TILE * TILE];
+    if (bt.counters[CNT_TILE_MODE] == 0ull) return;
+    const uint32_t f = blockIdx.y, tile = blockIdx.x;
+    const uint32_t g = f * tb.tiles_x * tb.tiles_y + tile;
+    const uint32_t n = tb.count[g];
+    if (n == 0u) return;
+    const uint32_t first = tb.start[g];
+    const uint32_t ox = (tile % tb.tiles_x) * TILE, oy = vw.y0 + (tile / tb.tiles_x) * TILE;
+    for (uint32_t i = threadIdx.x; i < TILE * TILE; i += blockDim.x) tile_keys[i] = VIS_EMPTY;
+    __syncthreads();
+
+    StagedTris &stg = stage_all[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const float4 *rv = bt.rv + (size_t)f * sc.V;
+    for (uint32_t base = warp * 32u; base < n; base += RASTER_WARPS * 32u) {
+        const uint32_t n_items = min(32u, n - base);
+        {   // ---- stage: lane = item ----
+            uint32_t tri = INVALID_TRI, rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;
+            if (lane < n_items) {
+                tri = tb.items[first + base + lane];
+                v0 = rv[sc.vidx0[tri]]; v1 = rv[sc.vidx1[tri]]; v2 = rv[sc.vidx2[tri]];
+                const BBox bb = bounding_box(v0, v1, v2, vw);
+                rx0 = max(bb.x0, ox); ry0 = max(bb.y0, oy);
+                rx1 = min(bb.x1, ox + TILE - 1u); ry1 = min(bb.y1, oy + TILE - 1u);
+                if (rx0 > rx1 || ry0 > ry1) tri = INVALID_TRI;
+            }
+            stage_item(stg, lane, tri, f, v0, v1, v2, rx0, ry0, rx1, ry1, ox, oy);
         }
         __syncwarp();
+        for (uint32_t it = 0; it < n_items; ++it) raster_item<true>(stg, it, lane, vw, nullptr, tile_keys, true);
+        __syncwarp();
+    }
+    __syncthreads();
+    // merge the tile into the visibility buffer (tiny triangles were written there directly by k_setup)
+    unsigned long long *vis = bt.vis + (size_t)f * vw.band_pixels;
+    for (uint32_t i = threadIdx.x; i < TILE * TILE; i += blockDim.x) {
+        const unsigned long long key = tile_keys[i];
+        const uint32_t x = ox + (i % TILE), y = oy + (i / TILE);
+        if (key != VIS_EMPTY && x < vw.W && y < vw.y1) atomicMin(vis + (size_t)(y - vw.y0) * vw.W + x, key);
     }
 }
 

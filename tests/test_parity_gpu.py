@@ -238,3 +238,46 @@ def test_renderer_cli_writes_reference_images(tmp_path):
     # errors: missing -l, unreadable model
     assert subprocess.run([exe, "-o", "x.obj"], capture_output=True).returncode == 1
     assert subprocess.run([exe, "-o", "/nonexistent.obj", "-l", os.path.join(S.DATA, "threepoint.csv")], capture_output=True).returncode == 1
+
+
+@pytest.fixture
+def tile_mode(monkeypatch):
+    """Force the screen-tile binned raster schedule (RAST_RASTER_MODE=tile; the default is the chunk queue)."""
+    monkeypatch.setenv("RAST_RASTER_MODE", "tile")
+
+
+@pytest.mark.parametrize("name", ["suzanne_640x480_pose1", "suzanne_640x480_dz2.2", "suzanne_257x129", "suzanne_1x37", "plane_640x480_threepoint", "suzanne_1920x1080"])
+def test_tile_binned_schedule_golden(name, tile_mode):
+    case = [c for c in CASES if c["name"] == name][0]
+    r = make_renderer(S.scene(case["scene"]), S.lights(case["lights"]))
+    try:
+        got = gpu_draw(r, S.case_args(case))
+        assert orc.fnv(got[0]) == case["frame_fnv"] and orc.fnv(got[1]) == case["depth_fnv"]
+        assert_parity(got, orc.oracle_draw(S.scene(case["scene"]), S.lights(case["lights"]), S.case_args(case)), name + " (tile bins)")
+    finally:
+        r.close()
+
+
+@pytest.mark.parametrize("seed,n_tris,size,cw", [(2, 40, (64, 48), False), (3, 120, (257, 129), True), (7, 150, (128, 128), True), (10, 3000, (320, 200), False)])
+def test_tile_binned_schedule_soups_bands_and_batches(seed, n_tris, size, cw, tile_mode):
+    scene = S.random_soup(seed, n_tris)
+    lights = S.random_lights(seed, 3)
+    oa = orc.make_args(size[0], size[1], scale=0.9, disp=(0.05, -0.03, 0.2), angles=(0.1 * seed, 0.37 * seed, -0.2), wind_clockwise=cw)
+    want = orc.oracle_draw(scene, lights, oa, threads=4)
+    r = make_renderer(scene, lights)
+    try:
+        assert_parity(gpu_draw(r, oa), want, "soup %d (tile bins)" % seed)
+        # a band whose edges cut through tiles
+        H = oa.image_height
+        y0, y1 = H // 3, min(H, H // 3 + max(1, H // 2))
+        r.set_band(y0, y1)
+        bf, bd = r.draw_frame(to_api_args(oa))
+        bt = r.triangle_ids(oa.image_width, y1 - y0)
+        assert np.array_equal(bf, want[0][:, y0:y1]) and np.array_equal(bd.view(np.uint32), want[1][y0:y1].view(np.uint32)) and np.array_equal(bt, want[2][y0:y1])
+        r.set_band(0, 0)
+        # several frames in one batch
+        frames, depths = r.draw_frames([to_api_args(oa)] * 3, want_depth=True)
+        for k in range(3):
+            assert np.array_equal(frames[k], want[0]) and np.array_equal(depths[k].view(np.uint32), want[1].view(np.uint32))
+    finally:
+        r.close()

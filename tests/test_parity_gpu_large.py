@@ -49,8 +49,11 @@ def test_config5_shape_tessellated_64_lights():
         r.close()
 
 
-def test_config4_shape_high_overdraw():
-    """Large overlapping triangles, depth complexity ~50: exercises the chunk queue, the early depth rejection and ties."""
+@pytest.mark.parametrize("mode", ["auto", "chunk", "tile"])
+def test_config4_shape_high_overdraw(mode, monkeypatch):
+    """Large overlapping triangles, depth complexity ~50: exercises both raster schedules (chunk queue with early
+    depth rejection; screen-tile bins, which "auto" switches to on the second call) and ties."""
+    monkeypatch.setenv("RAST_RASTER_MODE", mode)
     W, H = 1920, 1080
     pos, nrm, uv, tris = synth.overdraw_scene(12000, W, H, radius_px=80.0)
     scene = orc.Scene(pos, nrm, uv, tris, [{"kd": (0.8, 0.8, 0.8), "texels": None}])
