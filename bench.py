@@ -350,6 +350,21 @@ def main():
                "h2d_bytes_per_step": int(n * 144 + len(chunks) * len(wl["lights"]) * 32), "d2h_bytes_per_step": int(n * 7 * P),
                "note": "rast_draw_frames with pinned host outputs, %d frames per call: RGB8 + f32 depth of every frame copied D2H inside the timed region (wall clock, max over ranks)" % chunk}
         checksum = int(frames_host[len(chunks[-1]) // 2].astype(np.uint64).sum())
+        # the same with colour only (the reference's spin loop shows frames; its depth buffer is scratch)
+        def step_host_rgb():
+            for c in chunks:
+                r.draw_frames(c, frames_host[:len(c)], None)
+        step_host_rgb()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(opts.steps):
+            step_host_rgb()
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e["frames_only"] = {"value": (1 if band_mode else world) * n * opts.steps / float(t.item()), "d2h_bytes_per_step": int(n * 3 * P),
+                              "note": "same call with depths=NULL: only the RGB8 frames cross PCIe"}
         lib.rast_host_free(fb)
         lib.rast_host_free(db)
     else:

@@ -1,0 +1,94 @@
+"""The parts of the C ABI the parity tests do not reach: device-pointer outputs on a caller-owned stream,
+profiling, launch counting, statistics.  Needs a B200: `-m gpu`."""
+import numpy as np
+import pytest
+
+import orc
+import scenes as S
+from gpu_common import make_renderer, to_api_args
+from rasteriser_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+
+def test_device_outputs_on_a_torch_stream_equal_host_outputs():
+    import torch
+    r = make_renderer(S.scene("suzanne"), S.lights("threepoint"))
+    try:
+        W, H, n = 320, 240, 5
+        poses = [api.Args(W, H, tait_bryan_angles=(0.1, api.spin_angle(0.3, k, n), 0.0)) for k in range(n)]
+        host_frames, host_depths = r.draw_frames(poses, want_depth=True)
+        stream = torch.cuda.Stream()
+        r.set_stream(stream.cuda_stream)
+        frames = torch.zeros((n, 3, H, W), dtype=torch.uint8, device="cuda")
+        depths = torch.zeros((n, H, W), dtype=torch.float32, device="cuda")
+        with torch.cuda.stream(stream):
+            r.draw_frames_device(poses, frames.data_ptr(), depths.data_ptr())
+            total = frames.sum()          # consumer ordered after the kernels on the same stream
+        stream.synchronize()
+        assert np.array_equal(frames.cpu().numpy(), host_frames)
+        assert np.array_equal(depths.cpu().numpy().view(np.uint32), host_depths.view(np.uint32))
+        assert int(total) == int(host_frames.astype(np.uint64).sum())
+        # frames only (depths = NULL), then back to the context's own stream
+        frames.zero_()
+        r.draw_frames_device(poses, frames.data_ptr(), None)
+        r.sync()
+        assert np.array_equal(frames.cpu().numpy(), host_frames)
+        r.use_own_stream()
+        f1, _ = r.draw_frame(poses[2])
+        assert np.array_equal(f1, host_frames[2])
+        r.set_stream(0)                   # the legacy default stream is a valid choice too
+        f2, _ = r.draw_frame(poses[3])
+        assert np.array_equal(f2, host_frames[3])
+    finally:
+        r.close()
+
+
+def test_profiling_launch_count_and_stats():
+    scene, lights = S.scene("suzanne"), S.lights("threepoint")
+    r = make_renderer(scene, lights)
+    try:
+        oa = orc.make_args(640, 480)
+        l0 = r.launch_count()
+        r.set_profiling(True)
+        r.draw_frame(to_api_args(oa))
+        ms = r.pass_ms()
+        r.set_profiling(False)
+        assert set(ms) == {"clear", "vertex", "setup", "raster", "shade"}
+        assert ms["vertex"] > 0 and ms["setup"] > 0 and ms["raster"] > 0 and ms["shade"] > 0 and sum(ms.values()) < 50
+        assert r.launch_count() - l0 >= 4   # vertex, setup, raster, shade (+ clear when the slot is not known empty)
+        st = r.stats()
+        _, _, tri, cnt = orc.oracle_draw(scene, lights, oa, want_counters=True)
+        assert st["triangles"] == 968 and st["front_facing"] == cnt.front_facing == 614
+        assert st["visible_pixels"] == int((tri != orc.NO_TRIANGLE).sum()) == 109438
+        assert st["queued_chunks"] > 0
+    finally:
+        r.close()
+
+
+def test_depth_to_u8_matches_cimg_normalisation():
+    r = make_renderer(S.scene("suzanne"), S.lights("threepoint"))
+    try:
+        for kw in (dict(), dict(disp=(0, 0, 2.0)), dict(disp=(5.0, 0, 0))):   # usual, negative NDC depth, empty frame (min == max)
+            oa = orc.make_args(200, 120, **kw)
+            _, depth = r.draw_frame(to_api_args(oa))
+            want = np.zeros(depth.shape, np.uint8)
+            orc.oracle().orc_depth_to_u8(orc.ptr(depth), depth.size, orc.ptr(want))
+            assert np.array_equal(r.depth_to_u8(200, 120), want)
+    finally:
+        r.close()
+
+
+def test_two_contexts_are_independent():
+    a = make_renderer(S.scene("suzanne"), S.lights("threepoint"))
+    b = make_renderer(S.scene("plane"), S.lights("normalmap"))
+    try:
+        fa, _ = a.draw_frame(api.Args(160, 120))
+        fb, _ = b.draw_frame(api.Args(96, 64, tait_bryan_angles=(0.9, 0.3, 0.0)))
+        fa2, _ = a.draw_frame(api.Args(160, 120))
+        assert np.array_equal(fa, fa2) and fa.shape != fb.shape
+        z = np.load(S.GOLDEN + "/small_frames.npz")
+        assert np.array_equal(fa, z["suzanne_160x120_frame"])
+    finally:
+        a.close()
+        b.close()
