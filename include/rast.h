@@ -150,6 +150,10 @@ int rast_set_profiling(rast_ctx *ctx, int enabled);
 int rast_get_pass_ms(rast_ctx *ctx, float ms[RAST_PASS_COUNT]);
 /* number of kernel launches issued by this context since creation */
 uint64_t rast_launch_count(const rast_ctx *ctx);
+/* Diagnostic: the kernels divide several numerators by one divisor with a shared reciprocal (the compiler's
+ * own div.rn.f32 fast-path sequence, csrc/exact.cuh).  This compares that against IEEE division on the GPU
+ * for about n_samples pseudo-random quotients and returns how many differ in any bit (expected: 0). */
+int rast_selftest_division(rast_ctx *ctx, uint64_t n_samples, uint64_t seed, uint64_t *mismatches);
 
 /* pinned host memory for frame / depth buffers */
 void *rast_host_alloc(uint64_t bytes);

@@ -208,6 +208,12 @@ class Renderer:
     def launch_count(self):
         return int(self._lib.rast_launch_count(self._h))
 
+    def selftest_division(self, n_samples=1 << 30, seed=1):
+        """Quotients (out of ~n_samples) where the shared-reciprocal division differs from IEEE division: expected 0."""
+        bad = C.c_uint64(0)
+        self._check(self._lib.rast_selftest_division(self._h, int(n_samples), int(seed), C.byref(bad)), "rast_selftest_division")
+        return int(bad.value)
+
     def light_trans_dirs(self):
         return np.array([list(self._lights[i].trans_dir) for i in range(self.n_lights)], np.float32)
 

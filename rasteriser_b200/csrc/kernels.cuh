@@ -104,6 +104,8 @@ struct TriSetup {
     float z0, z1, z2;
     float d12x, d12y, d20x, d20y, d01x, d01y; // the pixel-invariant differences of edge() (drawing.cpp:38), times sign(area)
     float area;                               // |edge(v2; v0, v1)| (drawing.cpp:46)
+    float rcp1;                               // exact::div_reciprocal(area), for the shared-divisor quotients
+    bool div_ok;                              // exact::div_in_range(area)
     bool literal;                             // area is 0, inf or NaN: no sign shortcut
 };
 
@@ -123,6 +125,8 @@ __device__ __forceinline__ void tri_setup(TriSetup &s, const float4 &v0, const f
         s.d12x = -s.d12x; s.d12y = -s.d12y; s.d20x = -s.d20x; s.d20y = -s.d20y; s.d01x = -s.d01x; s.d01y = -s.d01y;
         s.area = -s.area;
     }
+    s.div_ok = exact::div_in_range(s.area);
+    s.rcp1 = exact::div_reciprocal(s.area);
 }
 
 // signed_area_2d (geometry.cpp:76-83), left to right
@@ -177,9 +181,7 @@ __device__ __forceinline__ bool candidate(const TriSetup &s, float e0, float e1,
 // and nearer than the cleared depth 1.0f (a fragment at z >= 1 or NaN can never pass the strict '<').
 __device__ __forceinline__ bool fragment(const TriSetup &s, float e0, float e1, float e2, float &b0, float &b1, float &b2, float &z) {
     using namespace exact;
-    b0 = div(e0, s.area);
-    b1 = div(e1, s.area);
-    b2 = div(e2, s.area);
+    div3(e0, e1, e2, s.area, s.rcp1, s.div_ok, b0, b1, b2);
     if (!(b0 >= 0.f && b1 >= 0.f && b2 >= 0.f)) return false;
     z = add(add(mul(s.z0, b0), mul(s.z1, b1)), mul(s.z2, b2));
     return z < 1.0f;
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(256) k_setup(const __grid_constant__ Scene sc,
 // Lanes own 2x2 pixel quads of a 16x8 block, so the per-pixel differences (p - a) and half of the products
 // of edge() are shared inside the quad; a ballot skips blocks no lane may cover.
 constexpr int RASTER_WARPS = 8;
-constexpr int STAGE_FIELDS = 25;
+constexpr int STAGE_FIELDS = 27;
 constexpr unsigned long long EARLY_Z_OVERDRAW = 6;
 
 // Conservative rejection of one 16x8 block (pixel extent [xa,xb] x [ya,yb]) against one sign-folded edge.
@@ -405,6 +407,8 @@ __device__ __forceinline__ void stage_item(StagedTris &stg, uint32_t lane, uint3
     }
     stg.w[23][lane] = live;
     stg.w[24][lane] = ox | (oy << 16);
+    stg.w[25][lane] = __float_as_uint(s.rcp1);
+    stg.w[26][lane] = s.div_ok ? 1u : 0u;
 }
 
 // Rasterise staged item `it` with the whole warp.  TILE_MODE = false: keys go to the visibility buffer `vis`
@@ -428,6 +432,8 @@ __device__ __forceinline__ void raster_item(const StagedTris &stg, uint32_t it, 
     s.d01x = __uint_as_float(stg.w[13][it]); s.d01y = __uint_as_float(stg.w[14][it]);
     s.area = __uint_as_float(stg.w[15][it]);
     s.literal = stg.w[16][it] != 0u;
+    s.rcp1 = __uint_as_float(stg.w[25][it]);
+    s.div_ok = stg.w[26][it] != 0u;
     const float rcp_area = __uint_as_float(stg.w[21][it]), z_margin = __uint_as_float(stg.w[22][it]);
     const uint32_t rect0 = stg.w[17][it], rect1 = stg.w[18][it], org = stg.w[24][it];
     const uint32_t rx0 = rect0 & 0xFFFFu, ry0 = rect0 >> 16, rx1 = rect1 & 0xFFFFu, ry1 = rect1 >> 16, ox = org & 0xFFFFu, oy = org >> 16;
@@ -703,7 +709,8 @@ __device__ __forceinline__ Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t
     const float e0 = sub(mul(sub(v2.x, v1.x), sub(py, v1.y)), mul(sub(v2.y, v1.y), sub(px, v1.x)));
     const float e1 = sub(mul(sub(v0.x, v2.x), sub(py, v2.y)), mul(sub(v0.y, v2.y), sub(px, v2.x)));
     const float e2 = sub(mul(sub(v1.x, v0.x), sub(py, v0.y)), mul(sub(v1.y, v0.y), sub(px, v0.x)));
-    const float b0 = div(e0, area), b1 = div(e1, area), b2 = div(e2, area);
+    float b0, b1, b2;
+    div3(e0, e1, e2, area, div_reciprocal(area), div_in_range(area), b0, b1, b2);
     out.depth = add(add(mul(v0.z, b0), mul(v1.z, b1)), mul(v2.z, b2));
 
     // interpolation_coords + camera-space depth (drawing.cpp:125-128)
@@ -846,6 +853,34 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View 
 }
 
 // ---- auxiliary kernels ----------------------------------------------------------------------
+// Self-test of exact::div3 against __fdiv_rn: pseudo-random operand pairs (xorshift), exponents spread over and
+// beyond the guarded range, mantissas biased towards the patterns that stress rounding (all ones, single bits,
+// near powers of two).  Counts quotients whose bits differ.
+__global__ void k_selftest_division(unsigned long long samples_per_thread, unsigned long long seed, unsigned long long *mismatches) {
+    unsigned long long x = seed ^ (0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1ull));
+    unsigned long long bad = 0;
+    auto next = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    auto make = [&](unsigned long long r) {
+        uint32_t mant = (uint32_t)(r >> 8) & 0x7FFFFFu;
+        const uint32_t style = (uint32_t)(r >> 40) & 7u;
+        if (style == 0u) mant = 0x7FFFFFu ^ ((uint32_t)(r >> 44) & 0xFu);      // all ones, last bits flipped
+        else if (style == 1u) mant = 1u << ((uint32_t)(r >> 44) % 23u);          // a single bit
+        else if (style == 2u) mant = (uint32_t)(r >> 44) & 0xFu;                  // just above a power of two
+        const uint32_t expo = 127u - 60u + (uint32_t)((r >> 48) % 121ull);       // 2^-60 .. 2^60
+        return __uint_as_float(((uint32_t)(r >> 63) << 31) | (expo << 23) | mant);
+    };
+    for (unsigned long long i = 0; i < samples_per_thread; ++i) {
+        const float b = make(next()), a0 = make(next()), a1 = make(next());
+        const float a2 = (i & 63ull) == 0ull ? 0.0f : make(next()); // zeros take the fallback path
+        float q0, q1, q2;
+        exact::div3(a0, a1, a2, b, exact::div_reciprocal(b), exact::div_in_range(b), q0, q1, q2);
+        bad += __float_as_uint(q0) != __float_as_uint(__fdiv_rn(a0, b));
+        bad += __float_as_uint(q1) != __float_as_uint(__fdiv_rn(a1, b));
+        bad += __float_as_uint(q2) != __float_as_uint(__fdiv_rn(a2, b));
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 // tri_rec[3t+2].z holds the caller's material index; .y becomes the index the shade pass uses:
 // materials[face.material] (drawing.cpp:173), with -1 / out of range mapped to the sentinel.
 __global__ void k_resolve_materials(int4 *tri_rec, uint64_t n_tris, uint32_t n_materials) {

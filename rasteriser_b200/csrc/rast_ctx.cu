@@ -753,6 +753,23 @@ int rast_get_pass_ms(rast_ctx *ctx, float ms[RAST_PASS_COUNT]) {
 
 uint64_t rast_launch_count(const rast_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int rast_selftest_division(rast_ctx *ctx, uint64_t n_samples, uint64_t seed, uint64_t *mismatches) {
+    if (!ctx || !mismatches) return RAST_EINVAL;
+    RAST_CUDA(ctx, cudaSetDevice(ctx->device));
+    RAST_CUDA(ctx, ctx->d_aux.reserve(64));
+    unsigned long long *cnt = ctx->d_aux.as<unsigned long long>();
+    RAST_CUDA(ctx, cudaMemsetAsync(cnt, 0, 8, ctx->stream));
+    const unsigned threads = 148u * 8u * 256u;
+    const unsigned long long per_thread = (n_samples / 3 + threads - 1) / threads; // three quotients per sample triple
+    rk::k_selftest_division<<<148 * 8, 256, 0, ctx->stream>>>(per_thread ? per_thread : 1ull, seed, cnt);
+    ctx->launches++;
+    unsigned long long host = 0;
+    RAST_CUDA(ctx, cudaMemcpyAsync(&host, cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *mismatches = host;
+    return RAST_OK;
+}
+
 void *rast_host_alloc(uint64_t bytes) {
     void *p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;

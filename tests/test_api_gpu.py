@@ -92,3 +92,14 @@ def test_two_contexts_are_independent():
     finally:
         a.close()
         b.close()
+
+
+def test_shared_reciprocal_division_is_ieee_exact():
+    """exact::div3 (three quotients by one divisor, the compiler's div.rn fast-path sequence with the reciprocal
+    hoisted) against __fdiv_rn on 2^33 pseudo-random quotients incl. rounding-stress mantissas: no bit may differ."""
+    r = api.Renderer(0)
+    try:
+        assert r.selftest_division(1 << 33, seed=12345) == 0
+        assert r.selftest_division(1 << 30, seed=987654321) == 0
+    finally:
+        r.close()
