@@ -19,7 +19,12 @@ namespace rk {
 constexpr unsigned long long VIS_EMPTY = ~0ull;
 constexpr uint32_t INVALID_TRI = 0xFFFFFFFFu;
 constexpr int CHUNK = 32;                   // a queued work item covers <= CHUNK x CHUNK pixels of a triangle's bbox
-constexpr uint32_t TINY_MAX_PIXELS = 16;    // bboxes up to this many pixels are rasterised by the setup thread itself
+// Bbox size (pixels) up to which the setup thread rasterises a triangle itself instead of queueing it.  Measured on
+// B200: 8 M-triangle mesh at 4K: 16 -> 0.64 ms/frame, 32 -> 0.42, 64 -> 0.39 (queueing a small bbox costs more than
+// walking it); a 968-triangle frame at 640x480 prefers 16 (queued bboxes run in parallel).  The context picks
+// clamp(T / 16384, TINY_MIN_PIXELS, TINY_MAX_PIXELS) at upload.
+constexpr uint32_t TINY_MIN_PIXELS = 16;
+constexpr uint32_t TINY_MAX_PIXELS = 64;
 constexpr float EDGE_SLACK = 2.384185791015625e-07f; // 2^-22, see candidate()
 
 // ---- device-side data ----------------------------------------------------------------------
@@ -72,6 +77,7 @@ struct Batch {
     unsigned long long *vis;  // visibility buffer [n_frames][band_pixels]
     uint2 *queue;             // work items (triangle, cx | cy<<12 | frame<<24)
     uint32_t queue_cap;
+    uint32_t tiny_max_pixels; // bboxes up to this many pixels are rasterised by the setup thread itself
     unsigned long long *counters; // [0] queue count (may exceed queue_cap), [1] queue cursor, [2] overflow flag
 };
 
@@ -254,7 +260,7 @@ __device__ __noinline__ void setup_triangle(uint32_t t, uint32_t f, float4 v0, f
     const uint32_t w = bb.x1 - bb.x0 + 1u, h = bb.y1 - bb.y0 + 1u;
     unsigned long long *vis = bt.vis + (size_t)f * vw.band_pixels;
 
-    bool inline_raster = (uint64_t)w * h <= TINY_MAX_PIXELS;
+    bool inline_raster = (uint64_t)w * h <= bt.tiny_max_pixels;
     if (!inline_raster) {
         const uint32_t ncx = (w + CHUNK - 1) / CHUNK, ncy = (h + CHUNK - 1) / CHUNK;
         const uint64_t n = (uint64_t)ncx * ncy;

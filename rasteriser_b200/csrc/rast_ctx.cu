@@ -89,6 +89,8 @@ struct rast_ctx {
     bool copied_pending[2] = {false, false};
     uint32_t queue_cap = QUEUE_MIN;
     // raster schedule: 0 = chunk queue, 1 = screen-tile bins; "auto" follows the overdraw estimate of the previous call
+    uint32_t tiny_max_pixels = rk::TINY_MIN_PIXELS;
+    bool tiny_max_forced = false;
     int raster_mode_forced = -1; // -1 auto, 0 chunk, 1 tile (RAST_RASTER_MODE)
     bool tile_mode_next = false;
     uint32_t list_cap = 1u << 22, items_cap = 1u << 25;
@@ -175,6 +177,7 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     bt.vis = ctx->d_vis.as<unsigned long long>();
     bt.queue = ctx->d_queue.as<uint2>();
     bt.queue_cap = ctx->queue_cap;
+    bt.tiny_max_pixels = ctx->tiny_max_pixels;
     bt.counters = ctx->d_counters.as<unsigned long long>();
     const rk::Scene &sc = ctx->scene;
     cudaStream_t st = ctx->stream;
@@ -468,6 +471,7 @@ int rast_create(int device, rast_ctx **out) {
     }
     ctx->stream = ctx->own_stream;
     if (const char *e = getenv("RAST_SHADE_PX")) ctx->shade_px = atoi(e) == 4 ? 4 : 1;
+    if (const char *e = getenv("RAST_TINY_MAX")) { ctx->tiny_max_pixels = (uint32_t)atoi(e); ctx->tiny_max_forced = true; }
     if (const char *e = getenv("RAST_RASTER_MODE")) ctx->raster_mode_forced = !strcmp(e, "tile") ? 1 : (!strcmp(e, "chunk") ? 0 : -1);
     *out = ctx;
     return RAST_OK;
@@ -573,6 +577,10 @@ int rast_upload_mesh(rast_ctx *ctx, const float *positions, uint32_t n_positions
     s.Nuv = n_uvs + 1;
     s.T = n_tris;
     ctx->mesh_materials_dirty = true;
+    if (!ctx->tiny_max_forced) { // few triangles: keep bboxes parallel (queue them); millions: the setup thread rasterises more itself
+        const uint64_t t = n_tris / 16384u;
+        ctx->tiny_max_pixels = (uint32_t)(t < rk::TINY_MIN_PIXELS ? rk::TINY_MIN_PIXELS : (t > rk::TINY_MAX_PIXELS ? rk::TINY_MAX_PIXELS : t));
+    }
     ctx->have_mesh = true;
     ctx->have_frame = false;
     return RAST_OK;
