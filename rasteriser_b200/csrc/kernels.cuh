@@ -250,8 +250,11 @@ __global__ void __launch_bounds__(256) k_vertex(Scene sc, View vw, Batch bt) {
 // larger ones are cut into CHUNK x CHUNK work items for k_raster_chunks.
 constexpr int SETUP_TRIS = 4; // triangles per thread: all index and vertex loads of a thread are in flight together
 
+#ifndef RAST_SETUP_INLINE
+#define RAST_SETUP_INLINE __noinline__
+#endif
 template <bool BINS>
-__device__ __noinline__ void setup_triangle(uint32_t t, uint32_t f, float4 v0, float4 v1, float4 v2, bool cw, const View &vw, const Batch &bt, const TileBins &tb) {
+__device__ RAST_SETUP_INLINE void setup_triangle(uint32_t t, uint32_t f, float4 v0, float4 v1, float4 v2, bool cw, const View &vw, const Batch &bt, const TileBins &tb) {
     const float a2 = signed_area_2d(v0, v1, v2);
     if (!((a2 > 0.f) != cw)) return; // back face (drawing.cpp:178-180)
 
