@@ -347,7 +347,7 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": (1 if band_mode else world) * n * opts.steps / float(t.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(n * 144 + len(chunks) * len(wl["lights"]) * 32), "d2h_bytes_per_step": int(n * 7 * P),
+               "h2d_bytes_per_step": int(n * 208 + len(chunks) * len(wl["lights"]) * 32), "d2h_bytes_per_step": int(n * 7 * P),
                "note": "rast_draw_frames with pinned host outputs, %d frames per call: RGB8 + f32 depth of every frame copied D2H inside the timed region (wall clock, max over ranks)" % chunk}
         checksum = int(frames_host[len(chunks[-1]) // 2].astype(np.uint64).sum())
         # the same with colour only (the reference's spin loop shows frames; its depth buffer is scratch)

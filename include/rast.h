@@ -33,6 +33,11 @@ extern "C" {
 #define RAST_ENOMEM (-4)   /* host allocation failed */
 
 #define RAST_NO_TRIANGLE 0xFFFFFFFFu
+/* rast_args.flat: 0 / 1 = the reference's -f switch, which its frame path never reads (arguments.cpp:45) -- both
+ * give smooth shading, exactly like the reference.  2 = EXTENSION, not reference behaviour: one normal per face,
+ * normalize(cross(c1-c0, c2-c0)) of the camera-space vertices (what readme.md:46 promises for -f; the reference
+ * computes those vertices "for later use in shading", drawing.cpp:231-233, and stops there). */
+#define RAST_FLAT_FACE 2
 
 typedef struct rast_ctx rast_ctx;
 

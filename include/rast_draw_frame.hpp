@@ -85,7 +85,7 @@ template <class ArgsT> inline rast_args to_rast_args(const ArgsT &a) {
         r.tait_bryan_angles[k] = a.tait_bryan_angles[k];
     }
     r.wind_clockwise = a.wind_clockwise ? 1 : 0;
-    r.flat = a.flat ? 1 : 0;
+    r.flat = a.flat ? 1 : 0; // like the reference, the path ignores it; the host program's --flat-mode face sets RAST_FLAT_FACE itself
     return r;
 }
 

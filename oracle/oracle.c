@@ -341,6 +341,7 @@ typedef struct {
     int wind_clockwise;
     const float *raster;  /* 4 floats per vertex */
     const float *cnormal; /* 3 floats per normal */
+    const float *campos;  /* 3 floats per vertex: xyz(modelview * (v,1)) (drawing.cpp:232-233); NULL unless flat == ORC_FLAT_FACE */
     uint8_t *frame;
     float *depth;
     uint32_t *tri_id;
@@ -409,6 +410,13 @@ static void raster_band(const raster_job *J, uint32_t y0, uint32_t y1, orc_count
                 /* perspective_interpolate normals + normalize (drawing.cpp:64-75,131-132) */
                 float m[3];
                 for (int k = 0; k < 3; ++k) m[k] = d * (i0 * n[0][k] + i1 * n[1][k] + i2 * n[2][k]);
+                if (J->campos) { /* extension: face normal = cross(c1 - c0, c2 - c0) (glm::cross order), then normalize */
+                    const float *c0 = J->campos + (size_t)face[0] * 3, *c1 = J->campos + (size_t)face[1] * 3, *c2 = J->campos + (size_t)face[2] * 3;
+                    float ea[3] = {c1[0] - c0[0], c1[1] - c0[1], c1[2] - c0[2]}, eb[3] = {c2[0] - c0[0], c2[1] - c0[1], c2[2] - c0[2]};
+                    m[0] = ea[1] * eb[2] - eb[1] * ea[2];
+                    m[1] = ea[2] * eb[0] - eb[2] * ea[0];
+                    m[2] = ea[0] * eb[1] - eb[0] * ea[1];
+                }
                 float inv = 1.f / sqrtf((m[0] * m[0] + m[1] * m[1]) + m[2] * m[2]);
                 float normal[3] = {m[0] * inv, m[1] * inv, m[2] * inv};
                 if (J->wind_clockwise) { normal[0] = -normal[0]; normal[1] = -normal[1]; normal[2] = -normal[2]; }
@@ -431,7 +439,7 @@ static void raster_band(const raster_job *J, uint32_t y0, uint32_t y1, orc_count
 
 /* the per-vertex passes of draw_frame (drawing.cpp:222-247) */
 static int prepare(const orc_scene *scene, orc_light *lights, uint32_t n_lights, const orc_args *args,
-                   float **raster_out, float **cnormal_out) {
+                   float **raster_out, float **cnormal_out, float **campos_out) {
     float modelview[16], camera[16], normal_matrix[16], view[16];
     orc_frame_matrices(args, modelview, camera, normal_matrix, view);
     orc_transform_lights(view, lights, n_lights);
@@ -442,6 +450,17 @@ static int prepare(const orc_scene *scene, orc_light *lights, uint32_t n_lights,
         orc_raster_vertex(camera, args->image_width, args->image_height, scene->positions + (size_t)i * 3, raster + (size_t)i * 4);
     for (uint32_t i = 0; i < scene->n_normals; ++i)
         orc_transform_direction(normal_matrix, scene->normals + (size_t)i * 3, cnormal + (size_t)i * 3);
+    *campos_out = 0;
+    if (args->flat == ORC_FLAT_FACE) { /* transform_vertices(modelview) + xyz_all (drawing.cpp:232-233) */
+        float *campos = (float *)malloc((size_t)(scene->n_positions ? scene->n_positions : 1) * 3 * sizeof(float));
+        if (!campos) { free(raster); free(cnormal); return -1; }
+        for (uint32_t i = 0; i < scene->n_positions; ++i) {
+            const float *p = scene->positions + (size_t)i * 3;
+            v4 c = mat_vec(modelview, v4_make(p[0], p[1], p[2], 1.f));
+            campos[(size_t)i * 3] = c.x; campos[(size_t)i * 3 + 1] = c.y; campos[(size_t)i * 3 + 2] = c.z;
+        }
+        *campos_out = campos;
+    }
     *raster_out = raster;
     *cnormal_out = cnormal;
     return 0;
@@ -450,14 +469,15 @@ static int prepare(const orc_scene *scene, orc_light *lights, uint32_t n_lights,
 void orc_draw_frame(const orc_scene *scene, orc_light *lights, uint32_t n_lights,
                     const orc_args *args, uint8_t *frame, float *depth, uint32_t *tri_id,
                     uint32_t band_y0, uint32_t band_y1, orc_counters *counters) {
-    float *raster, *cnormal;
-    if (prepare(scene, lights, n_lights, args, &raster, &cnormal)) return;
+    float *raster, *cnormal, *campos;
+    if (prepare(scene, lights, n_lights, args, &raster, &cnormal, &campos)) return;
     raster_job J = {scene, lights, n_lights, args->image_width, args->image_height, args->wind_clockwise,
-                    raster, cnormal, frame, depth, tri_id};
+                    raster, cnormal, campos, frame, depth, tri_id};
     if (band_y1 > args->image_height) band_y1 = args->image_height;
     raster_band(&J, band_y0, band_y1, counters);
     free(raster);
     free(cnormal);
+    free(campos);
 }
 
 typedef struct {
@@ -488,10 +508,10 @@ static void *band_worker_main(void *arg) {
 void orc_draw_frame_mt(const orc_scene *scene, orc_light *lights, uint32_t n_lights,
                        const orc_args *args, uint8_t *frame, float *depth, uint32_t *tri_id,
                        int n_threads, orc_counters *counters) {
-    float *raster, *cnormal;
-    if (prepare(scene, lights, n_lights, args, &raster, &cnormal)) return;
+    float *raster, *cnormal, *campos;
+    if (prepare(scene, lights, n_lights, args, &raster, &cnormal, &campos)) return;
     raster_job J = {scene, lights, n_lights, args->image_width, args->image_height, args->wind_clockwise,
-                    raster, cnormal, frame, depth, tri_id};
+                    raster, cnormal, campos, frame, depth, tri_id};
     const uint32_t H = args->image_height;
     if (n_threads < 1) n_threads = 1;
     if (n_threads > 1024) n_threads = 1024;
@@ -525,6 +545,7 @@ void orc_draw_frame_mt(const orc_scene *scene, orc_light *lights, uint32_t n_lig
     free(threads);
     free(raster);
     free(cnormal);
+    free(campos);
 }
 
 void orc_clear(uint32_t width, uint32_t height, uint8_t *frame, float *depth, uint32_t *tri_id) {

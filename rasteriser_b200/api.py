@@ -29,6 +29,7 @@ class Args:
     image_height: int = 304
     spin: bool = False
     flat: bool = False  # parsed by the reference, never read by the frame path
+    flat_mode: str = "reference"  # extension: "face" with flat=True shades with one normal per face (RAST_FLAT_FACE)
     wind_clockwise: bool = False
     scale: float = 1.0
     displacement: tuple = (0.0, 0.0, 0.0)
@@ -49,7 +50,7 @@ class Args:
         a.displacement = (C.c_float * 3)(*[float(x) for x in self.displacement])
         a.tait_bryan_angles = (C.c_float * 3)(*[float(x) for x in self.tait_bryan_angles])
         a.wind_clockwise = int(bool(self.wind_clockwise))
-        a.flat = int(bool(self.flat))
+        a.flat = 2 if (self.flat and self.flat_mode == "face") else int(bool(self.flat))
         return a
 
 

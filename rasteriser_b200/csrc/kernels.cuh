@@ -32,7 +32,9 @@ struct FrameParams {          // one per frame of a batch, built on the host (ho
     float camera[16];         // perspective * view * model   (drawing.cpp:229)
     float normal_m[16];       // transpose(inverse(modelview)) (geometry.cpp:101)
     uint32_t wind_clockwise;  // arguments.h:14
-    uint32_t pad[3];
+    uint32_t flat_face;       // extension (rast_args.flat == RAST_FLAT_FACE): one normal per face
+    uint32_t pad[2];
+    float modelview[16];      // view * model (drawing.cpp:226); only read in flat_face mode
 };
 
 struct LightDev {             // pre-combined per light: -trans_dir and intensity*colour (shading.cpp:21)
@@ -684,7 +686,7 @@ struct LightTable {
 };
 
 // The shading half of update_pixel (drawing.cpp:121-146) for the winning triangle of one pixel.
-template <bool PRE_NORMALS>
+template <bool PRE_NORMALS, bool FLAT>
 __device__ __forceinline__ Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t y, const Scene &sc, const float4 *__restrict__ rv,
                                               const float4 *__restrict__ cn, const float *__restrict__ normal_m, bool wind_clockwise,
                                               const LightTable &lt, const LightDev *__restrict__ lights) {
@@ -697,7 +699,24 @@ __device__ __forceinline__ Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t
 
     // vertex normals in camera space (transform_direction, geometry.cpp:35-42,97-108)
     float4 n0, n1, n2;
-    if (PRE_NORMALS) {
+    float fx = 0.f, fy = 0.f, fz = 0.f; // FLAT: un-normalised face normal
+    if (FLAT) {
+        // extension: cross(c1 - c0, c2 - c0) of the camera-space vertices xyz(modelview * (v, 1)) (drawing.cpp:232-233);
+        // normal_m points at the frame's modelview matrix in this mode
+        float mv[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) mv[k] = __ldg(normal_m + k);
+        const float *p0 = sc.pos + 3 * (size_t)r0.x, *p1 = sc.pos + 3 * (size_t)r0.y, *p2 = sc.pos + 3 * (size_t)r0.z;
+        const float4 c0 = mat_vec(mv, __ldg(p0), __ldg(p0 + 1), __ldg(p0 + 2), 1.f);
+        const float4 c1 = mat_vec(mv, __ldg(p1), __ldg(p1 + 1), __ldg(p1 + 2), 1.f);
+        const float4 c2 = mat_vec(mv, __ldg(p2), __ldg(p2 + 1), __ldg(p2 + 2), 1.f);
+        const float ax = sub(c1.x, c0.x), ay = sub(c1.y, c0.y), az = sub(c1.z, c0.z);
+        const float bx = sub(c2.x, c0.x), by = sub(c2.y, c0.y), bz = sub(c2.z, c0.z);
+        fx = sub(mul(ay, bz), mul(by, az)); // glm::cross
+        fy = sub(mul(az, bx), mul(bz, ax));
+        fz = sub(mul(ax, by), mul(bx, ay));
+        n0 = n1 = n2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (PRE_NORMALS) {
         n0 = __ldg(cn + r0.w); n1 = __ldg(cn + r1.x); n2 = __ldg(cn + r1.y);
     } else {
         const float *m0 = sc.nrm + 3 * (size_t)r0.w, *m1 = sc.nrm + 3 * (size_t)r1.x, *m2 = sc.nrm + 3 * (size_t)r1.y;
@@ -727,9 +746,9 @@ __device__ __forceinline__ Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t
     const float d = div(1.f, add(add(i0, i1), i2));
 
     // perspective_interpolate + normalize (drawing.cpp:64-75,131-132)
-    const float mx = mul(d, add(add(mul(i0, n0.x), mul(i1, n1.x)), mul(i2, n2.x)));
-    const float my = mul(d, add(add(mul(i0, n0.y), mul(i1, n1.y)), mul(i2, n2.y)));
-    const float mz = mul(d, add(add(mul(i0, n0.z), mul(i1, n1.z)), mul(i2, n2.z)));
+    const float mx = FLAT ? fx : mul(d, add(add(mul(i0, n0.x), mul(i1, n1.x)), mul(i2, n2.x)));
+    const float my = FLAT ? fy : mul(d, add(add(mul(i0, n0.y), mul(i1, n1.y)), mul(i2, n2.y)));
+    const float mz = FLAT ? fz : mul(d, add(add(mul(i0, n0.z), mul(i1, n1.z)), mul(i2, n2.z)));
     const float inv = div(1.f, fsqrt(add(add(mul(mx, mx), mul(my, my)), mul(mz, mz))));
     float nx = mul(mx, inv), ny = mul(my, inv), nz = mul(mz, inv);
     if (wind_clockwise) { nx = -nx; ny = -ny; nz = -nz; }
@@ -791,7 +810,7 @@ __device__ __forceinline__ void load_keys(const unsigned long long *p, unsigned 
     }
 }
 
-template <int PX, bool PRE_NORMALS>
+template <int PX, bool PRE_NORMALS, bool FLAT>
 __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View vw, Batch bt, const __grid_constant__ LightTable lt,
                                                                  const LightDev *__restrict__ lights, uint8_t *__restrict__ rgb, float *__restrict__ depth,
                                                                  uint32_t keep_frame) {
@@ -838,7 +857,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View 
             const bool cw = __ldg(&fp->wind_clockwise) != 0u;
 #pragma unroll
             for (int k = 0; k < PX; ++k)
-                if (cov & (1u << k)) px[k] = shade_pixel<PRE_NORMALS>((uint32_t)keys[k], x0 + k, vw.y0 + row, sc, rv, cn, fp->normal_m, cw, lt, lights);
+                if (cov & (1u << k)) px[k] = shade_pixel<PRE_NORMALS, FLAT>((uint32_t)keys[k], x0 + k, vw.y0 + row, sc, rv, cn, FLAT ? fp->modelview : fp->normal_m, cw, lt, lights);
             if (reset) {
                 if (PX == 4) {
                     *reinterpret_cast<ulonglong2 *>(vis + g * STRIDE) = make_ulonglong2(VIS_EMPTY, VIS_EMPTY);

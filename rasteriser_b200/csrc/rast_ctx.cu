@@ -74,6 +74,7 @@ struct rast_ctx {
     bool mesh_materials_dirty = false; // material indices in d_attr still have to be clamped against n_materials
     uint32_t n_materials = 0;
     bool pre_normals = false;
+    bool flat_face = false; // extension mode of the current call (rast_args.flat == RAST_FLAT_FACE)
     int shade_px = 1; // adjacent pixels per group in the shade pass: 1 measured faster than 4 (uchar4/float4 stores) on B200
     rk::LightTable light_table{}; // first PARAM_LIGHTS lights, passed to the shade kernel by value
     std::vector<rast_light> lights;
@@ -156,7 +157,9 @@ void fill_frame_params(const rast_args &a, rk::FrameParams &fp) {
     camera_matrix(modelview, a.aspect_ratio).store(fp.camera);
     transpose(inverse(modelview)).store(fp.normal_m);
     fp.wind_clockwise = a.wind_clockwise ? 1u : 0u;
-    fp.pad[0] = fp.pad[1] = fp.pad[2] = 0u;
+    fp.flat_face = a.flat == RAST_FLAT_FACE ? 1u : 0u;
+    fp.pad[0] = fp.pad[1] = 0u;
+    modelview.store(fp.modelview);
 }
 
 uint32_t batch_capacity(const rast_ctx *ctx, const rk::View &vw) {
@@ -244,17 +247,19 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     }
     if (prof) cudaEventRecord(ctx->ev_pass[4], st);
     if (vw.band_pixels) {
-        const bool vec = ctx->shade_px == 4 && (vw.W % 4u == 0u) && (((uintptr_t)rgb_dev & 15u) == 0u) && (((uintptr_t)depth_dev & 15u) == 0u);
+        const bool vec = !ctx->flat_face && ctx->shade_px == 4 && (vw.W % 4u == 0u) && (((uintptr_t)rgb_dev & 15u) == 0u) && (((uintptr_t)depth_dev & 15u) == 0u);
         const rk::LightDev *lights = ctx->d_lights.as<rk::LightDev>();
         const uint32_t rows = vw.y1 - vw.y0;
         const dim3 grid(grid_for(vw.W, rk::SHADE_THREADS * rk::SHADE_GROUPS * (vec ? 4 : 1)), rows, count);
         const rk::LightTable &lt = ctx->light_table;
-        if (vec) {
-            if (bt.cn) rk::k_resolve_shade<4, true><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
-            else rk::k_resolve_shade<4, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
+        if (ctx->flat_face) { // extension: face normals (never taken for reference-compatible arguments)
+            rk::k_resolve_shade<1, false, true><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
+        } else if (vec) {
+            if (bt.cn) rk::k_resolve_shade<4, true, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
+            else rk::k_resolve_shade<4, false, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
         } else {
-            if (bt.cn) rk::k_resolve_shade<1, true><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
-            else rk::k_resolve_shade<1, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
+            if (bt.cn) rk::k_resolve_shade<1, true, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
+            else rk::k_resolve_shade<1, false, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
         }
     }
     if (prof) cudaEventRecord(ctx->ev_pass[5], st);
@@ -280,8 +285,11 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
     const uint32_t W = args[0].image_width, H = args[0].image_height;
     if (W == 0 || H == 0 || W > 65535u || H > 65535u) return fail(ctx, RAST_EINVAL, "rast_draw: image size out of range");
     if ((uint64_t)W * H > 0xFFFFFFFFull) return fail(ctx, RAST_EINVAL, "rast_draw: more than 2^32 pixels");
-    for (uint32_t i = 1; i < n; ++i)
+    for (uint32_t i = 1; i < n; ++i) {
         if (args[i].image_width != W || args[i].image_height != H) return fail(ctx, RAST_EINVAL, "rast_draw_frames: all frames must share one image size");
+        if ((args[i].flat == RAST_FLAT_FACE) != (args[0].flat == RAST_FLAT_FACE)) return fail(ctx, RAST_EINVAL, "rast_draw_frames: all frames must share one flat mode");
+    }
+    ctx->flat_face = args[0].flat == RAST_FLAT_FACE;
     RAST_CUDA(ctx, cudaSetDevice(ctx->device));
     if (ctx->scene.mats == nullptr) { // no materials uploaded: everything uses the white sentinel
         int rc = rast_upload_materials(ctx, nullptr, 0);

@@ -43,6 +43,7 @@ const Flag kFlags[] = {
     {"", "frame-out", Kind::String, false, "file.png", "[extension] colour output (default frame.png)"},
     {"", "depth-out", Kind::String, false, "file.png", "[extension] depth output (default depth.png)"},
     {"", "quiet", Kind::Switch, false, "", "[extension] no progress output"},
+    {"", "flat-mode", Kind::String, false, "reference|face", "[extension] what -f does: 'reference' = nothing, like the reference (default); 'face' = one normal per face"},
 };
 const int kNumFlags = (int)(sizeof kFlags / sizeof kFlags[0]);
 
@@ -132,6 +133,10 @@ ParseResult parse_args(int argc, const char *const *argv, Args &args, std::strin
         else if (n == "frame-out") args.frame_out = value;
         else if (n == "depth-out") args.depth_out = value;
         else if (n == "quiet") args.quiet = true;
+        else if (n == "flat-mode") {
+            if (value != "reference" && value != "face") { message = "PARSE ERROR: Argument: (--flat-mode)\n             Value '" + value + "' does not meet constraint: reference|face"; return ParseResult::Error; }
+            args.flat_face = value == "face";
+        }
     }
     for (int k = 0; k < kNumFlags; ++k)
         if (kFlags[k].required && !seen[k]) {

@@ -28,6 +28,7 @@ struct Args {
     int device = 0;                   // --device N
     std::string frame_out = "frame.png", depth_out = "depth.png"; // --frame-out / --depth-out
     bool quiet = false;               // --quiet
+    bool flat_face = false;           // --flat-mode face: with -f, shade with one normal per face (extension; default keeps the reference's no-op)
 };
 
 enum class ParseResult { Ok, Help, Version, Error };

@@ -71,7 +71,16 @@ int main(int argc, char **argv) {
 
     try {
         rast::Session session(arguments.device);
+        const int flat_code = (arguments.flat && arguments.flat_face) ? RAST_FLAT_FACE : (arguments.flat ? 1 : 0);
         if (!arguments.spin) {
+            if (flat_code == RAST_FLAT_FACE) { // extension path: same calls as the shim, with the extension code in rast_args.flat
+                session.upload(vertices, faces, normals, uvs, model.materials);
+                rast_light *l = reinterpret_cast<rast_light *>(lights.data());
+                session.check(rast_set_lights(session.ctx(), l, (uint32_t)lights.size()), "rast_set_lights");
+                rast_args a = rast::to_rast_args(arguments);
+                a.flat = flat_code;
+                session.check(rast_draw_frame(session.ctx(), &a, frame_buffer.data(), depth_buffer.data(), l), "rast_draw_frame");
+            } else
             rast::draw_frame(session, vertices, faces, normals, uvs, lights, model.materials, arguments, &frame_buffer, &depth_buffer);
             // renderer.cpp:92-93: frame.png, and depth.normalize(0,255) saved as 8-bit grey
             err = host::png_write_planar(arguments.frame_out, frame_buffer.data(), arguments.image_width, arguments.image_height, 3);
@@ -95,6 +104,7 @@ int main(int argc, char **argv) {
                 const unsigned count = n - first < chunk ? n - first : chunk;
                 for (unsigned i = 0; i < count; ++i) {
                     poses[i] = rast::to_rast_args(arguments);
+                    poses[i].flat = flat_code;
                     poses[i].tait_bryan_angles[1] = rast_spin_angle(arguments.tait_bryan_angles[1], first + i, n);
                 }
                 session.check(rast_draw_frames(session.ctx(), poses.data(), count, frames, nullptr, 0), "rast_draw_frames");

@@ -109,3 +109,24 @@ def test_threaded_and_banded_oracle_equal_single():
         fb[:, y0:y1], db[y0:y1], tb[y0:y1] = f[:, y0:y1], d[y0:y1], t[y0:y1]
         assert (t[:y0] == orc.NO_TRIANGLE).all() and (t[y1:] == orc.NO_TRIANGLE).all()
     assert np.array_equal(f0, fb) and np.array_equal(d0.view(np.uint32), db.view(np.uint32)) and np.array_equal(t0, tb)
+
+
+def test_flat_flag_is_a_noop_and_face_extension_differs():
+    """-f is parsed and never read by the reference (arguments.cpp:45): flat = 1 must not change a single bit.
+    flat = 2 is this repository's extension (face normals); it changes colours only, never visibility."""
+    sc, li = S.scene("suzanne"), S.lights("threepoint")
+    a0, a1, a2 = orc.make_args(160, 120), orc.make_args(160, 120, flat=True), orc.make_args(160, 120)
+    a2.flat = 2
+    f0, d0, t0 = orc.oracle_draw(sc, li, a0)
+    f1, d1, t1 = orc.oracle_draw(sc, li, a1)
+    f2, d2, t2 = orc.oracle_draw(sc, li, a2)
+    assert np.array_equal(f0, f1) and np.array_equal(d0.view(np.uint32), d1.view(np.uint32)) and np.array_equal(t0, t1)
+    assert orc.fnv(f0) == [c for c in CASES if c["name"] == "suzanne_160x120"][0]["frame_fnv"]
+    assert np.array_equal(d0.view(np.uint32), d2.view(np.uint32)) and np.array_equal(t0, t2) and (f0 != f2).any()
+    # on the flat square the face normal equals the (single) vertex normal: same image within rounding
+    sq = S.scene("square")
+    b0, b2 = orc.make_args(120, 90, angles=(0.3, 0.4, 0.1)), orc.make_args(120, 90, angles=(0.3, 0.4, 0.1))
+    b2.flat = 2
+    g0, _, _ = orc.oracle_draw(sq, li, b0)
+    g2, _, _ = orc.oracle_draw(sq, li, b2)
+    assert np.abs(g0.astype(int) - g2.astype(int)).max() <= 1

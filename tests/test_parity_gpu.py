@@ -281,3 +281,62 @@ def test_tile_binned_schedule_soups_bands_and_batches(seed, n_tris, size, cw, ti
             assert np.array_equal(frames[k], want[0]) and np.array_equal(depths[k].view(np.uint32), want[1].view(np.uint32))
     finally:
         r.close()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(wind_clockwise=True, angles=(0.2, 2.5, -0.4), disp=(0.3, 0.1, 0.9)), dict(scale=1.25, disp=(0.1, -0.2, 0.5), angles=(0.3, 1.0, 0.2))])
+def test_flat_face_extension_matches_oracle(kw):
+    """EXTENSION (not reference behaviour): rast_args.flat = RAST_FLAT_FACE shades with one normal per face.  The
+    reference parses -f and ignores it, so there is nothing of the reference's to pin this against; the device must
+    equal the oracle's definition, and flat = 1 must stay identical to flat = 0."""
+    scene, lights = S.scene("suzanne"), S.lights("threepoint")
+    r = make_renderer(scene, lights)
+    try:
+        smooth = orc.make_args(320, 240, **kw)
+        ref_flag = orc.make_args(320, 240, flat=True, **kw)
+        face = orc.make_args(320, 240, **kw)
+        face.flat = 2
+        a = to_api_args(smooth)
+        f0, d0 = r.draw_frame(a)
+        a1 = to_api_args(ref_flag)
+        f1, d1 = r.draw_frame(a1)
+        assert np.array_equal(f0, f1) and np.array_equal(d0.view(np.uint32), d1.view(np.uint32))   # -f alone: no-op, like the reference
+        a2 = api.Args(320, 240, scale=smooth.scale, displacement=tuple(smooth.displacement), tait_bryan_angles=tuple(smooth.tait_bryan_angles),
+                      wind_clockwise=bool(smooth.wind_clockwise), flat=True, flat_mode="face")
+        f2, d2 = r.draw_frame(a2)
+        t2 = r.triangle_ids(320, 240)
+        want = orc.oracle_draw(scene, lights, face)
+        assert_parity((f2, d2, t2), want, "flat face")
+        assert np.array_equal(d2.view(np.uint32), d0.view(np.uint32))     # visibility is unchanged
+        assert (f2 != f0).any()                                            # the shading is not
+    finally:
+        r.close()
+
+
+def test_flat_face_soup_and_cli(tmp_path):
+    import os
+    import subprocess
+    from PIL import Image
+    from rasteriser_b200 import build
+    scene, lights = S.random_soup(4, 200), S.random_lights(4, 3)
+    oa = orc.make_args(97, 131, angles=(0.4, 1.48, -0.2), wind_clockwise=True)
+    oa.flat = 2
+    r = make_renderer(scene, lights)
+    try:
+        a = to_api_args(oa)
+        a.flat, a.flat_mode = True, "face"
+        f, d = r.draw_frame(a)
+        assert_parity((f, d, r.triangle_ids(97, 131)), orc.oracle_draw(scene, lights, oa), "flat soup")
+    finally:
+        r.close()
+    exe = build.build_renderer()
+    base = [exe, "-o", os.path.join(S.DATA, "Suzanne.obj"), "-l", os.path.join(S.DATA, "threepoint.csv"), "--mats-dir", S.DATA + "/", "-x", "200", "-y", "150", "--ry", "0.7"]
+    for extra, name in ((["-f"], "ref.png"), (["-f", "--flat-mode", "face"], "face.png")):
+        out = subprocess.run(base + extra + ["--frame-out", name, "--depth-out", "d_" + name], cwd=tmp_path, capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+    ref_img = np.ascontiguousarray(np.asarray(Image.open(tmp_path / "ref.png")).transpose(2, 0, 1))
+    face_img = np.ascontiguousarray(np.asarray(Image.open(tmp_path / "face.png")).transpose(2, 0, 1))
+    sm = orc.make_args(200, 150, angles=(0.0, 0.7, 0.0))
+    fa = orc.make_args(200, 150, angles=(0.0, 0.7, 0.0))
+    fa.flat = 2
+    assert np.array_equal(ref_img, orc.oracle_draw(S.scene("suzanne"), S.lights("threepoint"), sm)[0])   # -f == no -f, as in the reference
+    assert np.array_equal(face_img, orc.oracle_draw(S.scene("suzanne"), S.lights("threepoint"), fa)[0])
