@@ -514,6 +514,7 @@ __device__ __forceinline__ void raster_item(const StagedTris &stg, uint32_t it, 
     }
 }
 
+// (64 registers / 4 CTAs per SM measured: 1080p Suzanne raster +4 %, 8K overdraw -8 %; the default favours the former)
 __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_chunks(Scene sc, View vw, Batch bt) {
     __shared__ StagedTris stage_all[RASTER_WARPS];
     if (bt.counters[CNT_TILE_MODE] != 0ull) return; // this batch is rasterised by k_raster_tiles
@@ -810,6 +811,7 @@ __device__ __forceinline__ void load_keys(const unsigned long long *p, unsigned 
     }
 }
 
+// (forcing 10 or 12 CTAs per SM -- 48 / 40 registers -- measured 7-10 % slower than the 56 registers the compiler picks)
 template <int PX, bool PRE_NORMALS, bool FLAT>
 __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View vw, Batch bt, const __grid_constant__ LightTable lt,
                                                                  const LightDev *__restrict__ lights, uint8_t *__restrict__ rgb, float *__restrict__ depth,
