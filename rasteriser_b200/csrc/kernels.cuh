@@ -250,10 +250,16 @@ __global__ void __launch_bounds__(256) k_vertex(Scene sc, View vw, Batch bt) {
 // ---- K2: triangle setup, cull, classification -----------------------------------------------
 // draw_triangle up to the pixel loops (drawing.cpp:165-188).  Tiny bboxes are rasterised here;
 // larger ones are cut into CHUNK x CHUNK work items for k_raster_chunks.
-constexpr int SETUP_TRIS = 4; // triangles per thread: all index and vertex loads of a thread are in flight together
+#ifndef RAST_SETUP_TRIS
+#define RAST_SETUP_TRIS 1
+#endif
+constexpr int SETUP_TRIS = RAST_SETUP_TRIS; // triangles per thread: all index and vertex loads of a thread are in flight together
+                                            // (k_setup on 8 M / 50 M triangles, out-of-line body: 1 -> 0.187 / 0.898 ms, 2 -> 0.188 / 0.847,
+                                            //  4 -> 0.225 / 1.011, 8 -> 0.323 / 1.422; inlined body: 1 -> 0.154 / 0.706, 2 -> 0.175 / 0.817.  Once the queue
+                                            //  reservation is one atomic per warp, more triangles per thread only cost registers.)
 
 #ifndef RAST_SETUP_INLINE
-#define RAST_SETUP_INLINE __noinline__
+#define RAST_SETUP_INLINE __forceinline__
 #endif
 template <bool BINS>
 __device__ RAST_SETUP_INLINE void setup_triangle(uint32_t t, uint32_t f, float4 v0, float4 v1, float4 v2, bool cw, const View &vw, const Batch &bt, const TileBins &tb) {
