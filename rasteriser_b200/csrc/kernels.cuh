@@ -804,8 +804,15 @@ __device__ __forceinline__ Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t
 // 40 warps/SM).  Phase 2 walks the groups; a covered group re-reads its keys (L1 hits) and shades.
 // PX = 4 (W % 4 == 0, 16-byte aligned outputs): keys in as 2 x 16 B, colour out as one uchar4 per plane,
 // depth as one float4 (CImg planar layout, CImg.h:11715-11721).  PX = 1: scalar loads/stores, any W.
-constexpr int SHADE_THREADS = 128;
-constexpr int SHADE_GROUPS = 4;
+#ifndef RAST_SHADE_THREADS
+#define RAST_SHADE_THREADS 128
+#endif
+#ifndef RAST_SHADE_GROUPS
+#define RAST_SHADE_GROUPS 16
+#endif
+constexpr int SHADE_THREADS = RAST_SHADE_THREADS;
+constexpr int SHADE_GROUPS = RAST_SHADE_GROUPS; // measured (1080p spin step, shade ms): 2 -> 10.3, 4 -> 8.94, 8 -> 8.60, 15 -> 8.11, 16 -> 8.20, 24 -> 8.60, 32 -> 8.64
+__host__ __device__ constexpr int shade_groups(int px) { return px * SHADE_GROUPS <= 32 ? SHADE_GROUPS : 32 / px; } // one coverage bit per pixel in a 32-bit mask
 
 template <int PX>
 __device__ __forceinline__ void load_keys(const unsigned long long *p, unsigned long long (&keys)[PX]) {
@@ -823,7 +830,8 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View 
                                                                  const LightDev *__restrict__ lights, uint8_t *__restrict__ rgb, float *__restrict__ depth,
                                                                  uint32_t keep_frame) {
     constexpr uint32_t STRIDE = SHADE_THREADS * PX;
-    const uint32_t xb = blockIdx.x * (STRIDE * SHADE_GROUPS) + threadIdx.x * PX;
+    constexpr int GROUPS = shade_groups(PX);
+    const uint32_t xb = blockIdx.x * (STRIDE * GROUPS) + threadIdx.x * PX;
     const uint32_t row = blockIdx.y, f = blockIdx.z;
     const uint32_t P = vw.band_pixels;
     const size_t i0 = (size_t)f * P + (size_t)row * vw.W + xb;          // into vis / depth
@@ -834,7 +842,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View 
     // phase 1: all key loads in flight at once; one coverage bit per pixel
     uint32_t covered = 0;
 #pragma unroll
-    for (int g = 0; g < SHADE_GROUPS; ++g) {
+    for (int g = 0; g < GROUPS; ++g) {
         if (xb + g * STRIDE < vw.W) {
             unsigned long long keys[PX];
             load_keys<PX>(vis + g * STRIDE, keys);
@@ -852,7 +860,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View 
     const float4 *cn = reinterpret_cast<const float4 *>(cn_base);
     const FrameParams *fp = bt.frames + f;
 #pragma unroll 1
-    for (uint32_t g = 0; g < SHADE_GROUPS; ++g) {
+    for (uint32_t g = 0; g < GROUPS; ++g) {
         const uint32_t x0 = xb + g * STRIDE;
         if (x0 >= vw.W) break;
         Shaded px[PX];

@@ -250,7 +250,7 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
         const bool vec = !ctx->flat_face && ctx->shade_px == 4 && (vw.W % 4u == 0u) && (((uintptr_t)rgb_dev & 15u) == 0u) && (((uintptr_t)depth_dev & 15u) == 0u);
         const rk::LightDev *lights = ctx->d_lights.as<rk::LightDev>();
         const uint32_t rows = vw.y1 - vw.y0;
-        const dim3 grid(grid_for(vw.W, rk::SHADE_THREADS * rk::SHADE_GROUPS * (vec ? 4 : 1)), rows, count);
+        const dim3 grid(grid_for(vw.W, rk::SHADE_THREADS * rk::shade_groups(vec ? 4 : 1) * (vec ? 4 : 1)), rows, count);
         const rk::LightTable &lt = ctx->light_table;
         if (ctx->flat_face) { // extension: face normals (never taken for reference-compatible arguments)
             rk::k_resolve_shade<1, false, true><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
