@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "librast_b200.so")
+# RAST_LIB selects another build of the same library (tools/build_variants.py: A/B runs of kernel variants)
+LIB_PATH = os.environ.get("RAST_LIB") or os.path.join(PKG, "librast_b200.so")
 
 RAST_PASS_NAMES = ("clear", "vertex", "setup", "raster", "shade")
 NO_TRIANGLE = 0xFFFFFFFF

@@ -50,6 +50,17 @@ def build_lib(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines, verbose=False):
+    """build/variants/librast_b200_<name>.so: the same library with extra -D switches, selected at run time with
+    RAST_LIB=<path> (A/B measurements of kernel variants in one GPU session)."""
+    out_dir = os.path.join(ROOT, "build", "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, "librast_b200_%s.so" % name)
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + ["-shared", "-o", out, os.path.join(PKG, "csrc", "rast_ctx.cu")]
+    subprocess.check_call(cmd)
+    return out
+
+
 HOST_FLAGS = ["-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-fPIC"]
 
 

@@ -14,6 +14,13 @@
 
 #include "exact.cuh"
 
+#ifndef RAST_SHADE_OPAQUE_TEX
+#define RAST_SHADE_OPAQUE_TEX 1
+#endif
+#ifndef RAST_SHADE_LIGHT_SWITCH
+#define RAST_SHADE_LIGHT_SWITCH 1
+#endif
+
 namespace rk {
 
 constexpr unsigned long long VIS_EMPTY = ~0ull;
@@ -204,6 +211,52 @@ __device__ __forceinline__ void test_and_commit(const TriSetup &s, uint32_t x, u
     atomicMin(vis_row0 + (size_t)(y - vw.y0) * vw.W + x, key);
 }
 
+// The pixel loops of draw_triangle (drawing.cpp:190-201) over a small bbox, walked by ONE thread as 2x2 quads:
+// the differences (p - a) and the products of edge() are shared between the four pixels (36 operations per
+// quad instead of 60), each edge value is still mul(d, py - yk) - mul(d', px - xk) evaluated from scratch, so
+// the bits are those of edges().  The quads are visited in one flat loop so that the lanes of a warp -- each
+// with its own bbox -- stay in lockstep for min(count) iterations instead of diverging at every row end.
+__device__ __forceinline__ void raster_bbox_quads(const TriSetup &s, const BBox &bb, uint32_t tri, unsigned long long *vis_row0, const View &vw) {
+    using namespace exact;
+    uint32_t x = bb.x0, y = bb.y0;
+    for (;;) {
+        const float pxa = (float)x, pxb = (float)(x + 1u), pya = (float)y, pyb = (float)(y + 1u);
+        const float a0a = mul(s.d12x, sub(pya, s.y1)), a0b = mul(s.d12x, sub(pyb, s.y1));
+        const float a1a = mul(s.d20x, sub(pya, s.y2)), a1b = mul(s.d20x, sub(pyb, s.y2));
+        const float a2a = mul(s.d01x, sub(pya, s.y0)), a2b = mul(s.d01x, sub(pyb, s.y0));
+        const float c0a = mul(s.d12y, sub(pxa, s.x1)), c0b = mul(s.d12y, sub(pxb, s.x1));
+        const float c1a = mul(s.d20y, sub(pxa, s.x2)), c1b = mul(s.d20y, sub(pxb, s.x2));
+        const float c2a = mul(s.d01y, sub(pxa, s.x0)), c2b = mul(s.d01y, sub(pxb, s.x0));
+        // (xa,ya) (xb,ya) (xa,yb) (xb,yb)
+        const float m0 = fminf(fminf(sub(a0a, c0a), sub(a1a, c1a)), sub(a2a, c2a));
+        const float m1 = fminf(fminf(sub(a0a, c0b), sub(a1a, c1b)), sub(a2a, c2b));
+        const float m2 = fminf(fminf(sub(a0b, c0a), sub(a1b, c1a)), sub(a2b, c2a));
+        const float m3 = fminf(fminf(sub(a0b, c0b), sub(a1b, c1b)), sub(a2b, c2b));
+        const bool xb_in = x + 1u <= bb.x1, yb_in = y + 1u <= bb.y1;
+        uint32_t mask = (s.literal || m0 >= -EDGE_SLACK) ? 1u : 0u; // candidate()
+        if (xb_in && (s.literal || m1 >= -EDGE_SLACK)) mask |= 2u;
+        if (yb_in && (s.literal || m2 >= -EDGE_SLACK)) mask |= 4u;
+        if (xb_in && yb_in && (s.literal || m3 >= -EDGE_SLACK)) mask |= 8u;
+        while (mask) { // survivors: the literal divisions and the strict depth test
+            const uint32_t k = __ffs(mask) - 1u;
+            mask &= mask - 1u;
+            const float aa0 = (k & 2u) ? a0b : a0a, aa1 = (k & 2u) ? a1b : a1a, aa2 = (k & 2u) ? a2b : a2a;
+            const float cc0 = (k & 1u) ? c0b : c0a, cc1 = (k & 1u) ? c1b : c1a, cc2 = (k & 1u) ? c2b : c2a;
+            float b0, b1, b2, z;
+            if (fragment(s, sub(aa0, cc0), sub(aa1, cc1), sub(aa2, cc2), b0, b1, b2, z)) {
+                const unsigned long long key = ((unsigned long long)depth_key(z) << 32) | tri;
+                atomicMin(vis_row0 + (size_t)(y + (k >> 1) - vw.y0) * vw.W + x + (k & 1u), key);
+            }
+        }
+        x += 2u;
+        if (x > bb.x1) {
+            x = bb.x0;
+            y += 2u;
+            if (y > bb.y1) break;
+        }
+    }
+}
+
 // ---- K0: clear ------------------------------------------------------------------------------
 // renderer.cpp:85-86 / :107-108 (frame = 0, depth = 1.0f) become "no triangle" in the visibility buffer.
 // Only needed for slots that are not known to be empty: the shade pass hands every key it consumes
@@ -258,6 +311,11 @@ constexpr int SETUP_TRIS = RAST_SETUP_TRIS; // triangles per thread: all index a
                                             //  4 -> 0.225 / 1.011, 8 -> 0.323 / 1.422; inlined body: 1 -> 0.154 / 0.706, 2 -> 0.175 / 0.817.  Once the queue
                                             //  reservation is one atomic per warp, more triangles per thread only cost registers.)
 
+#ifndef RAST_SETUP_QUADS
+#define RAST_SETUP_QUADS 0 // 1: small bboxes are walked as 2x2 quads (raster_bbox_quads).  Measured slower on B200 (k_setup, 8 M / 50 M
+                           // triangles: 0.173 / 0.844 ms vs 0.156 / 0.710 ms pixel by pixel): sub-pixel triangles have 2-3 pixel wide bboxes,
+                           // so quads test 28 % more pixels and the kernel is latency-bound on the index -> vertex gathers, not on the loop
+#endif
 #ifndef RAST_SETUP_INLINE
 #define RAST_SETUP_INLINE __forceinline__
 #endif
@@ -315,8 +373,12 @@ __device__ RAST_SETUP_INLINE void setup_triangle(uint32_t t, uint32_t f, float4 
     if (inline_raster) {
         TriSetup s;
         tri_setup(s, v0, v1, v2);
+#if RAST_SETUP_QUADS
+        raster_bbox_quads(s, bb, t, vis, vw);
+#else
         for (uint32_t y = bb.y0; y <= bb.y1; ++y)
             for (uint32_t x = bb.x0; x <= bb.x1; ++x) test_and_commit(s, x, y, t, vis, vw);
+#endif
     }
 }
 
@@ -767,21 +829,46 @@ __device__ __forceinline__ Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t
         const float u = mul(d, add(add(mul(i0, uv0.x), mul(i1, uv1.x)), mul(i2, uv2.x))); // drawing.cpp:135
         const float v = mul(d, add(add(mul(i0, uv0.y), mul(i1, uv1.y)), mul(i2, uv2.y)));
         const long long toff = ((long long)(uint32_t)mt.z) | ((long long)mt.w << 32);
-        sample_texture(sc.texels + toff, mt.x, mt.y, mul(u, (float)mt.x), mul(sub(1.f, v), (float)mt.y), ar, ag, ab);
+        unsigned long long tex_base = (unsigned long long)(sc.texels + toff);
+#if RAST_SHADE_OPAQUE_TEX
+        asm volatile("" : "+l"(tex_base)); // opaque base: each corner becomes one IMAD.WIDE instead of a 64-bit add + LEA pair
+#endif
+        sample_texture(reinterpret_cast<const float4 *>(tex_base), mt.x, mt.y, mul(u, (float)mt.x), mul(sub(1.f, v), (float)mt.y), ar, ag, ab);
     }
 
     // shade / light_contribution (shading.cpp:20-34)
     float sr = 0.f, sg = 0.f, sb = 0.f;
     const uint32_t n_p = lt.n < PARAM_LIGHTS ? lt.n : PARAM_LIGHTS;
-#pragma unroll 1
-    for (uint32_t l = 0; l < n_p; ++l) {
+    auto one_light = [&](uint32_t l) {
         const float4 a = lt.a[l];
         const float2 c = lt.c[l];
         const float k = glm_max(0.f, add(add(mul(nx, a.x), mul(ny, a.y)), mul(nz, a.z)));
         sr = add(sr, mul(mul(mul(a.w, ar), k), 0.318309886183790671537767526745028724f));
         sg = add(sg, mul(mul(mul(c.x, ag), k), 0.318309886183790671537767526745028724f));
         sb = add(sb, mul(mul(mul(c.y, ab), k), 0.318309886183790671537767526745028724f));
+    };
+#if RAST_SHADE_LIGHT_SWITCH
+    // the light count is uniform over the launch: the common small counts run straight-line code with the
+    // light constants at immediate constant-bank offsets (same lights, same order, same operations)
+    if (n_p == 3u) {
+        one_light(0); one_light(1); one_light(2);
+    } else if (n_p == 1u) {
+        one_light(0);
+    } else if (n_p == 2u) {
+        one_light(0); one_light(1);
+    } else if (n_p == 4u) {
+        one_light(0); one_light(1); one_light(2); one_light(3);
+    } else {
+        uint32_t l = 0;
+#pragma unroll 1
+        for (; l + 4u <= n_p; l += 4u) { one_light(l); one_light(l + 1u); one_light(l + 2u); one_light(l + 3u); }
+#pragma unroll 1
+        for (; l < n_p; ++l) one_light(l);
     }
+#else
+#pragma unroll 1
+    for (uint32_t l = 0; l < n_p; ++l) one_light(l);
+#endif
 #pragma unroll 1
     for (uint32_t l = n_p; l < lt.n; ++l) { // beyond the parameter table: straight from global memory
         const LightDev L = lights[l];

@@ -1,5 +1,12 @@
 #include "loaders.hpp"
 
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -8,6 +15,7 @@
 #include <iostream>
 #include <map>
 #include <sstream>
+#include <thread>
 
 #include "image.hpp"
 #include "png.hpp"
@@ -65,28 +73,6 @@ struct Corner { int v, vt, vn; };
 
 // "make index zero-base, and also support relative index" (tiny_obj_loader.h:414-418)
 inline int resolve_index(int idx, int count) { return idx > 0 ? idx - 1 : (idx == 0 ? 0 : count + idx); }
-
-// i, i/j, i/j/k, i//k (tiny_obj_loader.h:680-711)
-Corner parse_corner(Cursor &c, int nv, int nvn, int nvt) {
-    Corner r = {-1, -1, -1};
-    r.v = resolve_index(std::atoi(c.p), nv);
-    c.p += std::strcspn(c.p, "/ \t\r");
-    if (*c.p != '/') return r;
-    ++c.p;
-    if (*c.p == '/') { // i//k
-        ++c.p;
-        r.vn = resolve_index(std::atoi(c.p), nvn);
-        c.p += std::strcspn(c.p, "/ \t\r");
-        return r;
-    }
-    r.vt = resolve_index(std::atoi(c.p), nvt);
-    c.p += std::strcspn(c.p, "/ \t\r");
-    if (*c.p != '/') return r;
-    ++c.p;
-    r.vn = resolve_index(std::atoi(c.p), nvn);
-    c.p += std::strcspn(c.p, "/ \t\r");
-    return r;
-}
 
 struct MtlEntry { std::string name; float kd[3]; std::string map_kd; };
 
@@ -233,95 +219,357 @@ bool load_texture(const std::string &path, MaterialData &m, std::string &error, 
     return true;
 }
 
-bool load_obj(const std::string &obj_file, const std::string &materials_directory, Model &model, std::string &error, bool verbose) {
-    std::ifstream in(obj_file.c_str());
-    if (!in) { error = "Cannot open file [" + obj_file + "]\n"; return false; }
+// ---- parallel OBJ reader ----------------------------------------------------------------------------------
+// LoadObj + exportFaceGroupToShape (tiny_obj_loader.h:1384-1650, :879-940) followed by load_obj's flattening of
+// all shapes (fileloader.cpp:103-118), restated for files of tens of millions of triangles: the file is held in
+// memory, cut into pieces at line boundaries, and every piece is visited twice by a pool of threads -- once to
+// count, once to parse straight into the final arrays.  What tinyobjloader does with state carried from line to
+// line (current material, faces pending since the last flush, the shape being built, the v / vn / vt counts
+// relative indices refer to) is resolved between the passes from per-piece counts and the few structural lines
+// (usemtl, mtllib, g, o), so the arrays equal the sequential reading whatever the thread count.
+namespace {
 
-    std::vector<MtlEntry> mtl;
-    std::map<std::string, int> mtl_by_name;
-    std::vector<std::vector<Corner>> pending;   // faces since the last flush ("faceGroup")
-    std::vector<int32_t> shape;                 // triangles of the shape being built
-    std::vector<std::vector<int32_t>> shapes;   // finished shapes, in file order
+struct Line { const char *b, *e; }; // [b, e): one logical line without its terminator, cut at an embedded NUL
+
+// next logical line at or after p (LF, CR and CRLF end a line); returns the start of the following line
+inline const char *scan_line(const char *p, const char *end, Line &ln) {
+    const char *q = p, *nul = nullptr;
+    while (q < end && *q != '\n' && *q != '\r') {
+        if (*q == '\0' && !nul) nul = q;
+        ++q;
+    }
+    ln.b = p;
+    ln.e = nul ? nul : q;
+    if (q < end) q += (*q == '\r' && q + 1 < end && q[1] == '\n') ? 2 : 1;
+    return q;
+}
+
+enum class Kind { Skip, V, VN, VT, F, UseMtl, MtlLib, Group };
+
+inline char at(const char *p, const char *e, int i) { return p + i < e ? p[i] : '\0'; }
+
+// the dispatch of LoadObj's line loop; `body` is where the payload starts
+inline Kind classify(const Line &ln, const char *&body) {
+    const char *p = ln.b, *e = ln.e;
+    while (p < e && is_blank(*p)) ++p;
+    if (p >= e || *p == '#') return Kind::Skip;
+    const char c0 = p[0], c1 = at(p, e, 1), c2 = at(p, e, 2);
+    if (c0 == 'v') {
+        if (is_blank(c1)) { body = p + 2; return Kind::V; }
+        if (c1 == 'n' && is_blank(c2)) { body = p + 3; return Kind::VN; }
+        if (c1 == 't' && is_blank(c2)) { body = p + 3; return Kind::VT; }
+        return Kind::Skip;
+    }
+    if (c0 == 'f' && is_blank(c1)) { body = p + 2; return Kind::F; }
+    if (e - p >= 7 && is_blank(p[6])) {
+        if (!std::memcmp(p, "usemtl", 6)) { body = p + 7; return Kind::UseMtl; }
+        if (!std::memcmp(p, "mtllib", 6)) { body = p + 7; return Kind::MtlLib; }
+    }
+    if ((c0 == 'g' || c0 == 'o') && is_blank(c1)) return Kind::Group;
+    return Kind::Skip;
+}
+
+inline float number(const char *&p, const char *e) { // parseFloat on the next blank-delimited token
+    while (p < e && is_blank(*p)) ++p;
+    const char *t = p;
+    while (t < e && !is_blank(*t) && *t != '\r') ++t;
+    const float f = parse_obj_float(p, t, 0.0);
+    p = t;
+    return f;
+}
+
+// atoi on [p, e): leading isspace characters, an optional sign, decimal digits
+inline int bounded_atoi(const char *p, const char *e) {
+    while (p < e && (*p == ' ' || (*p >= '\t' && *p <= '\r'))) ++p;
+    bool neg = false;
+    if (p < e && (*p == '+' || *p == '-')) neg = *p++ == '-';
+    unsigned v = 0;
+    while (p < e && is_digit(*p)) v = v * 10u + (unsigned)(*p++ - '0');
+    return neg ? (int)(0u - v) : (int)v;
+}
+inline const char *corner_stop(const char *p, const char *e) { // strcspn(p, "/ \t\r")
+    while (p < e && *p != '/' && !is_blank(*p) && *p != '\r') ++p;
+    return p;
+}
+
+// i, i/j, i/j/k, i//k (tiny_obj_loader.h:680-711).  PARSE = false only walks the token the same way (pass 1
+// needs the corner count, and the walk does not depend on the numbers).
+template <bool PARSE> inline Corner parse_corner(const char *&p, const char *e, int nv, int nvn, int nvt) {
+    Corner r = {-1, -1, -1};
+    if (PARSE) r.v = resolve_index(bounded_atoi(p, e), nv);
+    p = corner_stop(p, e);
+    if (p >= e || *p != '/') return r;
+    ++p;
+    if (p < e && *p == '/') { // i//k
+        ++p;
+        if (PARSE) r.vn = resolve_index(bounded_atoi(p, e), nvn);
+        p = corner_stop(p, e);
+        return r;
+    }
+    if (PARSE) r.vt = resolve_index(bounded_atoi(p, e), nvt);
+    p = corner_stop(p, e);
+    if (p >= e || *p != '/') return r;
+    ++p;
+    if (PARSE) r.vn = resolve_index(bounded_atoi(p, e), nvn);
+    p = corner_stop(p, e);
+    return r;
+}
+inline void skip_corner_gap(const char *&p, const char *e) { // strspn(p, " \t\r")
+    while (p < e && (is_blank(*p) || *p == '\r')) ++p;
+}
+
+// A run of lines between two structural lines (or piece boundaries): its faces share one material and one fate.
+struct Segment {
+    uint64_t faces = 0, tris = 0; // 'f' lines, triangles they fan into
     int material = -1;
-    std::ostringstream warn;
+    bool keep = false;
+    uint64_t tri_offset = 0;      // where its triangles go in Model::tris (triangles, not ints)
+};
+struct Event { Kind kind; Line line; const char *body; };
+struct Piece {
+    const char *b, *e;
+    uint64_t nv = 0, nvn = 0, nvt = 0;          // lines of each kind in the piece
+    uint64_t v0 = 0, vn0 = 0, vt0 = 0;          // counts before the piece (prefix sums)
+    std::vector<Event> events;                   // structural lines, in order
+    size_t first_segment = 0;                    // segments of the piece: events.size() + 1, in order
+};
 
-    // exportFaceGroupToShape (tiny_obj_loader.h:879-940): fan (f0, f[k-1], f[k]), one material id per triangle
-    auto flush_faces = [&]() -> bool {
-        if (pending.empty()) return false;
-        for (const std::vector<Corner> &face : pending) {
-            if (face.size() < 2) continue;
-            const Corner c0 = face[0];
-            Corner c2 = face[1];
-            for (size_t k = 2; k < face.size(); ++k) {
-                const Corner c1 = c2;
-                c2 = face[k];
-                const int32_t t[10] = {c0.v, c1.v, c2.v, c0.vn, c1.vn, c2.vn, c0.vt, c1.vt, c2.vt, material};
-                shape.insert(shape.end(), t, t + 10);
-            }
-        }
-        return true;
-    };
+template <class Fn> void run_parallel(unsigned threads, size_t n, Fn fn) {
+    if (threads <= 1 || n <= 1) {
+        for (size_t i = 0; i < n; ++i) fn(i);
+        return;
+    }
+    std::atomic<size_t> next(0);
+    std::vector<std::thread> pool;
+    const unsigned nt = (unsigned)std::min<size_t>(threads, n);
+    for (unsigned t = 0; t < nt; ++t)
+        pool.emplace_back([&]() {
+            for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+        });
+    for (std::thread &t : pool) t.join();
+}
 
-    std::string line;
-    while (in.peek() != -1) {
-        next_line(in, line);
-        if (line.empty()) continue;
-        Cursor c{line.c_str()};
-        c.skip_blanks();
-        if (*c.p == '\0' || *c.p == '#') continue;
-        if (c.p[0] == 'v' && is_blank(c.p[1])) {
-            c.p += 2;
-            for (int k = 0; k < 3; ++k) model.positions.push_back(c.number());
-        } else if (c.p[0] == 'v' && c.p[1] == 'n' && is_blank(c.p[2])) {
-            c.p += 3;
-            for (int k = 0; k < 3; ++k) model.normals.push_back(c.number());
-        } else if (c.p[0] == 'v' && c.p[1] == 't' && is_blank(c.p[2])) {
-            c.p += 3;
-            for (int k = 0; k < 2; ++k) model.uvs.push_back(c.number());
-        } else if (c.p[0] == 'f' && is_blank(c.p[1])) {
-            c.p += 2;
-            c.skip_blanks();
-            std::vector<Corner> face;
-            while (!is_eol(*c.p)) {
-                face.push_back(parse_corner(c, (int)(model.positions.size() / 3), (int)(model.normals.size() / 3), (int)(model.uvs.size() / 2)));
-                c.p += std::strspn(c.p, " \t\r");
+double seconds_since(const std::chrono::steady_clock::time_point &t0) {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+} // namespace
+
+bool load_obj(const std::string &obj_file, const std::string &materials_directory, Model &model, std::string &error, bool verbose,
+              unsigned threads, LoadStats *stats) {
+    const auto t_start = std::chrono::steady_clock::now();
+    if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+    const int fd = ::open(obj_file.c_str(), O_RDONLY);
+    struct stat st;
+    if (fd < 0 || ::fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) {
+        if (fd >= 0) ::close(fd);
+        error = "Cannot open file [" + obj_file + "]\n";
+        return false;
+    }
+    const size_t size = (size_t)st.st_size;
+    Pod<char> text;
+    text.resize_uninitialized(size + 1);
+    text[size] = '\0';
+    {   // the file into memory, in parallel slices (page-cache copies scale with threads)
+        const size_t slice = 64u << 20;
+        const size_t n_slices = (size + slice - 1) / slice;
+        std::atomic<bool> bad(false);
+        run_parallel(threads, n_slices, [&](size_t i) {
+            size_t off = i * slice;
+            const size_t stop = std::min(size, off + slice);
+            while (off < stop) {
+                const ssize_t got = ::pread(fd, text.data() + off, stop - off, (off_t)off);
+                if (got <= 0) { bad = true; return; }
+                off += (size_t)got;
             }
-            pending.push_back(face);
-        } else if (!std::strncmp(c.p, "usemtl", 6) && is_blank(c.p[6])) {
-            c.p += 7;
-            const std::string name = c.word();
-            const auto it = mtl_by_name.find(name);
-            const int id = it != mtl_by_name.end() ? it->second : -1;
-            if (id != material) { // per-face materials: flush into the current shape, keep the shape open
-                flush_faces();
-                pending.clear();
-                material = id;
-            }
-        } else if (!std::strncmp(c.p, "mtllib", 6) && is_blank(c.p[6])) {
-            std::istringstream names(std::string(c.p + 7));
-            std::string fn;
-            bool any = false, found = false;
-            while (std::getline(names, fn, ' ')) {
-                any = true;
-                const std::string path = materials_directory.empty() ? fn : materials_directory + fn; // plain concatenation
-                std::ifstream mf(path.c_str());
-                if (!mf) { warn << "WARN: Material file [ " << path << " ] not found." << std::endl; continue; }
-                parse_mtl(mf, mtl, mtl_by_name);
-                found = true;
-                break;
-            }
-            if (!any) warn << "WARN: Looks like empty filename for mtllib. Use default material. \n";
-            else if (!found) warn << "WARN: Failed to load material file(s). Use default material.\n";
-        } else if ((c.p[0] == 'g' || c.p[0] == 'o') && is_blank(c.p[1])) {
-            // a new group / object closes the shape; as in tinyobjloader 1.0.5 the shape is kept only if faces
-            // were still pending at this point
-            if (flush_faces()) shapes.push_back(shape);
-            shape.clear();
-            pending.clear();
+        });
+        ::close(fd);
+        if (bad) { error = "Cannot read file [" + obj_file + "]\n"; return false; }
+    }
+    const double t_read = seconds_since(t_start);
+    const char *begin = text.data(), *end = begin + size;
+
+    // pieces of about 4 MB, each starting at a line start
+    std::vector<Piece> pieces;
+    {
+        const size_t target = std::max<size_t>(size / (threads * 8u) + 1, 1u << 20);
+        const char *p = begin;
+        while (p < end) {
+            const char *q = (size_t)(end - p) > target ? p + target : end;
+            if (q < end) { Line ln; q = scan_line(q, end, ln); } // finish the line q falls into
+            Piece pc;
+            pc.b = p; pc.e = q;
+            pieces.push_back(pc);
+            p = q;
         }
     }
-    const bool flushed = flush_faces();
-    if (flushed || !shape.empty()) shapes.push_back(shape);
+
+    // pass 1: counts per piece and per segment; the structural lines
+    std::vector<std::vector<Segment>> piece_segments(pieces.size());
+    run_parallel(threads, pieces.size(), [&](size_t i) {
+        Piece &pc = pieces[i];
+        std::vector<Segment> &segs = piece_segments[i];
+        segs.emplace_back();
+        Line ln;
+        for (const char *p = pc.b; p < pc.e;) {
+            p = scan_line(p, pc.e, ln);
+            const char *body = nullptr;
+            switch (classify(ln, body)) {
+                case Kind::V: ++pc.nv; break;
+                case Kind::VN: ++pc.nvn; break;
+                case Kind::VT: ++pc.nvt; break;
+                case Kind::F: {
+                    const char *c = body;
+                    while (c < ln.e && is_blank(*c)) ++c;
+                    uint64_t corners = 0;
+                    while (c < ln.e) {
+                        parse_corner<false>(c, ln.e, 0, 0, 0);
+                        skip_corner_gap(c, ln.e);
+                        ++corners;
+                    }
+                    ++segs.back().faces;
+                    if (corners >= 3) segs.back().tris += corners - 2;
+                    break;
+                }
+                case Kind::UseMtl: pc.events.push_back(Event{Kind::UseMtl, ln, body}); segs.emplace_back(); break;
+                case Kind::MtlLib: pc.events.push_back(Event{Kind::MtlLib, ln, body}); segs.emplace_back(); break;
+                case Kind::Group: pc.events.push_back(Event{Kind::Group, ln, nullptr}); segs.emplace_back(); break;
+                case Kind::Skip: break;
+            }
+        }
+    });
+    const double t_scan = seconds_since(t_start);
+
+    // between the passes (sequential, a few structural lines): materials, which segments survive, where they go
+    std::vector<MtlEntry> mtl;
+    std::map<std::string, int> mtl_by_name;
+    std::ostringstream warn;
+    std::vector<Segment> segments;
+    std::vector<uint64_t> shape_tris; // triangles per exported shape, for the progress lines
+    {
+        uint64_t v = 0, vn = 0, vt = 0;
+        for (size_t i = 0; i < pieces.size(); ++i) {
+            pieces[i].v0 = v; pieces[i].vn0 = vn; pieces[i].vt0 = vt;
+            v += pieces[i].nv; vn += pieces[i].nvn; vt += pieces[i].nvt;
+            pieces[i].first_segment = segments.size();
+            segments.insert(segments.end(), piece_segments[i].begin(), piece_segments[i].end());
+        }
+        model.positions.resize_uninitialized(v * 3);
+        model.normals.resize_uninitialized(vn * 3);
+        model.uvs.resize_uninitialized(vt * 2);
+
+        int material = -1;
+        std::vector<size_t> pending, shape; // segment ids: faces since the last flush / flushed into the open shape
+        uint64_t pending_faces = 0;
+        auto flush = [&]() { // exportFaceGroupToShape: true iff any face line was pending
+            if (pending_faces == 0) { pending.clear(); return false; }
+            shape.insert(shape.end(), pending.begin(), pending.end());
+            pending.clear();
+            pending_faces = 0;
+            return true;
+        };
+        auto close_shape = [&](bool keep) {
+            uint64_t n = 0;
+            for (size_t id : shape) { segments[id].keep = keep; n += segments[id].tris; }
+            if (keep) shape_tris.push_back(n);
+            shape.clear();
+        };
+        for (size_t i = 0; i < pieces.size(); ++i) {
+            const Piece &pc = pieces[i];
+            for (size_t k = 0; k <= pc.events.size(); ++k) {
+                if (k > 0) { // the structural line that opens segment k of the piece
+                    const Event &ev = pc.events[k - 1];
+                    if (ev.kind == Kind::UseMtl) {
+                        const char *w = ev.body;
+                        while (w < ev.line.e && (*w == ' ' || *w == '\t' || *w == '\r' || *w == '\n')) ++w;
+                        const char *we = w;
+                        while (we < ev.line.e && !(*we == ' ' || *we == '\t' || *we == '\r' || *we == '\n')) ++we;
+                        const auto it = mtl_by_name.find(std::string(w, we));
+                        const int id = it != mtl_by_name.end() ? it->second : -1;
+                        if (id != material) { // per-face materials: flush into the current shape, keep the shape open
+                            flush();
+                            material = id;
+                        }
+                    } else if (ev.kind == Kind::MtlLib) {
+                        std::istringstream names(std::string(ev.body, ev.line.e));
+                        std::string fn;
+                        bool any = false, found = false;
+                        while (std::getline(names, fn, ' ')) {
+                            any = true;
+                            const std::string path = materials_directory.empty() ? fn : materials_directory + fn; // plain concatenation
+                            std::ifstream mf(path.c_str());
+                            if (!mf) { warn << "WARN: Material file [ " << path << " ] not found." << std::endl; continue; }
+                            parse_mtl(mf, mtl, mtl_by_name);
+                            found = true;
+                            break;
+                        }
+                        if (!any) warn << "WARN: Looks like empty filename for mtllib. Use default material. \n";
+                        else if (!found) warn << "WARN: Failed to load material file(s). Use default material.\n";
+                    } else { // g / o: the shape is exported only if faces were still pending (tinyobjloader 1.0.5)
+                        close_shape(flush());
+                    }
+                }
+                const size_t id = pc.first_segment + k;
+                segments[id].material = material;
+                pending.push_back(id);
+                pending_faces += segments[id].faces;
+            }
+        }
+        const bool flushed = flush();
+        uint64_t in_shape = 0;
+        for (size_t id : shape) in_shape += segments[id].tris;
+        if (flushed || in_shape > 0) close_shape(true);
+        uint64_t t = 0;
+        for (Segment &sg : segments)
+            if (sg.keep) { sg.tri_offset = t; t += sg.tris; }
+        model.tris.resize_uninitialized(t * 10);
+    }
+    const double t_resolve = seconds_since(t_start);
+
+    // pass 2: every piece parses its lines into place
+    run_parallel(threads, pieces.size(), [&](size_t i) {
+        const Piece &pc = pieces[i];
+        float *pos = model.positions.data() + pc.v0 * 3, *nrm = model.normals.data() + pc.vn0 * 3, *uv = model.uvs.data() + pc.vt0 * 2;
+        int nv = (int)pc.v0, nvn = (int)pc.vn0, nvt = (int)pc.vt0;
+        size_t seg = pc.first_segment;
+        int32_t *out = model.tris.data() + segments[seg].tri_offset * 10;
+        Line ln;
+        for (const char *p = pc.b; p < pc.e;) {
+            p = scan_line(p, pc.e, ln);
+            const char *body = nullptr;
+            switch (classify(ln, body)) {
+                case Kind::V: for (int k = 0; k < 3; ++k) *pos++ = number(body, ln.e); ++nv; break;
+                case Kind::VN: for (int k = 0; k < 3; ++k) *nrm++ = number(body, ln.e); ++nvn; break;
+                case Kind::VT: for (int k = 0; k < 2; ++k) *uv++ = number(body, ln.e); ++nvt; break;
+                case Kind::F: {
+                    const Segment &sg = segments[seg];
+                    if (!sg.keep) break;
+                    const char *c = body;
+                    while (c < ln.e && is_blank(*c)) ++c;
+                    Corner c0 = {-1, -1, -1}, c2 = c0;
+                    for (uint64_t k = 0; c < ln.e; ++k) { // fan (f0, f[k-1], f[k]), one material id per triangle
+                        const Corner cur = parse_corner<true>(c, ln.e, nv, nvn, nvt);
+                        skip_corner_gap(c, ln.e);
+                        if (k == 0) { c0 = cur; continue; }
+                        const Corner c1 = c2;
+                        c2 = cur;
+                        if (k >= 2) {
+                            const int32_t t[10] = {c0.v, c1.v, c2.v, c0.vn, c1.vn, c2.vn, c0.vt, c1.vt, c2.vt, sg.material};
+                            std::memcpy(out, t, sizeof t);
+                            out += 10;
+                        }
+                    }
+                    break;
+                }
+                case Kind::UseMtl: case Kind::MtlLib: case Kind::Group:
+                    ++seg;
+                    out = model.tris.data() + segments[seg].tri_offset * 10;
+                    break;
+                case Kind::Skip: break;
+            }
+        }
+    });
+    const double t_parse = seconds_since(t_start);
 
     error = warn.str();
     // load_materials (fileloader.cpp:47-58)
@@ -335,11 +583,73 @@ bool load_obj(const std::string &obj_file, const std::string &materials_director
         model.materials.push_back(m);
     }
     // load_triangles per shape (fileloader.cpp:60-77,116-118)
-    for (const std::vector<int32_t> &s : shapes) {
-        if (verbose) std::cout << "Loading " << s.size() / 10 << " triangles..." << std::endl;
-        model.tris.insert(model.tris.end(), s.begin(), s.end());
+    if (verbose) {
+        for (uint64_t n : shape_tris) std::cout << "Loading " << n << " triangles..." << std::endl;
+        std::cout << "Loaded model " << obj_file << "." << std::endl;
     }
-    if (verbose) std::cout << "Loaded model " << obj_file << "." << std::endl;
+    if (stats) {
+        stats->threads = threads;
+        stats->file_bytes = size;
+        stats->read_s = t_read; stats->scan_s = t_scan - t_read; stats->resolve_s = t_resolve - t_scan; stats->parse_s = t_parse - t_resolve;
+        stats->total_s = seconds_since(t_start);
+    }
+    return true;
+}
+
+// ---- binary mesh cache ---------------------------------------------------------------------------------------
+namespace {
+struct CacheHeader {
+    char magic[8];          // "RASTMESH"
+    uint32_t version, n_materials;
+    uint64_t n_pos, n_nrm, n_uv, n_tri_ints;
+};
+bool write_all(std::FILE *f, const void *p, size_t n) { return n == 0 || std::fwrite(p, 1, n, f) == n; }
+bool read_all(std::FILE *f, void *p, size_t n) { return n == 0 || std::fread(p, 1, n, f) == n; }
+} // namespace
+
+bool save_mesh_cache(const std::string &file, const Model &model, std::string &error) {
+    std::FILE *f = std::fopen(file.c_str(), "wb");
+    if (!f) { error = "Cannot write mesh cache [" + file + "]"; return false; }
+    CacheHeader h = {{'R', 'A', 'S', 'T', 'M', 'E', 'S', 'H'}, 1u, (uint32_t)model.materials.size(),
+                     model.positions.size(), model.normals.size(), model.uvs.size(), model.tris.size()};
+    bool ok = write_all(f, &h, sizeof h) && write_all(f, model.positions.data(), model.positions.size() * 4) &&
+              write_all(f, model.normals.data(), model.normals.size() * 4) && write_all(f, model.uvs.data(), model.uvs.size() * 4) &&
+              write_all(f, model.tris.data(), model.tris.size() * 4);
+    for (const MaterialData &m : model.materials) {
+        const uint32_t len = m.has_texture ? (uint32_t)m.texture_file.size() : 0u;
+        ok = ok && write_all(f, m.kd, 12) && write_all(f, &len, 4) && write_all(f, m.texture_file.data(), len);
+    }
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok) error = "Cannot write mesh cache [" + file + "]";
+    return ok;
+}
+
+bool load_mesh_cache(const std::string &file, Model &model, std::string &error, bool verbose) {
+    std::FILE *f = std::fopen(file.c_str(), "rb");
+    if (!f) { error = "Cannot open mesh cache [" + file + "]"; return false; }
+    CacheHeader h;
+    bool ok = read_all(f, &h, sizeof h) && !std::memcmp(h.magic, "RASTMESH", 8) && h.version == 1u;
+    if (ok) {
+        model.positions.resize_uninitialized(h.n_pos); model.normals.resize_uninitialized(h.n_nrm);
+        model.uvs.resize_uninitialized(h.n_uv); model.tris.resize_uninitialized(h.n_tri_ints);
+        ok = read_all(f, model.positions.data(), h.n_pos * 4) && read_all(f, model.normals.data(), h.n_nrm * 4) &&
+             read_all(f, model.uvs.data(), h.n_uv * 4) && read_all(f, model.tris.data(), h.n_tri_ints * 4);
+    }
+    for (uint32_t i = 0; ok && i < h.n_materials; ++i) {
+        MaterialData m;
+        uint32_t len = 0;
+        ok = read_all(f, m.kd, 12) && read_all(f, &len, 4) && len < (1u << 20);
+        std::string tex(len, '\0');
+        ok = ok && read_all(f, &tex[0], len);
+        if (ok && len) {
+            std::string terr;
+            if (!load_texture(tex, m, terr, verbose)) { error = terr; std::fclose(f); return false; }
+        }
+        if (ok) model.materials.push_back(m);
+    }
+    std::fclose(f);
+    if (!ok) { error = "Bad mesh cache [" + file + "]"; return false; }
+    if (verbose) std::cout << "Loaded model " << file << "." << std::endl;
     return true;
 }
 

@@ -10,6 +10,9 @@
 #pragma once
 
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -30,16 +33,70 @@ struct Light {              // struct Light (headers/light.h:7-14)
     float trans_dir[3];
 };
 
+// Growable array of a trivially-copyable type whose resize leaves new elements UNINITIALISED: the parallel
+// OBJ loader sizes the output once and lets each worker thread first-touch the part it writes (a
+// std::vector would zero gigabytes on one thread first).
+template <class T> class Pod {
+public:
+    Pod() = default;
+    Pod(const Pod &) = delete;
+    Pod &operator=(const Pod &) = delete;
+    Pod(Pod &&o) noexcept : p_(o.p_), n_(o.n_), cap_(o.cap_) { o.p_ = nullptr; o.n_ = o.cap_ = 0; }
+    Pod &operator=(Pod &&o) noexcept { if (this != &o) { std::free(p_); p_ = o.p_; n_ = o.n_; cap_ = o.cap_; o.p_ = nullptr; o.n_ = o.cap_ = 0; } return *this; }
+    ~Pod() { std::free(p_); }
+    T *data() { return p_; }
+    const T *data() const { return p_; }
+    size_t size() const { return n_; }
+    bool empty() const { return n_ == 0; }
+    T &operator[](size_t i) { return p_[i]; }
+    const T &operator[](size_t i) const { return p_[i]; }
+    T *begin() { return p_; }
+    T *end() { return p_ + n_; }
+    const T *begin() const { return p_; }
+    const T *end() const { return p_ + n_; }
+    void clear() { n_ = 0; }
+    void resize_uninitialized(size_t n) {
+        if (n > cap_) {
+            T *q = static_cast<T *>(std::realloc(p_, n * sizeof(T)));
+            if (!q) throw std::bad_alloc();
+            p_ = q; cap_ = n;
+        }
+        n_ = n;
+    }
+    void assign(const T *first, const T *last) {
+        resize_uninitialized((size_t)(last - first));
+        if (n_) std::memcpy(p_, first, n_ * sizeof(T));
+    }
+private:
+    T *p_ = nullptr;
+    size_t n_ = 0, cap_ = 0;
+};
+
 struct Model {
-    std::vector<float> positions, normals, uvs;
-    std::vector<int32_t> tris; // 10 per triangle
+    Pod<float> positions, normals, uvs;
+    Pod<int32_t> tris; // 10 per triangle
     std::vector<MaterialData> materials;
     size_t n_tris() const { return tris.size() / 10; }
 };
 
+struct LoadStats {          // filled by load_obj when non-null (tools/bench_loader, tests)
+    unsigned threads = 0;
+    size_t file_bytes = 0;
+    double read_s = 0, scan_s = 0, resolve_s = 0, parse_s = 0, total_s = 0;
+};
+
 // load_obj (fileloader.cpp:79-121).  Prints the reference's progress lines to stdout.  Returns false with
 // `error` set when the .obj cannot be read; warnings (missing .mtl) go to `error` with a true return.
-bool load_obj(const std::string &obj_file, const std::string &materials_directory, Model &model, std::string &error, bool verbose = true);
+// The file is read into memory once and parsed by `threads` workers (0 = all hardware threads) in two passes:
+// count, then parse straight into the final arrays.  The result is independent of the thread count.
+bool load_obj(const std::string &obj_file, const std::string &materials_directory, Model &model, std::string &error, bool verbose = true,
+              unsigned threads = 0, LoadStats *stats = nullptr);
+
+// Binary mesh cache (host extension, opt-in with --mesh-cache): the arrays load_obj produced, written verbatim
+// with a small header, so a 50 M-triangle scene is read back at memory-copy speed instead of re-parsed.
+// Textures are not cached (they are re-read from materials_directory through the stored names).
+bool save_mesh_cache(const std::string &file, const Model &model, std::string &error);
+bool load_mesh_cache(const std::string &file, Model &model, std::string &error, bool verbose = true);
 
 // load_lights (fileloader.cpp:123-133): rows of direction_x,dir_y,dir_z,intensity,red,green,blue.
 bool load_lights(const std::string &file, std::vector<Light> &lights, std::string &error);
