@@ -43,6 +43,8 @@ const Flag kFlags[] = {
     {"", "frame-out", Kind::String, false, "file.png", "[extension] colour output (default frame.png)"},
     {"", "depth-out", Kind::String, false, "file.png", "[extension] depth output (default depth.png)"},
     {"", "quiet", Kind::Switch, false, "", "[extension] no progress output"},
+    {"", "mesh-cache", Kind::String, false, "file.rastmesh", "[extension] binary copy of the parsed model: read it if present, else parse the .obj and write it"},
+    {"", "load-threads", Kind::UInt, false, "count", "[extension] threads parsing the .obj (default: all hardware threads)"},
     {"", "flat-mode", Kind::String, false, "reference|face", "[extension] what -f does: 'reference' = nothing, like the reference (default); 'face' = one normal per face"},
 };
 const int kNumFlags = (int)(sizeof kFlags / sizeof kFlags[0]);
@@ -133,6 +135,8 @@ ParseResult parse_args(int argc, const char *const *argv, Args &args, std::strin
         else if (n == "frame-out") args.frame_out = value;
         else if (n == "depth-out") args.depth_out = value;
         else if (n == "quiet") args.quiet = true;
+        else if (n == "mesh-cache") args.mesh_cache = value;
+        else if (n == "load-threads") args.load_threads = (unsigned)num;
         else if (n == "flat-mode") {
             if (value != "reference" && value != "face") { message = "PARSE ERROR: Argument: (--flat-mode)\n             Value '" + value + "' does not meet constraint: reference|face"; return ParseResult::Error; }
             args.flat_face = value == "face";

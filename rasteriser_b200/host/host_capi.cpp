@@ -19,6 +19,28 @@ void *rasth_load_obj(const char *obj_file, const char *mats_dir, char *err, int 
     if (!ok) { delete m; return nullptr; }
     return m;
 }
+// the same with an explicit thread count; stats = {threads, file_bytes, read_s, scan_s, resolve_s, parse_s, total_s}
+void *rasth_load_obj_mt(const char *obj_file, const char *mats_dir, unsigned threads, double stats[7], char *err, int err_cap) {
+    host::Model *m = new host::Model();
+    std::string e;
+    host::LoadStats st;
+    const bool ok = host::load_obj(obj_file, mats_dir ? mats_dir : "", *m, e, false, threads, &st);
+    if (err && err_cap > 0) { std::strncpy(err, e.c_str(), (size_t)err_cap - 1); err[err_cap - 1] = 0; }
+    if (stats) { stats[0] = st.threads; stats[1] = (double)st.file_bytes; stats[2] = st.read_s; stats[3] = st.scan_s; stats[4] = st.resolve_s; stats[5] = st.parse_s; stats[6] = st.total_s; }
+    if (!ok) { delete m; return nullptr; }
+    return m;
+}
+void rasth_set_obj_piece_bytes(uint64_t bytes) { host::set_obj_piece_bytes((size_t)bytes); }
+int rasth_save_mesh_cache(void *h, const char *file) {
+    std::string e;
+    return host::save_mesh_cache(file, *static_cast<host::Model *>(h), e) ? 0 : -1;
+}
+void *rasth_load_mesh_cache(const char *file) {
+    host::Model *m = new host::Model();
+    std::string e;
+    if (!host::load_mesh_cache(file, *m, e, false)) { delete m; return nullptr; }
+    return m;
+}
 void rasth_model_free(void *h) { delete static_cast<host::Model *>(h); }
 void rasth_model_sizes(void *h, uint64_t out[5]) {
     host::Model *m = static_cast<host::Model *>(h);
@@ -50,6 +72,7 @@ int rasth_load_lights(const char *file, float *out7, int capacity) {
     return (int)l.size();
 }
 float rasth_parse_float(const char *s) { return host::parse_obj_float(s, s + std::strlen(s)); }
+void rasth_png_set_threads(unsigned threads) { host::png_set_threads(threads); }
 int rasth_png_write(const char *path, const uint8_t *planar, uint32_t w, uint32_t h, uint32_t c) { return host::png_write_planar(path, planar, w, h, c).empty() ? 0 : -1; }
 int rasth_png_read(const char *path, uint32_t dims[3], uint8_t *out, uint64_t cap) {
     host::PngImage img;

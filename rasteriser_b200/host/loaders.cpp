@@ -1,6 +1,7 @@
 #include "loaders.hpp"
 
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -150,6 +151,9 @@ void parse_mtl(std::istream &in, std::vector<MtlEntry> &materials, std::map<std:
 // as ldexp(mantissa * 5^e, e); the double is then narrowed to float.  A malformed token yields the default.
 float parse_obj_float(const char *s, const char *end, double dflt) {
     static const double kNegPow10[] = {1.0, 0.1, 0.01, 0.001, 0.0001, 0.00001, 0.000001, 0.0000001};
+    // beyond the literal table tinyobjloader calls pow(10.0, -n) for every digit; the same calls, made once
+    constexpr int kPowTable = 64;
+    static const struct Pow { double v[kPowTable]; Pow() { for (int i = 0; i < kPowTable; ++i) v[i] = std::pow(10.0, -i); } } kPow;
     double value = dflt;
     do {
         if (s >= end) break;
@@ -170,7 +174,7 @@ float parse_obj_float(const char *s, const char *end, double dflt) {
                 ++c;
                 n_read = 1;
                 while (c != end && is_digit(*c)) {
-                    mantissa += (int)(*c - '0') * (n_read < 8 ? kNegPow10[n_read] : std::pow(10.0, -n_read));
+                    mantissa += (int)(*c - '0') * (n_read < 8 ? kNegPow10[n_read] : (n_read < kPowTable ? kPow.v[n_read] : std::pow(10.0, -n_read)));
                     ++n_read;
                     ++c;
                 }
@@ -349,11 +353,15 @@ template <class Fn> void run_parallel(unsigned threads, size_t n, Fn fn) {
     for (std::thread &t : pool) t.join();
 }
 
+size_t g_piece_bytes = 0; // test hook: forces the piece size so that small files exercise the piece boundaries
+
 double seconds_since(const std::chrono::steady_clock::time_point &t0) {
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 } // namespace
+
+void set_obj_piece_bytes(size_t bytes) { g_piece_bytes = bytes; }
 
 bool load_obj(const std::string &obj_file, const std::string &materials_directory, Model &model, std::string &error, bool verbose,
               unsigned threads, LoadStats *stats) {
@@ -367,10 +375,22 @@ bool load_obj(const std::string &obj_file, const std::string &materials_director
         return false;
     }
     const size_t size = (size_t)st.st_size;
-    Pod<char> text;
-    text.resize_uninitialized(size + 1);
-    text[size] = '\0';
-    {   // the file into memory, in parallel slices (page-cache copies scale with threads)
+    // The text is mapped, not copied: the pages are faulted in by the worker threads of pass 1.  The parser may look
+    // one byte past a token, so a NUL must follow the text -- the zero fill of the last mapped page provides it,
+    // except when the size is an exact multiple of the page size; then the file is read into a buffer instead.
+    struct Text {
+        const char *p = nullptr; size_t mapped = 0; Pod<char> owned;
+        ~Text() { if (mapped) ::munmap(const_cast<char *>(p), mapped); }
+    } text;
+    const size_t page = (size_t)::sysconf(_SC_PAGESIZE);
+    if (size > 0 && size % page != 0) {
+        void *m = ::mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m != MAP_FAILED) { text.p = static_cast<const char *>(m); text.mapped = size; ::madvise(m, size, MADV_WILLNEED); }
+    }
+    if (!text.p) {
+        text.owned.resize_uninitialized(size + 1);
+        text.owned[size] = '\0';
+        text.p = text.owned.data();
         const size_t slice = 64u << 20;
         const size_t n_slices = (size + slice - 1) / slice;
         std::atomic<bool> bad(false);
@@ -378,21 +398,21 @@ bool load_obj(const std::string &obj_file, const std::string &materials_director
             size_t off = i * slice;
             const size_t stop = std::min(size, off + slice);
             while (off < stop) {
-                const ssize_t got = ::pread(fd, text.data() + off, stop - off, (off_t)off);
+                const ssize_t got = ::pread(fd, text.owned.data() + off, stop - off, (off_t)off);
                 if (got <= 0) { bad = true; return; }
                 off += (size_t)got;
             }
         });
-        ::close(fd);
-        if (bad) { error = "Cannot read file [" + obj_file + "]\n"; return false; }
+        if (bad) { ::close(fd); error = "Cannot read file [" + obj_file + "]\n"; return false; }
     }
+    ::close(fd);
     const double t_read = seconds_since(t_start);
-    const char *begin = text.data(), *end = begin + size;
+    const char *begin = text.p, *end = begin + size;
 
-    // pieces of about 4 MB, each starting at a line start
+    // pieces of at least 1 MB (8 per thread), each starting at a line start
     std::vector<Piece> pieces;
     {
-        const size_t target = std::max<size_t>(size / (threads * 8u) + 1, 1u << 20);
+        const size_t target = g_piece_bytes ? g_piece_bytes : std::max<size_t>(size / (threads * 8u) + 1, 1u << 20);
         const char *p = begin;
         while (p < end) {
             const char *q = (size_t)(end - p) > target ? p + target : end;

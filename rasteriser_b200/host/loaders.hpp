@@ -92,6 +92,8 @@ struct LoadStats {          // filled by load_obj when non-null (tools/bench_loa
 bool load_obj(const std::string &obj_file, const std::string &materials_directory, Model &model, std::string &error, bool verbose = true,
               unsigned threads = 0, LoadStats *stats = nullptr);
 
+void set_obj_piece_bytes(size_t bytes); // test hook: 0 = automatic
+
 // Binary mesh cache (host extension, opt-in with --mesh-cache): the arrays load_obj produced, written verbatim
 // with a small header, so a 50 M-triangle scene is read back at memory-copy speed instead of re-parsed.
 // Textures are not cached (they are re-read from materials_directory through the stored names).

@@ -29,11 +29,16 @@ struct Tri { int32_t i[10]; }; // struct Triangle (headers/face.h:6-13)
 struct Vec3 { float x, y, z; };
 struct Vec2 { float x, y; };
 
-template <class T, class U> std::vector<T> pack(const std::vector<U> &flat) {
-    std::vector<T> out(flat.size() * sizeof(U) / sizeof(T));
-    if (!out.empty()) memcpy(out.data(), flat.data(), out.size() * sizeof(T));
-    return out;
-}
+// The loader's flat arrays seen as the reference's vector<vec3> / vector<vec2> / vector<Triangle>: same bytes, no copy
+// (a 50 M-triangle scene is 2 GB of indices).
+template <class T> struct View {
+    typedef T value_type;
+    const T *p;
+    size_t n;
+    const T *data() const { return p; }
+    size_t size() const { return n; }
+};
+template <class T, class U> View<T> view(const host::Pod<U> &flat) { return View<T>{reinterpret_cast<const T *>(flat.data()), flat.size() * sizeof(U) / sizeof(T)}; }
 
 } // namespace
 
@@ -55,15 +60,24 @@ int main(int argc, char **argv) {
     std::string err;
     if (!host::load_lights(arguments.lights_file, lights, err)) { std::cerr << err << std::endl; return 1; } // renderer.cpp:75
     if (!arguments.obj_file.empty()) {                                                                        // renderer.cpp:78-82
-        const bool ok = host::load_obj(arguments.obj_file, arguments.materials_directory, model, err, verbose);
-        if (!err.empty()) std::cerr << err << std::endl; // fileloader.cpp:95-97
-        if (!ok) return 1;
+        bool cached = false;
+        if (!arguments.mesh_cache.empty()) {
+            std::string cerr_text;
+            cached = host::load_mesh_cache(arguments.mesh_cache, model, cerr_text, verbose);
+            if (!cached) model = host::Model();
+        }
+        if (!cached) {
+            const bool ok = host::load_obj(arguments.obj_file, arguments.materials_directory, model, err, verbose, arguments.load_threads);
+            if (!err.empty()) std::cerr << err << std::endl; // fileloader.cpp:95-97
+            if (!ok) return 1;
+            if (!arguments.mesh_cache.empty() && !host::save_mesh_cache(arguments.mesh_cache, model, err)) std::cerr << err << std::endl;
+        }
     } else {
         host::add_square(model);
     }
-    const std::vector<Vec3> vertices = pack<Vec3>(model.positions), normals = pack<Vec3>(model.normals);
-    const std::vector<Vec2> uvs = pack<Vec2>(model.uvs);
-    const std::vector<Tri> faces = pack<Tri>(model.tris);
+    const View<Vec3> vertices = view<Vec3>(model.positions), normals = view<Vec3>(model.normals);
+    const View<Vec2> uvs = view<Vec2>(model.uvs);
+    const View<Tri> faces = view<Tri>(model.tris);
 
     // renderer.cpp:85-86
     Image<unsigned char> frame_buffer(arguments.image_width, arguments.image_height, 3, 0);

@@ -1,8 +1,10 @@
 #include "png.hpp"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include <zlib.h>
 
@@ -115,42 +117,127 @@ std::string png_read(const std::string &path, PngImage &out) {
     return "";
 }
 
-std::string png_write(const std::string &path, const uint8_t *interleaved, unsigned width, unsigned height, unsigned channels) {
+// ---- writer ------------------------------------------------------------------------------------------------------
+// The image is cut into bands of rows, one per worker thread.  Each band is filtered (type 0) and deflated on its
+// own as a raw deflate stream that ends on a byte boundary (Z_SYNC_FLUSH; the last band ends the stream with
+// Z_FINISH), so the concatenation of the band streams between one zlib header and the Adler-32 of the whole image
+// is ONE valid zlib stream -- the pigz construction.  Every band becomes its own IDAT chunk (a decoder
+// concatenates IDAT payloads, PNG spec 11.2.4), with its CRC computed by the band's thread as well.
+namespace {
+
+unsigned g_png_threads = 0; // 0 = hardware threads
+
+struct Band {
+    unsigned y0 = 0, y1 = 0;
+    std::vector<uint8_t> chunk; // complete IDAT chunk: length, "IDAT", payload, CRC
+    uLong adler = 1;            // Adler-32 of the band's filtered bytes
+    uLong raw_len = 0;
+    bool ok = false;
+};
+
+// rows(y, dst): writes the `stride` interleaved bytes of row y
+template <class RowFn>
+std::string write_png_file(const std::string &path, unsigned width, unsigned height, unsigned channels, RowFn rows) {
     if (channels < 1 || channels > 4) return "png_write: 1..4 channels";
     static const uint8_t colour_of[5] = {0, 0, 4, 2, 6};
     const size_t stride = (size_t)width * channels;
-    std::vector<uint8_t> raw((stride + 1) * height);
-    for (unsigned y = 0; y < height; ++y) { // filter type 0 (None) per row: fastest, values are what matters
-        raw[(stride + 1) * y] = 0;
-        std::memcpy(&raw[(stride + 1) * y + 1], interleaved + stride * y, stride);
+    unsigned threads = g_png_threads ? g_png_threads : std::max(1u, std::thread::hardware_concurrency());
+    // at least 64 KB of pixels per band, so that restarting the deflate window costs nothing measurable
+    const size_t min_rows = std::max<size_t>(1, (64u << 10) / std::max<size_t>(stride, 1));
+    const unsigned n_bands = (unsigned)std::max<size_t>(1, std::min<size_t>(threads, height / min_rows));
+    std::vector<Band> bands(n_bands);
+    for (unsigned b = 0; b < n_bands; ++b) {
+        bands[b].y0 = (unsigned)((uint64_t)height * b / n_bands);
+        bands[b].y1 = (unsigned)((uint64_t)height * (b + 1) / n_bands);
     }
-    uLongf clen = compressBound((uLong)raw.size());
-    std::vector<uint8_t> comp(clen);
-    if (compress2(comp.data(), &clen, raw.data(), (uLong)raw.size(), 1) != Z_OK) return "png_write: deflate failed";
-    comp.resize(clen);
-
-    std::vector<uint8_t> file(kSignature, kSignature + 8), ihdr;
+    auto work = [&](unsigned b) {
+        Band &bd = bands[b];
+        const size_t n_rows = bd.y1 - bd.y0;
+        std::vector<uint8_t> raw((stride + 1) * n_rows);
+        for (size_t r = 0; r < n_rows; ++r) { // filter type 0 (None) per row: fastest, values are what matters
+            raw[(stride + 1) * r] = 0;
+            rows(bd.y0 + (unsigned)r, &raw[(stride + 1) * r + 1]);
+        }
+        bd.raw_len = (uLong)raw.size();
+        bd.adler = adler32(1L, raw.data(), (uInt)raw.size());
+        z_stream zs;
+        std::memset(&zs, 0, sizeof zs);
+        if (deflateInit2(&zs, 1, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return;
+        const size_t head = b == 0 ? 2 : 0, tail = b + 1 == n_bands ? 4 : 0; // zlib header / Adler-32 slot
+        bd.chunk.resize(8 + head + deflateBound(&zs, (uLong)raw.size()) + 16 + tail + 4);
+        uint8_t *payload = bd.chunk.data() + 8;
+        if (head) { payload[0] = 0x78; payload[1] = 0x01; } // deflate, 32 KB window, fastest level, no dictionary
+        zs.next_in = raw.data();
+        zs.avail_in = (uInt)raw.size();
+        zs.next_out = payload + head;
+        zs.avail_out = (uInt)(bd.chunk.size() - 8 - head - tail - 4);
+        const int rc = deflate(&zs, b + 1 == n_bands ? Z_FINISH : Z_SYNC_FLUSH);
+        const bool done = (b + 1 == n_bands) ? rc == Z_STREAM_END : (rc == Z_OK && zs.avail_in == 0 && zs.avail_out != 0);
+        const size_t clen = head + zs.total_out;
+        deflateEnd(&zs);
+        if (!done) return;
+        bd.chunk.resize(8 + clen + tail + 4); // the tail (Adler-32 of the whole image) is filled in by the caller
+        bd.ok = true;
+    };
+    if (n_bands == 1) work(0);
+    else {
+        std::vector<std::thread> pool;
+        for (unsigned b = 0; b < n_bands; ++b) pool.emplace_back(work, b);
+        for (std::thread &t : pool) t.join();
+    }
+    uLong adler = 1;
+    for (unsigned b = 0; b < n_bands; ++b) {
+        if (!bands[b].ok) return "png_write: deflate failed";
+        adler = b == 0 ? bands[0].adler : adler32_combine(adler, bands[b].adler, (z_off_t)bands[b].raw_len);
+    }
+    for (unsigned b = 0; b < n_bands; ++b) { // chunk framing: big-endian length, type, ..., CRC over type + payload
+        std::vector<uint8_t> &c = bands[b].chunk;
+        const size_t len = c.size() - 12;
+        if (b + 1 == n_bands) { c[8 + len - 4] = (uint8_t)(adler >> 24); c[8 + len - 3] = (uint8_t)(adler >> 16); c[8 + len - 2] = (uint8_t)(adler >> 8); c[8 + len - 1] = (uint8_t)adler; }
+        c[0] = (uint8_t)(len >> 24); c[1] = (uint8_t)(len >> 16); c[2] = (uint8_t)(len >> 8); c[3] = (uint8_t)len;
+        std::memcpy(&c[4], "IDAT", 4);
+        const uint32_t crc = (uint32_t)crc32(0L, &c[4], (uInt)(len + 4));
+        c[8 + len] = (uint8_t)(crc >> 24); c[9 + len] = (uint8_t)(crc >> 16); c[10 + len] = (uint8_t)(crc >> 8); c[11 + len] = (uint8_t)crc;
+    }
+    std::vector<uint8_t> head(kSignature, kSignature + 8), ihdr, tail;
     put_be32(ihdr, width);
     put_be32(ihdr, height);
     ihdr.push_back(8);
     ihdr.push_back(colour_of[channels]);
     ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);
-    put_chunk(file, "IHDR", ihdr);
-    put_chunk(file, "IDAT", comp);
-    put_chunk(file, "IEND", std::vector<uint8_t>());
+    put_chunk(head, "IHDR", ihdr);
+    put_chunk(tail, "IEND", std::vector<uint8_t>());
     FILE *f = std::fopen(path.c_str(), "wb");
     if (!f) return "cannot write " + path;
-    const bool ok = std::fwrite(file.data(), 1, file.size(), f) == file.size();
-    std::fclose(f);
+    bool ok = std::fwrite(head.data(), 1, head.size(), f) == head.size();
+    for (unsigned b = 0; ok && b < n_bands; ++b) ok = std::fwrite(bands[b].chunk.data(), 1, bands[b].chunk.size(), f) == bands[b].chunk.size();
+    ok = ok && std::fwrite(tail.data(), 1, tail.size(), f) == tail.size();
+    ok = (std::fclose(f) == 0) && ok;
     return ok ? "" : "short write to " + path;
 }
 
+} // namespace
+
+void png_set_threads(unsigned threads) { g_png_threads = threads; }
+
+std::string png_write(const std::string &path, const uint8_t *interleaved, unsigned width, unsigned height, unsigned channels) {
+    const size_t stride = (size_t)width * channels;
+    return write_png_file(path, width, height, channels, [=](unsigned y, uint8_t *dst) { std::memcpy(dst, interleaved + stride * y, stride); });
+}
+
+// planar [c][h][w] (CImg layout, CImg.h:11715-11721) -> file; the interleaving happens row by row inside the bands
 std::string png_write_planar(const std::string &path, const uint8_t *planar, unsigned width, unsigned height, unsigned channels) {
     const size_t plane = (size_t)width * height;
-    std::vector<uint8_t> inter(plane * channels);
-    for (unsigned c = 0; c < channels; ++c)
-        for (size_t i = 0; i < plane; ++i) inter[i * channels + c] = planar[c * plane + i];
-    return png_write(path, inter.data(), width, height, channels);
+    return write_png_file(path, width, height, channels, [=](unsigned y, uint8_t *dst) {
+        const uint8_t *row = planar + (size_t)y * width;
+        if (channels == 3) {
+            const uint8_t *r = row, *g = row + plane, *b = row + 2 * plane;
+            for (unsigned x = 0; x < width; ++x) { dst[3 * x] = r[x]; dst[3 * x + 1] = g[x]; dst[3 * x + 2] = b[x]; }
+        } else {
+            for (unsigned c = 0; c < channels; ++c)
+                for (unsigned x = 0; x < width; ++x) dst[(size_t)x * channels + c] = row[c * plane + x];
+        }
+    });
 }
 
 } // namespace host

@@ -19,6 +19,8 @@ struct PngImage {
 // Returns an empty string on success, else an error message.
 std::string png_read(const std::string &path, PngImage &out);
 std::string png_write(const std::string &path, const uint8_t *interleaved, unsigned width, unsigned height, unsigned channels);
+// The writer deflates bands of rows on several threads (0 = all hardware threads, the default).
+void png_set_threads(unsigned threads);
 // planar [c][h][w] (CImg layout) -> file
 std::string png_write_planar(const std::string &path, const uint8_t *planar, unsigned width, unsigned height, unsigned channels);
 

@@ -17,6 +17,12 @@ def lib():
         l = C.CDLL(build.build_host_lib())
         l.rasth_load_obj.restype = C.c_void_p
         l.rasth_load_obj.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+        l.rasth_load_obj_mt.restype = C.c_void_p
+        l.rasth_load_obj_mt.argtypes = [C.c_char_p, C.c_char_p, C.c_uint, C.c_void_p, C.c_char_p, C.c_int]
+        l.rasth_set_obj_piece_bytes.argtypes = [C.c_uint64]
+        l.rasth_save_mesh_cache.argtypes = [C.c_void_p, C.c_char_p]
+        l.rasth_load_mesh_cache.restype = C.c_void_p
+        l.rasth_load_mesh_cache.argtypes = [C.c_char_p]
         l.rasth_model_free.argtypes = [C.c_void_p]
         l.rasth_model_sizes.argtypes = [C.c_void_p, C.c_void_p]
         l.rasth_model_copy.argtypes = [C.c_void_p] + [C.c_void_p] * 4
@@ -31,13 +37,42 @@ def lib():
     return _lib
 
 
-def load_obj(path, mats_dir=""):
-    """-> dict(pos, nrm, uv, tris, materials=[dict(kd, texels)]), warnings"""
+def load_obj(path, mats_dir="", threads=0, stats=None):
+    """-> dict(pos, nrm, uv, tris, materials=[dict(kd, texels)]), warnings.  threads = OBJ parser threads (0 = all);
+    stats: optional dict that receives the loader's timings."""
     l = lib()
     err = C.create_string_buffer(4096)
-    h = l.rasth_load_obj(path.encode(), mats_dir.encode(), err, 4096)
+    st = (C.c_double * 7)()
+    h = l.rasth_load_obj_mt(path.encode(), mats_dir.encode(), threads, st, err, 4096)
     if not h:
         raise RuntimeError(err.value.decode())
+    if stats is not None:
+        stats.update(dict(zip(("threads", "file_bytes", "read_s", "scan_s", "resolve_s", "parse_s", "total_s"), list(st))))
+    return _model_to_dict(l, h), err.value.decode()
+
+
+def load_mesh_cache(path):
+    l = lib()
+    h = l.rasth_load_mesh_cache(path.encode())
+    if not h:
+        raise RuntimeError("cannot read mesh cache " + path)
+    return _model_to_dict(l, h)
+
+
+def save_mesh_cache(obj_path, mats_dir, cache_path, threads=0):
+    """Parse obj_path with the product loader and write its binary cache."""
+    l = lib()
+    err = C.create_string_buffer(4096)
+    h = l.rasth_load_obj_mt(obj_path.encode(), mats_dir.encode(), threads, None, err, 4096)
+    if not h:
+        raise RuntimeError(err.value.decode())
+    rc = l.rasth_save_mesh_cache(h, cache_path.encode())
+    l.rasth_model_free(h)
+    if rc != 0:
+        raise RuntimeError("cannot write mesh cache " + cache_path)
+
+
+def _model_to_dict(l, h):
     sz = np.zeros(5, np.uint64)
     l.rasth_model_sizes(h, sz.ctypes.data)
     pos, nrm = np.zeros((int(sz[0]), 3), np.float32), np.zeros((int(sz[1]), 3), np.float32)
@@ -53,7 +88,7 @@ def load_obj(path, mats_dir=""):
             l.rasth_model_material(h, i, kd.ctypes.data, info.ctypes.data, tex.ctypes.data)
         mats.append(dict(kd=tuple(float(x) for x in kd), texels=tex))
     l.rasth_model_free(h)
-    return dict(pos=pos, nrm=nrm, uv=uv, tris=tris, materials=mats), err.value.decode()
+    return dict(pos=pos, nrm=nrm, uv=uv, tris=tris, materials=mats)
 
 
 def load_lights(path):

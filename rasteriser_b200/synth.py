@@ -108,3 +108,34 @@ def random_lights(n, seed=12345):
     l[:, 3] = 1024.0 / n
     l[:, 4:7] = u[:, 3:4]
     return l
+
+
+def write_obj(path, positions, normals, uvs, tris, mtllib=None, usemtl=None, digits=9):
+    """Write the arrays as a Wavefront .obj (v / vn / vt / f i/j/k lines, 1-based) -- the input of the loader
+    benchmarks and tests.  %.{digits}g text of an fp32 value is not guaranteed to parse back to the same bits
+    through tinyobjloader's float reader; what matters is that the product loader and the reference's read the
+    SAME text identically.  Written in slices so an 8 M-triangle file does not need its text in memory at once."""
+    positions = np.asarray(positions, np.float32).reshape(-1, 3)
+    normals = np.asarray(normals, np.float32).reshape(-1, 3)
+    uvs = np.asarray(uvs, np.float32).reshape(-1, 2)
+    tris = np.asarray(tris, np.int32).reshape(-1, 10)
+    fmt = "%." + str(digits) + "g"
+    with open(path, "w") as f:
+        f.write("# written by rasteriser_b200.synth.write_obj\n")
+        if mtllib:
+            f.write("mtllib %s\n" % mtllib)
+        for tag, arr in (("v", positions), ("vn", normals), ("vt", uvs)):
+            line = tag + " " + " ".join([fmt] * arr.shape[1]) + "\n"
+            for s in range(0, len(arr), 1 << 18):
+                f.write("".join(line % tuple(r) for r in arr[s:s + (1 << 18)].tolist()))
+        if usemtl:
+            f.write("usemtl %s\n" % usemtl)
+        has_n, has_t = len(normals) > 0, len(uvs) > 0
+        for s in range(0, len(tris), 1 << 18):
+            t = tris[s:s + (1 << 18)].astype(np.int64) + 1
+            if has_n and has_t:
+                f.write("".join("f %d/%d/%d %d/%d/%d %d/%d/%d\n" % (r[0], r[6], r[3], r[1], r[7], r[4], r[2], r[8], r[5]) for r in t.tolist()))
+            elif has_n:
+                f.write("".join("f %d//%d %d//%d %d//%d\n" % (r[0], r[3], r[1], r[4], r[2], r[5]) for r in t.tolist()))
+            else:
+                f.write("".join("f %d %d %d\n" % (r[0], r[1], r[2]) for r in t.tolist()))

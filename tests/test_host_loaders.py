@@ -1,6 +1,7 @@
 """Host side of the product (C++ loaders, PNG codec, flag parser) against the reference's own loader
 output (tests/golden/scenes.npz came from fileloader.cpp + tinyobjloader) and, where the reference can be
 compiled (dev container), against it live on adversarial OBJ files.  CPU only."""
+import ctypes as C
 import os
 import shutil
 import tempfile
@@ -153,3 +154,160 @@ def test_flag_table_matches_reference():
     assert hostlib.parse_args(["renderer", "--version"])[0] == 2
     rc, a = hostlib.parse_args(["renderer", "-l", "a", "--", "--bogus"])
     assert rc == 0
+
+
+# ---- parallel OBJ reader (loaders at scale) -------------------------------------------------
+def _ref_load(path, mats_dir):
+    ref = orc.ref()
+    h = ref.ref_load_obj(path.encode(), mats_dir.encode())
+    assert h
+    sz = np.zeros(5, np.uint64)
+    ref.ref_scene_sizes(h, orc.ptr(sz))
+    pos, nrm = np.zeros((int(sz[0]), 3), np.float32), np.zeros((int(sz[1]), 3), np.float32)
+    uv, tris = np.zeros((int(sz[2]), 2), np.float32), np.zeros((int(sz[3]), 10), np.int32)
+    ref.ref_scene_copy(h, orc.ptr(pos), orc.ptr(nrm), orc.ptr(uv), orc.ptr(tris))
+    ref.ref_scene_destroy(h)
+    return dict(pos=pos, nrm=nrm, uv=uv, tris=tris, n_materials=int(sz[4]))
+
+
+def _same_model(a, b, what):
+    for k in ("pos", "nrm", "uv"):
+        assert a[k].shape == b[k].shape and np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), (what, k)
+    assert a["tris"].shape == b["tris"].shape and np.array_equal(a["tris"], b["tris"]), (what, "tris")
+
+
+def _random_obj(rng, n_lines):
+    """OBJ text exercising everything that carries state from line to line: number formats, relative indices,
+    polygons and degenerate faces, usemtl (known / unknown / repeated), g / o (with and without pending faces),
+    comments, blank lines, CRLF and bare-CR line ends."""
+    out = ["mtllib adv.mtl"]
+    nv = nvn = nvt = 0
+    num = lambda: rng.choice(["%d" % rng.randint(-9, 10), "%.6f" % rng.uniform(-2, 2), "%+.3f" % rng.uniform(-2, 2), "%.9g" % rng.uniform(-1, 1),
+                              "%.3e" % rng.uniform(-50, 50), "%.12f" % rng.uniform(0, 1), ".5", "7.", "1E2", "-0"])
+    for _ in range(n_lines):
+        r = rng.rand()
+        if r < 0.30 or nv < 3:
+            out.append("v %s %s %s" % (num(), num(), num())); nv += 1
+        elif r < 0.38:
+            out.append("vn %s %s %s" % (num(), num(), num())); nvn += 1
+        elif r < 0.46:
+            out.append("vt %s %s" % (num(), num())); nvt += 1
+        elif r < 0.80:
+            corners = []
+            for _ in range(rng.choice([1, 2, 3, 3, 3, 3, 4, 4, 5, 7])):
+                v = rng.randint(1, nv + 1) if rng.rand() < 0.7 else -rng.randint(1, nv + 1)
+                style = rng.randint(0, 4)
+                if style == 1 and nvt:
+                    corners.append("%d/%d" % (v, rng.randint(1, nvt + 1)))
+                elif style == 2 and nvt and nvn:
+                    corners.append("%d/%d/%d" % (v, rng.randint(1, nvt + 1) if rng.rand() < 0.8 else -rng.randint(1, nvt + 1), rng.randint(1, nvn + 1)))
+                elif style == 3 and nvn:
+                    corners.append("%d//%d" % (v, -rng.randint(1, nvn + 1) if rng.rand() < 0.3 else rng.randint(1, nvn + 1)))
+                else:
+                    corners.append("%d" % v)
+            out.append("f " + rng.choice([" ", "  ", "\t"]).join(corners) + rng.choice(["", " ", "  "]))
+        elif r < 0.88:
+            out.append("usemtl " + rng.choice(["red", "blue", "nosuchmaterial", "red"]))
+        elif r < 0.94:
+            out.append(rng.choice(["g ", "o "]) + rng.choice(["a", "b c", "thing"]))
+        elif r < 0.97:
+            out.append("# comment f 1 2 3")
+        else:
+            out.append("")
+    text = ""
+    for line in out:
+        text += line + rng.choice(["\n", "\n", "\n", "\r\n"])
+    return text
+
+
+@pytest.mark.skipif(orc.ref() is None, reason="oracle/_ref/libref.so not available")
+def test_random_objs_equal_reference_loader_for_any_piece_size_and_thread_count():
+    l = hostlib.lib()
+    rng = np.random.RandomState(1234)
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            open(os.path.join(tmp, "adv.mtl"), "w").write(ADVERSARIAL_MTL)
+            for case in range(12):
+                p = os.path.join(tmp, "r%d.obj" % case)
+                text = _random_obj(rng, 40 + 60 * case)
+                if case % 3 == 0:  # a size that is an exact multiple of the page size takes the read (not mmap) path
+                    text += "#" * ((-len(text) - 1) % 4096) + "\n"
+                    assert len(text) % 4096 == 0
+                open(p, "w", newline="").write(text)
+                want = _ref_load(p, tmp + "/")
+                for piece, threads in ((0, 1), (1, 4), (37, 3), (256, 2), (4096, 8)):
+                    l.rasth_set_obj_piece_bytes(piece)
+                    got, _ = hostlib.load_obj(p, tmp + "/", threads=threads)
+                    _same_model(got, want, "case %d piece %d threads %d" % (case, piece, threads))
+                    assert len(got["materials"]) == want["n_materials"]
+    finally:
+        l.rasth_set_obj_piece_bytes(0)
+
+
+def test_tessellated_mesh_roundtrip_threads_and_cache():
+    """A 139 k-triangle OBJ written by synth.write_obj: the arrays do not depend on the thread count or the piece
+    size, equal the reference loader's (when available), and survive the binary mesh cache unchanged."""
+    from rasteriser_b200 import synth
+    l = hostlib.lib()
+    z = np.load(os.path.join(S.GOLDEN, "scenes.npz"))
+    pos, nrm, uv, tris = synth.tessellate(z["suzanne_pos"], z["suzanne_nrm"], z["suzanne_uv"], z["suzanne_tris"], 12)
+    with tempfile.TemporaryDirectory() as tmp:
+        shutil.copy(os.path.join(DATA, "Suzanne.mtl"), tmp)
+        shutil.copy(os.path.join(DATA, "SuzanneTex.png"), tmp)
+        p = os.path.join(tmp, "tess.obj")
+        synth.write_obj(p, pos, nrm, uv, tris, mtllib="Suzanne.mtl")
+        plain = os.path.join(tmp, "plain") + "/"   # the same material without its texture: the reference build cannot decode PNG here
+        os.mkdir(plain)
+        open(plain + "Suzanne.mtl", "w").write("newmtl Material\nKd 0.64 0.64 0.64\n")
+        stats = {}
+        base, _ = hostlib.load_obj(p, tmp + "/", threads=1, stats=stats)
+        assert stats["file_bytes"] == os.path.getsize(p) and stats["threads"] == 1
+        assert base["tris"].shape == tris.shape and np.array_equal(base["tris"][:, :9], tris[:, :9])
+        assert np.allclose(base["pos"], pos, rtol=0, atol=1e-6)
+        try:
+            for piece, threads in ((0, 0), (100000, 5), (4097, 16)):
+                l.rasth_set_obj_piece_bytes(piece)
+                got, _ = hostlib.load_obj(p, tmp + "/", threads=threads)
+                _same_model(got, base, "piece %d threads %d" % (piece, threads))
+        finally:
+            l.rasth_set_obj_piece_bytes(0)
+        if orc.ref() is not None:
+            _same_model(base, _ref_load(p, plain), "reference loader")
+        c = os.path.join(tmp, "tess.rastmesh")
+        hostlib.save_mesh_cache(p, tmp + "/", c)
+        back = hostlib.load_mesh_cache(c)
+        _same_model(back, base, "mesh cache")
+        assert len(back["materials"]) == len(base["materials"]) == 1
+        assert np.array_equal(back["materials"][0]["texels"], base["materials"][0]["texels"])
+        with pytest.raises(RuntimeError):
+            hostlib.load_mesh_cache(p)  # not a cache file
+
+
+def test_png_writer_bands_decode_identically():
+    """The writer deflates bands of rows on several threads into one zlib stream (one IDAT per band): PIL and the
+    product's own decoder must read back the same pixels whatever the thread count."""
+    from PIL import Image
+    l = hostlib.lib()
+    l.rasth_png_set_threads.argtypes = [C.c_uint]
+    rng = np.random.RandomState(7)
+    w, h = 1024, 771
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = np.stack([(xx // 4) % 256, (yy // 3) % 256, rng.randint(0, 256, (h, w))]).astype(np.uint8)  # gradients + noise
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            for threads in (1, 2, 3, 8, 0):
+                l.rasth_png_set_threads(threads)
+                for c, planes in ((3, img), (1, img[2:3])):
+                    p = os.path.join(tmp, "b%d_%d.png" % (threads, c))
+                    assert l.rasth_png_write(p.encode(), np.ascontiguousarray(planes).ctypes.data, w, h, c) == 0
+                    with Image.open(p) as im:
+                        im.load()  # a corrupt stream (bad Adler-32 / CRC) raises here
+                        back = np.asarray(im)
+                    assert np.array_equal(back if c == 1 else back.transpose(2, 0, 1), planes[0] if c == 1 else planes)
+                    dims, out = np.zeros(3, np.uint32), np.zeros(w * h * c, np.uint8)
+                    assert l.rasth_png_read(p.encode(), dims.ctypes.data, out.ctypes.data, out.size) == 0
+                    assert np.array_equal(out.reshape(h, w, c), planes.transpose(1, 2, 0))
+            sizes = [os.path.getsize(os.path.join(tmp, "b%d_3.png" % t)) for t in (1, 8)]
+            assert sizes[1] < sizes[0] * 1.02  # cutting into bands costs almost nothing in size
+    finally:
+        l.rasth_png_set_threads(0)

@@ -235,6 +235,15 @@ def test_renderer_cli_writes_reference_images(tmp_path):
     wf, _, _ = orc.oracle_draw(S.scene("suzanne"), S.lights("threepoint"), oa)
     got = np.ascontiguousarray(np.asarray(Image.open(tmp_path / "spin_04.png")).transpose(2, 0, 1))
     assert np.array_equal(got, wf)
+    # --mesh-cache: the first run parses the .obj and writes the cache, the second reads it; same images
+    cache = str(tmp_path / "suzanne.rastmesh")
+    for run in range(2):
+        out = subprocess.run(cmd + ["--mesh-cache", cache, "--load-threads", "3", "--frame-out", "c%d.png" % run, "--depth-out", "cd%d.png" % run],
+                             cwd=tmp_path, capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        assert os.path.exists(cache) and (("Loading 968 triangles..." in out.stdout) == (run == 0))
+        assert orc.fnv(np.ascontiguousarray(np.asarray(Image.open(tmp_path / ("c%d.png" % run))).transpose(2, 0, 1))) == case["frame_fnv"]
+        assert orc.fnv(np.ascontiguousarray(np.asarray(Image.open(tmp_path / ("cd%d.png" % run))))) == case["depth_u8_fnv"]
     # errors: missing -l, unreadable model
     assert subprocess.run([exe, "-o", "x.obj"], capture_output=True).returncode == 1
     assert subprocess.run([exe, "-o", "/nonexistent.obj", "-l", os.path.join(S.DATA, "threepoint.csv")], capture_output=True).returncode == 1
