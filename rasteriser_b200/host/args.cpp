@@ -39,6 +39,8 @@ const Flag kFlags[] = {
     // extensions
     {"", "frames", Kind::UInt, false, "count", "[extension] frames in the headless spin sequence (-s), default 720"},
     {"", "save-frames", Kind::String, false, "pattern", "[extension] write every spin frame as PNG, printf pattern with one %u"},
+    {"", "record", Kind::String, false, "spin.png", "[extension] write the spin sequence (-s) as one animated PNG (APNG)"},
+    {"", "record-delay", Kind::UInt, false, "ms", "[extension] frame delay of --record in milliseconds (default 33)"},
     {"", "device", Kind::Int, false, "index", "[extension] CUDA device to render on"},
     {"", "frame-out", Kind::String, false, "file.png", "[extension] colour output (default frame.png)"},
     {"", "depth-out", Kind::String, false, "file.png", "[extension] depth output (default depth.png)"},
@@ -131,6 +133,8 @@ ParseResult parse_args(int argc, const char *const *argv, Args &args, std::strin
         else if (n == "dz") args.displacement[2] = (float)num;
         else if (n == "frames") args.frames = (unsigned)num;
         else if (n == "save-frames") args.save_frames = value;
+        else if (n == "record") args.record = value;
+        else if (n == "record-delay") args.record_delay_ms = (unsigned)num;
         else if (n == "device") args.device = (int)num;
         else if (n == "frame-out") args.frame_out = value;
         else if (n == "depth-out") args.depth_out = value;

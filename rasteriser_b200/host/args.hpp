@@ -25,6 +25,8 @@ struct Args {
     // extensions (not in the reference)
     unsigned int frames = 720;        // --frames N: length of the headless spin sequence
     std::string save_frames;          // --save-frames PATTERN: printf pattern with one %u, e.g. spin_%04u.png
+    std::string record;               // --record FILE: the spin sequence as one animated PNG
+    unsigned int record_delay_ms = 33; // --record-delay MS
     int device = 0;                   // --device N
     std::string frame_out = "frame.png", depth_out = "depth.png"; // --frame-out / --depth-out
     bool quiet = false;               // --quiet

@@ -74,6 +74,14 @@ int rasth_load_lights(const char *file, float *out7, int capacity) {
 float rasth_parse_float(const char *s) { return host::parse_obj_float(s, s + std::strlen(s)); }
 void rasth_png_set_threads(unsigned threads) { host::png_set_threads(threads); }
 int rasth_png_write(const char *path, const uint8_t *planar, uint32_t w, uint32_t h, uint32_t c) { return host::png_write_planar(path, planar, w, h, c).empty() ? 0 : -1; }
+// frames: n planar [c][h][w] images back to back -> one animated PNG
+int rasth_apng_write(const char *path, const uint8_t *frames, uint32_t n, uint32_t w, uint32_t h, uint32_t c, uint32_t delay_ms) {
+    host::ApngWriter a;
+    if (!a.open(path, w, h, c, n, delay_ms).empty()) return -1;
+    for (uint32_t i = 0; i < n; ++i)
+        if (!a.add_frame_planar(frames + (size_t)i * c * w * h).empty()) return -1;
+    return a.close().empty() ? 0 : -1;
+}
 int rasth_png_read(const char *path, uint32_t dims[3], uint8_t *out, uint64_t cap) {
     host::PngImage img;
     if (!host::png_read(path, img).empty()) return -1;

@@ -113,6 +113,11 @@ int main(int argc, char **argv) {
             unsigned char *frames = static_cast<unsigned char *>(rast_host_alloc((uint64_t)chunk * 3 * P));
             if (!frames) { std::cerr << "out of pinned host memory" << std::endl; return 1; }
             std::vector<rast_args> poses(chunk);
+            host::ApngWriter recording;
+            if (!arguments.record.empty()) {
+                err = recording.open(arguments.record, arguments.image_width, arguments.image_height, 3, n, arguments.record_delay_ms);
+                if (!err.empty()) { std::cerr << err << std::endl; return 1; }
+            }
             const auto t0 = std::chrono::steady_clock::now();
             for (unsigned first = 0; first < n; first += chunk) {
                 const unsigned count = n - first < chunk ? n - first : chunk;
@@ -122,6 +127,12 @@ int main(int argc, char **argv) {
                     poses[i].tait_bryan_angles[1] = rast_spin_angle(arguments.tait_bryan_angles[1], first + i, n);
                 }
                 session.check(rast_draw_frames(session.ctx(), poses.data(), count, frames, nullptr, 0), "rast_draw_frames");
+                if (!arguments.record.empty()) {
+                    for (unsigned i = 0; i < count; ++i) {
+                        err = recording.add_frame_planar(frames + (size_t)i * 3 * P);
+                        if (!err.empty()) { std::cerr << err << std::endl; return 1; }
+                    }
+                }
                 if (!arguments.save_frames.empty()) {
                     for (unsigned i = 0; i < count; ++i) {
                         char name[4096];
@@ -133,6 +144,10 @@ int main(int argc, char **argv) {
             }
             const std::chrono::duration<float> dt = std::chrono::steady_clock::now() - t0;
             if (verbose) std::cout << n << " frames in " << dt.count() << " s: " << std::to_string((float)n / dt.count()) << " frames/s" << std::endl; // renderer.cpp:120
+            if (!arguments.record.empty()) {
+                err = recording.close();
+                if (!err.empty()) { std::cerr << err << std::endl; return 1; }
+            }
             // the last frame is left in frame.png so the run has a visible result
             err = host::png_write_planar(arguments.frame_out, frames + (size_t)((n - 1) % chunk) * 3 * P, arguments.image_width, arguments.image_height, 3);
             rast_host_free(frames);

@@ -14,18 +14,6 @@ namespace {
 const uint8_t kSignature[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
 
 uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
-void put_be32(std::vector<uint8_t> &v, uint32_t x) {
-    v.push_back((uint8_t)(x >> 24)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x);
-}
-
-void put_chunk(std::vector<uint8_t> &file, const char type[4], const std::vector<uint8_t> &payload) {
-    put_be32(file, (uint32_t)payload.size());
-    const size_t start = file.size();
-    file.insert(file.end(), type, type + 4);
-    file.insert(file.end(), payload.begin(), payload.end());
-    put_be32(file, (uint32_t)crc32(0L, file.data() + start, (uInt)(file.size() - start)));
-}
-
 int paeth(int a, int b, int c) {
     const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
     return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
@@ -122,24 +110,24 @@ std::string png_read(const std::string &path, PngImage &out) {
 // own as a raw deflate stream that ends on a byte boundary (Z_SYNC_FLUSH; the last band ends the stream with
 // Z_FINISH), so the concatenation of the band streams between one zlib header and the Adler-32 of the whole image
 // is ONE valid zlib stream -- the pigz construction.  Every band becomes its own IDAT chunk (a decoder
-// concatenates IDAT payloads, PNG spec 11.2.4), with its CRC computed by the band's thread as well.
+// concatenates IDAT payloads, PNG spec 11.2.4).
 namespace {
 
 unsigned g_png_threads = 0; // 0 = hardware threads
 
 struct Band {
     unsigned y0 = 0, y1 = 0;
-    std::vector<uint8_t> chunk; // complete IDAT chunk: length, "IDAT", payload, CRC
+    std::vector<uint8_t> data;  // this band's part of the zlib stream (band 0 starts with the zlib header, the last band
+                                // ends with the Adler-32 of the whole image)
     uLong adler = 1;            // Adler-32 of the band's filtered bytes
     uLong raw_len = 0;
     bool ok = false;
 };
 
-// rows(y, dst): writes the `stride` interleaved bytes of row y
+// rows(y, dst): writes the `stride` interleaved bytes of row y.  Returns the zlib stream of the filtered image in
+// pieces, one per band, or an empty vector on failure.
 template <class RowFn>
-std::string write_png_file(const std::string &path, unsigned width, unsigned height, unsigned channels, RowFn rows) {
-    if (channels < 1 || channels > 4) return "png_write: 1..4 channels";
-    static const uint8_t colour_of[5] = {0, 0, 4, 2, 6};
+std::vector<Band> deflate_image(unsigned width, unsigned height, unsigned channels, RowFn rows) {
     const size_t stride = (size_t)width * channels;
     unsigned threads = g_png_threads ? g_png_threads : std::max(1u, std::thread::hardware_concurrency());
     // at least 64 KB of pixels per band, so that restarting the deflate window costs nothing measurable
@@ -164,19 +152,18 @@ std::string write_png_file(const std::string &path, unsigned width, unsigned hei
         std::memset(&zs, 0, sizeof zs);
         if (deflateInit2(&zs, 1, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return;
         const size_t head = b == 0 ? 2 : 0, tail = b + 1 == n_bands ? 4 : 0; // zlib header / Adler-32 slot
-        bd.chunk.resize(8 + head + deflateBound(&zs, (uLong)raw.size()) + 16 + tail + 4);
-        uint8_t *payload = bd.chunk.data() + 8;
-        if (head) { payload[0] = 0x78; payload[1] = 0x01; } // deflate, 32 KB window, fastest level, no dictionary
+        bd.data.resize(head + deflateBound(&zs, (uLong)raw.size()) + 16 + tail);
+        if (head) { bd.data[0] = 0x78; bd.data[1] = 0x01; } // deflate, 32 KB window, fastest level, no dictionary
         zs.next_in = raw.data();
         zs.avail_in = (uInt)raw.size();
-        zs.next_out = payload + head;
-        zs.avail_out = (uInt)(bd.chunk.size() - 8 - head - tail - 4);
+        zs.next_out = bd.data.data() + head;
+        zs.avail_out = (uInt)(bd.data.size() - head - tail);
         const int rc = deflate(&zs, b + 1 == n_bands ? Z_FINISH : Z_SYNC_FLUSH);
         const bool done = (b + 1 == n_bands) ? rc == Z_STREAM_END : (rc == Z_OK && zs.avail_in == 0 && zs.avail_out != 0);
         const size_t clen = head + zs.total_out;
         deflateEnd(&zs);
         if (!done) return;
-        bd.chunk.resize(8 + clen + tail + 4); // the tail (Adler-32 of the whole image) is filled in by the caller
+        bd.data.resize(clen + tail); // the tail is filled in below
         bd.ok = true;
     };
     if (n_bands == 1) work(0);
@@ -187,34 +174,62 @@ std::string write_png_file(const std::string &path, unsigned width, unsigned hei
     }
     uLong adler = 1;
     for (unsigned b = 0; b < n_bands; ++b) {
-        if (!bands[b].ok) return "png_write: deflate failed";
+        if (!bands[b].ok) return std::vector<Band>();
         adler = b == 0 ? bands[0].adler : adler32_combine(adler, bands[b].adler, (z_off_t)bands[b].raw_len);
     }
-    for (unsigned b = 0; b < n_bands; ++b) { // chunk framing: big-endian length, type, ..., CRC over type + payload
-        std::vector<uint8_t> &c = bands[b].chunk;
-        const size_t len = c.size() - 12;
-        if (b + 1 == n_bands) { c[8 + len - 4] = (uint8_t)(adler >> 24); c[8 + len - 3] = (uint8_t)(adler >> 16); c[8 + len - 2] = (uint8_t)(adler >> 8); c[8 + len - 1] = (uint8_t)adler; }
-        c[0] = (uint8_t)(len >> 24); c[1] = (uint8_t)(len >> 16); c[2] = (uint8_t)(len >> 8); c[3] = (uint8_t)len;
-        std::memcpy(&c[4], "IDAT", 4);
-        const uint32_t crc = (uint32_t)crc32(0L, &c[4], (uInt)(len + 4));
-        c[8 + len] = (uint8_t)(crc >> 24); c[9 + len] = (uint8_t)(crc >> 16); c[10 + len] = (uint8_t)(crc >> 8); c[11 + len] = (uint8_t)crc;
-    }
-    std::vector<uint8_t> head(kSignature, kSignature + 8), ihdr, tail;
-    put_be32(ihdr, width);
-    put_be32(ihdr, height);
-    ihdr.push_back(8);
-    ihdr.push_back(colour_of[channels]);
-    ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);
-    put_chunk(head, "IHDR", ihdr);
-    put_chunk(tail, "IEND", std::vector<uint8_t>());
+    std::vector<uint8_t> &last = bands[n_bands - 1].data;
+    const size_t n = last.size();
+    last[n - 4] = (uint8_t)(adler >> 24); last[n - 3] = (uint8_t)(adler >> 16); last[n - 2] = (uint8_t)(adler >> 8); last[n - 1] = (uint8_t)adler;
+    return bands;
+}
+
+// one chunk straight to the file: big-endian length, type, [4-byte prefix,] payload, CRC over type + prefix + payload
+bool write_chunk(FILE *f, const char type[4], const uint8_t *prefix, size_t prefix_len, const uint8_t *payload, size_t len) {
+    uint8_t head[8];
+    const uint32_t total = (uint32_t)(prefix_len + len);
+    head[0] = (uint8_t)(total >> 24); head[1] = (uint8_t)(total >> 16); head[2] = (uint8_t)(total >> 8); head[3] = (uint8_t)total;
+    std::memcpy(head + 4, type, 4);
+    uLong crc = crc32(0L, head + 4, 4);
+    if (prefix_len) crc = crc32(crc, prefix, (uInt)prefix_len);
+    if (len) crc = crc32(crc, payload, (uInt)len);
+    const uint8_t tail[4] = {(uint8_t)(crc >> 24), (uint8_t)(crc >> 16), (uint8_t)(crc >> 8), (uint8_t)crc};
+    return std::fwrite(head, 1, 8, f) == 8 && (prefix_len == 0 || std::fwrite(prefix, 1, prefix_len, f) == prefix_len) &&
+           (len == 0 || std::fwrite(payload, 1, len, f) == len) && std::fwrite(tail, 1, 4, f) == 4;
+}
+
+bool write_header(FILE *f, unsigned width, unsigned height, unsigned channels) {
+    static const uint8_t colour_of[5] = {0, 0, 4, 2, 6};
+    uint8_t ihdr[13] = {(uint8_t)(width >> 24), (uint8_t)(width >> 16), (uint8_t)(width >> 8), (uint8_t)width,
+                        (uint8_t)(height >> 24), (uint8_t)(height >> 16), (uint8_t)(height >> 8), (uint8_t)height, 8, colour_of[channels], 0, 0, 0};
+    return std::fwrite(kSignature, 1, 8, f) == 8 && write_chunk(f, "IHDR", nullptr, 0, ihdr, 13);
+}
+
+template <class RowFn>
+std::string write_png_file(const std::string &path, unsigned width, unsigned height, unsigned channels, RowFn rows) {
+    if (channels < 1 || channels > 4) return "png_write: 1..4 channels";
+    const std::vector<Band> bands = deflate_image(width, height, channels, rows);
+    if (bands.empty()) return "png_write: deflate failed";
     FILE *f = std::fopen(path.c_str(), "wb");
     if (!f) return "cannot write " + path;
-    bool ok = std::fwrite(head.data(), 1, head.size(), f) == head.size();
-    for (unsigned b = 0; ok && b < n_bands; ++b) ok = std::fwrite(bands[b].chunk.data(), 1, bands[b].chunk.size(), f) == bands[b].chunk.size();
-    ok = ok && std::fwrite(tail.data(), 1, tail.size(), f) == tail.size();
+    bool ok = write_header(f, width, height, channels);
+    for (size_t b = 0; ok && b < bands.size(); ++b) ok = write_chunk(f, "IDAT", nullptr, 0, bands[b].data.data(), bands[b].data.size());
+    ok = ok && write_chunk(f, "IEND", nullptr, 0, nullptr, 0);
     ok = (std::fclose(f) == 0) && ok;
     return ok ? "" : "short write to " + path;
 }
+
+template <class Dst> void interleave_row(const uint8_t *planar, size_t plane, unsigned width, unsigned channels, unsigned y, Dst *dst) {
+    const uint8_t *row = planar + (size_t)y * width;
+    if (channels == 3) {
+        const uint8_t *r = row, *g = row + plane, *b = row + 2 * plane;
+        for (unsigned x = 0; x < width; ++x) { dst[3 * x] = r[x]; dst[3 * x + 1] = g[x]; dst[3 * x + 2] = b[x]; }
+    } else {
+        for (unsigned c = 0; c < channels; ++c)
+            for (unsigned x = 0; x < width; ++x) dst[(size_t)x * channels + c] = row[c * plane + x];
+    }
+}
+
+void put_u32(uint8_t *p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
 
 } // namespace
 
@@ -228,16 +243,59 @@ std::string png_write(const std::string &path, const uint8_t *interleaved, unsig
 // planar [c][h][w] (CImg layout, CImg.h:11715-11721) -> file; the interleaving happens row by row inside the bands
 std::string png_write_planar(const std::string &path, const uint8_t *planar, unsigned width, unsigned height, unsigned channels) {
     const size_t plane = (size_t)width * height;
-    return write_png_file(path, width, height, channels, [=](unsigned y, uint8_t *dst) {
-        const uint8_t *row = planar + (size_t)y * width;
-        if (channels == 3) {
-            const uint8_t *r = row, *g = row + plane, *b = row + 2 * plane;
-            for (unsigned x = 0; x < width; ++x) { dst[3 * x] = r[x]; dst[3 * x + 1] = g[x]; dst[3 * x + 2] = b[x]; }
-        } else {
-            for (unsigned c = 0; c < channels; ++c)
-                for (unsigned x = 0; x < width; ++x) dst[(size_t)x * channels + c] = row[c * plane + x];
+    return write_png_file(path, width, height, channels, [=](unsigned y, uint8_t *dst) { interleave_row(planar, plane, width, channels, y, dst); });
+}
+
+// ---- animated PNG (APNG 1.0): the recorded form of the spin sequence ---------------------------------------------
+// signature, IHDR, acTL(frames, plays), then per frame fcTL + the frame's zlib stream -- IDAT chunks for frame 0,
+// fdAT chunks (sequence number + data) for the others -- and IEND.  Viewers without APNG support show frame 0.
+ApngWriter::~ApngWriter() { if (f_) std::fclose(static_cast<FILE *>(f_)); }
+
+std::string ApngWriter::open(const std::string &path, unsigned width, unsigned height, unsigned channels, unsigned n_frames, unsigned delay_ms) {
+    if (channels < 1 || channels > 4 || n_frames == 0) return "apng: bad arguments";
+    FILE *f = std::fopen(path.c_str(), "wb");
+    if (!f) return "cannot write " + path;
+    f_ = f; path_ = path; w_ = width; h_ = height; c_ = channels; frames_ = n_frames; delay_ms_ = delay_ms; written_ = 0; seq_ = 0;
+    uint8_t actl[8];
+    put_u32(actl, n_frames);
+    put_u32(actl + 4, 0); // loop forever
+    if (!write_header(f, width, height, channels) || !write_chunk(f, "acTL", nullptr, 0, actl, 8)) return "short write to " + path;
+    return "";
+}
+
+std::string ApngWriter::add_frame_planar(const uint8_t *planar) {
+    FILE *f = static_cast<FILE *>(f_);
+    if (!f || written_ >= frames_) return "apng: not open or too many frames";
+    const size_t plane = (size_t)w_ * h_;
+    const unsigned width = w_, channels = c_;
+    const std::vector<Band> bands = deflate_image(w_, h_, c_, [=](unsigned y, uint8_t *dst) { interleave_row(planar, plane, width, channels, y, dst); });
+    if (bands.empty()) return "apng: deflate failed";
+    uint8_t fctl[26];
+    put_u32(fctl, seq_++);
+    put_u32(fctl + 4, w_); put_u32(fctl + 8, h_); put_u32(fctl + 12, 0); put_u32(fctl + 16, 0);
+    fctl[20] = (uint8_t)(delay_ms_ >> 8); fctl[21] = (uint8_t)delay_ms_; // delay numerator
+    fctl[22] = (uint8_t)(1000 >> 8); fctl[23] = (uint8_t)(1000 & 0xFF);   // denominator: milliseconds
+    fctl[24] = 0; fctl[25] = 0;                                           // dispose: none, blend: source
+    bool ok = write_chunk(f, "fcTL", nullptr, 0, fctl, 26);
+    for (size_t b = 0; ok && b < bands.size(); ++b) {
+        if (written_ == 0) ok = write_chunk(f, "IDAT", nullptr, 0, bands[b].data.data(), bands[b].data.size());
+        else {
+            uint8_t seq[4];
+            put_u32(seq, seq_++);
+            ok = write_chunk(f, "fdAT", seq, 4, bands[b].data.data(), bands[b].data.size());
         }
-    });
+    }
+    ++written_;
+    return ok ? "" : "short write to " + path_;
+}
+
+std::string ApngWriter::close() {
+    FILE *f = static_cast<FILE *>(f_);
+    if (!f) return "";
+    bool ok = written_ == frames_ && write_chunk(f, "IEND", nullptr, 0, nullptr, 0);
+    ok = (std::fclose(f) == 0) && ok;
+    f_ = nullptr;
+    return ok ? "" : "apng: incomplete file " + path_;
 }
 
 } // namespace host

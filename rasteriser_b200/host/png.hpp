@@ -24,4 +24,20 @@ void png_set_threads(unsigned threads);
 // planar [c][h][w] (CImg layout) -> file
 std::string png_write_planar(const std::string &path, const uint8_t *planar, unsigned width, unsigned height, unsigned channels);
 
+// Animated PNG: frames of one size appended one at a time (planar CImg layout in), `delay_ms` between frames.
+class ApngWriter {
+public:
+    ApngWriter() = default;
+    ~ApngWriter();
+    ApngWriter(const ApngWriter &) = delete;
+    ApngWriter &operator=(const ApngWriter &) = delete;
+    std::string open(const std::string &path, unsigned width, unsigned height, unsigned channels, unsigned n_frames, unsigned delay_ms);
+    std::string add_frame_planar(const uint8_t *planar);
+    std::string close(); // fails unless exactly n_frames were added
+private:
+    void *f_ = nullptr;
+    std::string path_;
+    unsigned w_ = 0, h_ = 0, c_ = 0, frames_ = 0, delay_ms_ = 0, written_ = 0, seq_ = 0;
+};
+
 } // namespace host

@@ -311,3 +311,26 @@ def test_png_writer_bands_decode_identically():
             assert sizes[1] < sizes[0] * 1.02  # cutting into bands costs almost nothing in size
     finally:
         l.rasth_png_set_threads(0)
+
+
+def test_animated_png_frames_decode_identically():
+    """--record: the spin sequence as one APNG (acTL / fcTL / fdAT around the writer's zlib streams); PIL must see
+    every frame with the right pixels, and a plain PNG reader (the product's own) the first one."""
+    from PIL import Image
+    l = hostlib.lib()
+    l.rasth_apng_write.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    rng = np.random.RandomState(11)
+    n, w, h = 5, 320, 200
+    frames = rng.randint(0, 256, (n, 3, h, w)).astype(np.uint8)
+    frames[:, :, 50:150, 60:200] = 17  # compressible areas as well
+    with tempfile.TemporaryDirectory() as tmp:
+        p = os.path.join(tmp, "spin.png")
+        assert l.rasth_apng_write(p.encode(), frames.ctypes.data, n, w, h, 3, 40) == 0
+        with Image.open(p) as im:
+            assert getattr(im, "n_frames", 1) == n and im.info.get("duration") == 40
+            for k in range(n):
+                im.seek(k)
+                assert np.array_equal(np.asarray(im.convert("RGB")).transpose(2, 0, 1), frames[k]), k
+        dims, out = np.zeros(3, np.uint32), np.zeros(w * h * 3, np.uint8)
+        assert l.rasth_png_read(p.encode(), dims.ctypes.data, out.ctypes.data, out.size) == 0
+        assert np.array_equal(out.reshape(h, w, 3), frames[0].transpose(1, 2, 0))

@@ -228,9 +228,16 @@ def test_renderer_cli_writes_reference_images(tmp_path):
     assert orc.fnv(frame) == case["frame_fnv"]
     assert orc.fnv(depth8) == case["depth_u8_fnv"]
     # headless spin: 5 frames, last one saved; equals a single frame at the same angle
-    out = subprocess.run(cmd[:11] + ["-s", "--frames", "5", "--save-frames", "spin_%02u.png"], cwd=tmp_path, capture_output=True, text=True)
+    out = subprocess.run(cmd[:11] + ["-s", "--frames", "5", "--save-frames", "spin_%02u.png", "--record", "spin.png", "--record-delay", "50"],
+                         cwd=tmp_path, capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     assert "frames/s" in out.stdout and (tmp_path / "spin_04.png").exists()
+    with Image.open(tmp_path / "spin.png") as rec:  # the recorded sequence: one animated PNG holding the same five frames
+        assert rec.n_frames == 5 and rec.info.get("duration") == 50
+        for k in (0, 4):
+            rec.seek(k)
+            single = np.asarray(Image.open(tmp_path / ("spin_%02d.png" % k)))
+            assert np.array_equal(np.asarray(rec.convert("RGB")), single)
     oa = orc.make_args(640, 480, angles=(0.0, float(orc.oracle().orc_spin_angle(0.0, 4, 5)), 0.0))
     wf, _, _ = orc.oracle_draw(S.scene("suzanne"), S.lights("threepoint"), oa)
     got = np.ascontiguousarray(np.asarray(Image.open(tmp_path / "spin_04.png")).transpose(2, 0, 1))
