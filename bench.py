@@ -132,6 +132,20 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm
 # ------------------------------------------------------------------------------------------------
+class _StdoutToStderr:
+    """The reference's own code prints progress lines ("Loaded texture ...", material.h:21) to stdout from C++;
+    bench.py's stdout must carry exactly one JSON line, so fd 1 points at stderr while the reference runs."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def cpu_reference_runner(wl):
     """Returns (kind, render(pose_args_list) -> seconds, threads).  kind = "reference" when the reference's
     own sources were compiled here (oracle/_ref/libref.so), else "port" (oracle/liboracle.so).  Frames are
@@ -160,8 +174,9 @@ def cpu_reference_runner(wl):
                 paths.append(p.encode())
         arr = (C.c_char_p * max(1, len(paths)))(*paths)
         kd = np.array(kd, np.float32)
-        h = ref.ref_scene_create(orc.ptr(scene.positions), len(scene.positions), orc.ptr(scene.normals), len(scene.normals), orc.ptr(scene.uvs), len(scene.uvs),
-                                 orc.ptr(scene.tris), len(scene.tris), orc.ptr(kd), arr, len(wl["materials"]))
+        with _StdoutToStderr():
+            h = ref.ref_scene_create(orc.ptr(scene.positions), len(scene.positions), orc.ptr(scene.normals), len(scene.normals), orc.ptr(scene.uvs), len(scene.uvs),
+                                     orc.ptr(scene.tris), len(scene.tris), orc.ptr(kd), arr, len(wl["materials"]))
         kind = "reference"
 
         def one(a):
