@@ -8,7 +8,7 @@ import json,sys
 d=json.loads(sys.stdin.read()); p=d['roofline']['pass_ms_per_step']
 print('$1 $3 ms/step', round(d['ms_per_step'],4), 'vertex', round(p['vertex'],4), 'setup', round(p['setup'],4), 'raster', round(p['raster'],4), 'shade', round(p['shade'],4), 'checksum', d['checksum'])" | tee -a gpurun_out/${tag}_summary.txt
 }
-for w in spin1080p tess4k tess4k_64lights; do
+for w in ${WORKLOADS:-spin1080p tess4k tess4k_64lights}; do
   run default "" $w
   for v in "${@:2}"; do run $v build/variants/librast_b200_$v.so $w; done
 done
