@@ -1044,6 +1044,37 @@ __global__ void k_selftest_division(unsigned long long samples_per_thread, unsig
     if (bad) atomicAdd(mismatches, bad);
 }
 
+// rast_upload_mesh on the device: the caller's Triangle array (10 x int32 per triangle, headers/face.h:6-13) is copied
+// to the GPU as it is and rearranged here -- vertex indices into three SoA arrays, the rest into the 48-byte record of
+// the shade pass, absent (-1) normals / uvs pointed at the sentinel entry.  Out-of-range indices (undefined behaviour in
+// the reference: vector operator[], drawing.cpp:167-173) are reported through `first_error`: the smallest key
+// (triangle * 16 + corner * 4 + kind) wins, i.e. the error a sequential check in triangle order would hit first.
+enum { UPLOAD_ERR_VERTEX = 0, UPLOAD_ERR_NORMAL = 1, UPLOAD_ERR_UV = 2 };
+__global__ void __launch_bounds__(256) k_build_tri_records(const int *__restrict__ tris, uint64_t n_tris, uint32_t n_positions, uint32_t n_normals, uint32_t n_uvs,
+                                                            int *__restrict__ vidx, int4 *__restrict__ rec, unsigned long long *first_error) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tris) return;
+    const int2 *src = reinterpret_cast<const int2 *>(tris + 10 * t); // 40-byte rows are 8-byte aligned
+    int f[10];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { const int2 v = __ldg(src + k); f[2 * k] = v.x; f[2 * k + 1] = v.y; }
+    int n[3], uvi[3];
+    unsigned long long err = ~0ull;
+#pragma unroll
+    for (int k = 2; k >= 0; --k) { // descending, so that the smallest key is kept
+        if (f[6 + k] >= 0 && (uint32_t)f[6 + k] >= n_uvs) err = t * 16ull + k * 4 + UPLOAD_ERR_UV;
+        if (f[3 + k] >= 0 && (uint32_t)f[3 + k] >= n_normals) err = t * 16ull + k * 4 + UPLOAD_ERR_NORMAL;
+        if (f[k] < 0 || (uint32_t)f[k] >= n_positions) err = t * 16ull + k * 4 + UPLOAD_ERR_VERTEX;
+        n[k] = f[3 + k] >= 0 ? f[3 + k] : (int)n_normals;
+        uvi[k] = f[6 + k] >= 0 ? f[6 + k] : (int)n_uvs;
+    }
+    if (err != ~0ull) atomicMin(first_error, err);
+    vidx[t] = f[0]; vidx[n_tris + t] = f[1]; vidx[2 * n_tris + t] = f[2];
+    rec[3 * t] = make_int4(f[0], f[1], f[2], n[0]);
+    rec[3 * t + 1] = make_int4(n[1], n[2], uvi[0], uvi[1]);
+    rec[3 * t + 2] = make_int4(uvi[2], f[9], f[9], 0); // .z keeps the caller's material index, .y is resolved at draw time
+}
+
 // tri_rec[3t+2].z holds the caller's material index; .y becomes the index the shade pass uses:
 // materials[face.material] (drawing.cpp:173), with -1 / out of range mapped to the sentinel.
 __global__ void k_resolve_materials(int4 *tri_rec, uint64_t n_tris, uint32_t n_materials) {

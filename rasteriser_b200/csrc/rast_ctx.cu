@@ -531,47 +531,46 @@ int rast_upload_mesh(rast_ctx *ctx, const float *positions, uint32_t n_positions
     if (!ctx) return RAST_EINVAL;
     if ((n_positions && !positions) || (n_normals && !normals) || (n_uvs && !uvs) || (n_tris && !tris)) return fail(ctx, RAST_EINVAL, "rast_upload_mesh: null array");
     if (n_tris > 0xFFFFFFFEull) return fail(ctx, RAST_EINVAL, "rast_upload_mesh: triangle index must fit 32 bits");
-    // Out-of-range indices are undefined behaviour in the reference (vector operator[], drawing.cpp:167-173);
-    // here they are rejected up front.  -1 marks an absent normal / uv / material (face.h:6-13).
-    std::vector<int> vidx;
-    std::vector<int4> rec;
-    try {
-        vidx.resize((size_t)n_tris * 3);
-        rec.resize((size_t)n_tris * 3);
-    } catch (...) { return fail(ctx, RAST_ENOMEM, "rast_upload_mesh: out of host memory"); }
-    // absent (-1) normals / uvs point at a sentinel entry appended after the real ones; the material index is
-    // resolved against the sentinel in rast_upload_materials' table at draw time (kept raw here, remapped below)
-    for (uint64_t t = 0; t < n_tris; ++t) {
-        const int32_t *f = tris + 10 * t;
-        int n[3], uvi[3];
-        for (int k = 0; k < 3; ++k) {
-            if (f[k] < 0 || (uint32_t)f[k] >= n_positions) return fail(ctx, RAST_EINVAL, "rast_upload_mesh: vertex index out of range");
-            if (f[3 + k] >= 0 && (uint32_t)f[3 + k] >= n_normals) return fail(ctx, RAST_EINVAL, "rast_upload_mesh: normal index out of range");
-            if (f[6 + k] >= 0 && (uint32_t)f[6 + k] >= n_uvs) return fail(ctx, RAST_EINVAL, "rast_upload_mesh: uv index out of range");
-            vidx[(size_t)k * n_tris + t] = f[k];
-            n[k] = f[3 + k] >= 0 ? f[3 + k] : (int)n_normals;
-            uvi[k] = f[6 + k] >= 0 ? f[6 + k] : (int)n_uvs;
-        }
-        rec[3 * t] = make_int4(f[0], f[1], f[2], n[0]);
-        rec[3 * t + 1] = make_int4(n[1], n[2], uvi[0], uvi[1]);
-        rec[3 * t + 2] = make_int4(uvi[2], f[9], f[9], 0); // .z keeps the caller's material index, .y is resolved at draw time
-    }
+    // The Triangle array goes to the device as it is; k_build_tri_records splits it into the SoA vertex indices and the
+    // shade records and validates every index there (no per-triangle work on the host: 50 M triangles = 2 GB).
     RAST_CUDA(ctx, cudaSetDevice(ctx->device));
     RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     RAST_CUDA(ctx, ctx->d_pos.reserve((size_t)n_positions * 12));
     RAST_CUDA(ctx, ctx->d_nrm.reserve(((size_t)n_normals + 1) * 12));
     RAST_CUDA(ctx, ctx->d_uv.reserve(((size_t)n_uvs + 1) * 8));
-    RAST_CUDA(ctx, cudaMemset(ctx->d_nrm.as<float>() + (size_t)n_normals * 3, 0, 12)); // sentinel: zero normal
-    RAST_CUDA(ctx, cudaMemset(ctx->d_uv.as<float>() + (size_t)n_uvs * 2, 0, 8));       // sentinel: uv (0,0)
-    RAST_CUDA(ctx, ctx->d_vidx.reserve(vidx.size() * 4));
-    RAST_CUDA(ctx, ctx->d_attr.reserve(rec.size() * 16));
-    if (n_positions) RAST_CUDA(ctx, cudaMemcpy(ctx->d_pos.p, positions, (size_t)n_positions * 12, cudaMemcpyHostToDevice));
-    if (n_normals) RAST_CUDA(ctx, cudaMemcpy(ctx->d_nrm.p, normals, (size_t)n_normals * 12, cudaMemcpyHostToDevice));
-    if (n_uvs) RAST_CUDA(ctx, cudaMemcpy(ctx->d_uv.p, uvs, (size_t)n_uvs * 8, cudaMemcpyHostToDevice));
+    RAST_CUDA(ctx, ctx->d_vidx.reserve((size_t)n_tris * 3 * 4));
+    RAST_CUDA(ctx, ctx->d_attr.reserve((size_t)n_tris * 3 * 16));
+    RAST_CUDA(ctx, ctx->d_counters.reserve(128));
+    // every copy is ordered on the context's stream (the caller's arrays are pageable: the calls return when the data
+    // has left them), so the kernels that follow on that stream see the data whatever kind of stream it is
+    RAST_CUDA(ctx, cudaMemsetAsync(ctx->d_nrm.as<float>() + (size_t)n_normals * 3, 0, 12, ctx->stream)); // sentinel: zero normal
+    RAST_CUDA(ctx, cudaMemsetAsync(ctx->d_uv.as<float>() + (size_t)n_uvs * 2, 0, 8, ctx->stream));       // sentinel: uv (0,0)
+    if (n_positions) RAST_CUDA(ctx, cudaMemcpyAsync(ctx->d_pos.p, positions, (size_t)n_positions * 12, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_normals) RAST_CUDA(ctx, cudaMemcpyAsync(ctx->d_nrm.p, normals, (size_t)n_normals * 12, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_uvs) RAST_CUDA(ctx, cudaMemcpyAsync(ctx->d_uv.p, uvs, (size_t)n_uvs * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (n_tris) {
-        RAST_CUDA(ctx, cudaMemcpy(ctx->d_vidx.p, vidx.data(), vidx.size() * 4, cudaMemcpyHostToDevice));
-        RAST_CUDA(ctx, cudaMemcpy(ctx->d_attr.p, rec.data(), rec.size() * 16, cudaMemcpyHostToDevice));
+        DeviceBuffer raw; // freed on return
+        struct Release { DeviceBuffer &b; ~Release() { b.release(); } } release_raw{raw};
+        RAST_CUDA(ctx, raw.reserve((size_t)n_tris * 40));
+        RAST_CUDA(ctx, cudaMemcpyAsync(raw.p, tris, (size_t)n_tris * 40, cudaMemcpyHostToDevice, ctx->stream));
+        unsigned long long *first_error = ctx->d_counters.as<unsigned long long>() + 15; // beyond the per-batch counters
+        RAST_CUDA(ctx, cudaMemsetAsync(first_error, 0xFF, 8, ctx->stream));
+        rk::k_build_tri_records<<<grid_for(n_tris, 256), 256, 0, ctx->stream>>>(raw.as<int>(), n_tris, n_positions, n_normals, n_uvs, ctx->d_vidx.as<int>(),
+                                                                                 ctx->d_attr.as<int4>(), first_error);
+        ++ctx->launches;
+        unsigned long long err = ~0ull;
+        RAST_CUDA(ctx, cudaMemcpyAsync(&err, first_error, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (err != ~0ull) {
+            ctx->have_mesh = false;
+            switch (err & 3ull) {
+                case rk::UPLOAD_ERR_VERTEX: return fail(ctx, RAST_EINVAL, "rast_upload_mesh: vertex index out of range");
+                case rk::UPLOAD_ERR_NORMAL: return fail(ctx, RAST_EINVAL, "rast_upload_mesh: normal index out of range");
+                default: return fail(ctx, RAST_EINVAL, "rast_upload_mesh: uv index out of range");
+            }
+        }
     }
+    RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     rk::Scene &s = ctx->scene;
     s.pos = ctx->d_pos.as<float>();
     s.nrm = ctx->d_nrm.as<float>();

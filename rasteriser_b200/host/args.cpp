@@ -44,6 +44,7 @@ const Flag kFlags[] = {
     {"", "device", Kind::Int, false, "index", "[extension] CUDA device to render on"},
     {"", "frame-out", Kind::String, false, "file.png", "[extension] colour output (default frame.png)"},
     {"", "depth-out", Kind::String, false, "file.png", "[extension] depth output (default depth.png)"},
+    {"", "timing", Kind::Switch, false, "", "[extension] print the wall time of each stage (load, context, upload + draw, outputs) to stderr"},
     {"", "quiet", Kind::Switch, false, "", "[extension] no progress output"},
     {"", "mesh-cache", Kind::String, false, "file.rastmesh", "[extension] binary copy of the parsed model: read it if present, else parse the .obj and write it"},
     {"", "load-threads", Kind::UInt, false, "count", "[extension] threads parsing the .obj (default: all hardware threads)"},
@@ -139,6 +140,7 @@ ParseResult parse_args(int argc, const char *const *argv, Args &args, std::strin
         else if (n == "frame-out") args.frame_out = value;
         else if (n == "depth-out") args.depth_out = value;
         else if (n == "quiet") args.quiet = true;
+        else if (n == "timing") args.timing = true;
         else if (n == "mesh-cache") args.mesh_cache = value;
         else if (n == "load-threads") args.load_threads = (unsigned)num;
         else if (n == "flat-mode") {

@@ -30,6 +30,7 @@ struct Args {
     int device = 0;                   // --device N
     std::string frame_out = "frame.png", depth_out = "depth.png"; // --frame-out / --depth-out
     bool quiet = false;               // --quiet
+    bool timing = false;              // --timing: stage wall times on stderr
     std::string mesh_cache;           // --mesh-cache FILE: binary copy of the parsed model (read if present, else written after parsing)
     unsigned int load_threads = 0;    // --load-threads N: OBJ parser threads (0 = all hardware threads)
     bool flat_face = false;           // --flat-mode face: with -f, shade with one normal per face (extension; default keeps the reference's no-op)

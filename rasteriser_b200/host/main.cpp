@@ -54,6 +54,12 @@ int main(int argc, char **argv) {
         case host::ParseResult::Ok: break;
     }
     const bool verbose = !arguments.quiet;
+    auto t_stage = std::chrono::steady_clock::now();
+    auto stage = [&](const char *name) { // --timing: wall time since the previous stage
+        const auto now = std::chrono::steady_clock::now();
+        if (arguments.timing) std::cerr << "[timing] " << name << " " << std::chrono::duration<double>(now - t_stage).count() << " s" << std::endl;
+        t_stage = now;
+    };
 
     host::Model model;
     std::vector<host::Light> lights;
@@ -75,6 +81,7 @@ int main(int argc, char **argv) {
     } else {
         host::add_square(model);
     }
+    stage("load scene");
     const View<Vec3> vertices = view<Vec3>(model.positions), normals = view<Vec3>(model.normals);
     const View<Vec2> uvs = view<Vec2>(model.uvs);
     const View<Tri> faces = view<Tri>(model.tris);
@@ -85,6 +92,7 @@ int main(int argc, char **argv) {
 
     try {
         rast::Session session(arguments.device);
+        stage("create context");
         const int flat_code = (arguments.flat && arguments.flat_face) ? RAST_FLAT_FACE : (arguments.flat ? 1 : 0);
         if (!arguments.spin) {
             if (flat_code == RAST_FLAT_FACE) { // extension path: same calls as the shim, with the extension code in rast_args.flat
@@ -96,6 +104,7 @@ int main(int argc, char **argv) {
                 session.check(rast_draw_frame(session.ctx(), &a, frame_buffer.data(), depth_buffer.data(), l), "rast_draw_frame");
             } else
             rast::draw_frame(session, vertices, faces, normals, uvs, lights, model.materials, arguments, &frame_buffer, &depth_buffer);
+            stage("upload + draw_frame");
             // renderer.cpp:92-93: frame.png, and depth.normalize(0,255) saved as 8-bit grey
             err = host::png_write_planar(arguments.frame_out, frame_buffer.data(), arguments.image_width, arguments.image_height, 3);
             if (!err.empty()) { std::cerr << err << std::endl; return 1; }
@@ -103,6 +112,7 @@ int main(int argc, char **argv) {
             session.check(rast_depth_to_u8(session.ctx(), depth8.data()), "rast_depth_to_u8"); // normalize + uchar cast on the device
             err = host::png_write(arguments.depth_out, depth8.data(), arguments.image_width, arguments.image_height, 1);
             if (!err.empty()) { std::cerr << err << std::endl; return 1; }
+            stage("frame.png + depth.png");
         } else {
             // headless spin: N frames, ry_k = ry + k * 2*pi/N, rendered in batches through rast_draw_frames
             session.upload(vertices, faces, normals, uvs, model.materials);

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--threads", default="1,2,4,8,0")
     ap.add_argument("--keep", default="")
     ap.add_argument("--no-reference", action="store_true")
+    ap.add_argument("--cli", action="store_true", help="also time the renderer executable end to end on the scene (needs a GPU)")
     o = ap.parse_args()
     from rasteriser_b200 import hostio, synth
     import orc
@@ -79,6 +80,19 @@ def main():
     dt = time.perf_counter() - t0
     hostio.lib().rasth_model_free(h)
     out["mesh_cache"] = {"file_mb": os.path.getsize(cache) / 1e6, "seconds": dt, "mb_per_s": os.path.getsize(cache) / 1e6 / dt}
+    if o.cli:  # the whole command line on this scene: parse (or cache read), upload, one 4K frame, frame.png + depth.png
+        import subprocess
+        exe = os.path.join(ROOT, "rasteriser_b200", "renderer")
+        lights = os.path.join(data, "threepoint.csv")
+        runs = {}
+        for name, extra in (("parse_obj", []), ("mesh_cache", ["--mesh-cache", cache])):
+            t0 = time.perf_counter()
+            r = subprocess.run([exe, "-o", path, "-l", lights, "-x", "3840", "-y", "2160", "--quiet", "--timing"] + extra, cwd=tmp, capture_output=True, text=True)
+            runs[name] = {"seconds": time.perf_counter() - t0, "returncode": r.returncode,
+                          "stages_s": {l.split("] ")[1].rsplit(" ", 2)[0]: float(l.split()[-2]) for l in r.stderr.splitlines() if l.startswith("[timing]")}}
+            if r.returncode != 0:
+                runs[name]["stderr"] = r.stderr[-300:]
+        out["renderer_cli_4k_frame"] = runs
     print(json.dumps(out))
 
 
