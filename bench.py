@@ -247,6 +247,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--frames", type=int, default=0, help="override frames per step (profiling runs)")
+    ap.add_argument("--band-gather", default="peer", choices=["peer", "nccl"], help="N>1 single frame: how the row bands reach rank 0")
     ap.add_argument("--gather", action="store_true", help="N>1 spin: also gather the finished RGB frames to rank 0 (NCCL) inside the timed region")
     opts = ap.parse_args()
 
@@ -301,7 +302,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # sort-first bands: by default every rank's shade pass stores its band straight into rank 0's full-size image over
+    # NVLink (peer memory, multi.PeerImage) and one tiny all-reduce orders completion; --band-gather nccl keeps the
+    # staged variant (band slabs gathered with NCCL, then stitched on rank 0)
+    peer = multi.PeerImage(r, W, H) if band_mode and opts.band_gather == "peer" else None
+
     def step_device():
+        if peer is not None:
+            peer.draw_band(arr)
+            peer.barrier()
+            return
         r.draw_frames_device(arr, frames_dev.data_ptr(), depths_dev.data_ptr())
         if band_mode:  # NCCL over NVLink: band slabs to rank 0, on the same stream as the kernels
             multi.gather_bands(frames_dev[0], H)
@@ -383,7 +393,12 @@ def main():
         lib.rast_host_free(fb)
         lib.rast_host_free(db)
     else:
-        checksum = int(frames_dev[n // 2].sum().item())
+        if peer is not None:  # rank 0 holds the stitched frame
+            peer.barrier()
+            got = peer.read()
+            checksum = int(got[0].astype(np.uint64).sum()) if got is not None else 0
+        else:
+            checksum = int(frames_dev[n // 2].sum().item())
 
     # ---- per-pass kernel durations (CUDA events around each launch, same stream) ----
     r.set_profiling(True)
@@ -449,12 +464,15 @@ def main():
         line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": opts.steps, "warmup": max(3, opts.warmup),
                 "ms_per_step": ms_total / opts.steps, "higher_is_better": True, "scaling": "strong" if band_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["label"], "frames_per_step_per_gpu": n, "image": [W, H], "triangles": len(wl["tris"]),
-                           "partition": ("sort-first row bands, band slabs gathered to rank 0 with NCCL inside the timed region" if band_mode else
+                           "partition": (("sort-first row bands, each rank's shade pass stores its band into rank 0's image over NVLink peer memory (CUDA IPC), one 4-byte all-reduce per frame orders completion, all inside the timed region" if peer is not None else
+                                          "sort-first row bands, band slabs gathered to rank 0 with NCCL inside the timed region") if band_mode else
                                          "frame k of the global sequence on rank k mod N; no collective" + ("; RGB frames gathered to rank 0 with NCCL" if opts.gather and world > 1 else "")), "l2": "working set per 32-frame batch ~1 GB >> 126 MB L2 (inputs/outputs larger than L2)",
                            "outputs": "RGB8 planes + f32 depth per frame, written to HBM"},
                 "mtris_per_s": fps * len(wl["tris"]) / 1e6, "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
                 "stats_last_frame": st, "checksum": checksum}
         print(json.dumps(line))
+    if peer is not None:
+        peer.close()
     if world > 1:
         dist.destroy_process_group()
     r.close()

@@ -121,6 +121,26 @@ float rast_spin_angle(float ry0, uint32_t k, uint32_t n_frames);
 /* Restrict rendering to image rows [y0, y1).  Output buffers then hold only those rows:
  * frame [3][y1-y0][W], depth [y1-y0][W].  y0 = y1 = 0 restores the whole frame. */
 int rast_set_band(rast_ctx *ctx, uint32_t y0, uint32_t y1);
+/* Device-pointer draws (rast_draw_frames with device_ptrs != 0) normally write planes that are exactly one band
+ * large.  With a plane stride of `pixels` (>= the band) the R, G, B planes -- and consecutive frames' depth planes --
+ * are `pixels` apart instead, so a band can be written straight into its rows of a full-size image: pass
+ * frames = image + y0 * W, depths = depth_image + y0 * W and pixels = W * H.  0 restores the default. */
+int rast_set_output_plane_stride(rast_ctx *ctx, uint64_t pixels);
+
+/* ---- peer memory: one process per GPU, bands / frames written straight into rank 0's image over NVLink ---------
+ * The reference has no counterpart (single process, single thread).  rast_device_alloc returns plain cudaMalloc
+ * memory of the context's device; rast_ipc_export turns it into a handle another process of the same node opens with
+ * rast_ipc_open (cudaIpcOpenMemHandle with peer access).  The opened pointer is valid as `frames` / `depths` of a
+ * device-pointer draw: the shade pass then stores its pixels into the owner's memory -- the gather IS the kernel's
+ * store, no staging buffer and no collective.  The owner must not read the image before every writer's stream has
+ * finished (any barrier does). */
+#define RAST_IPC_HANDLE_BYTES 64
+void *rast_device_alloc(rast_ctx *ctx, uint64_t bytes);
+int rast_device_free(rast_ctx *ctx, void *device_ptr);
+int rast_device_read(rast_ctx *ctx, void *host_dst, const void *device_src, uint64_t bytes);
+int rast_ipc_export(rast_ctx *ctx, void *device_ptr, unsigned char handle[RAST_IPC_HANDLE_BYTES]);
+int rast_ipc_open(rast_ctx *ctx, const unsigned char handle[RAST_IPC_HANDLE_BYTES], void **device_ptr);
+int rast_ipc_close(rast_ctx *ctx, void *device_ptr);
 
 /* ---- draw_frame (drawing.cpp:205-258) ------------------------------------------------------ */
 /* Clears (frame 0, depth 1.0f: renderer.cpp:85-86,107-108), draws, and copies the result into HOST

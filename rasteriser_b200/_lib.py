@@ -47,6 +47,13 @@ SYMBOLS = {
     "rast_transform_lights": (None, [C.c_void_p, C.POINTER(RastLight), C.c_uint32]),
     "rast_spin_angle": (C.c_float, [C.c_float, C.c_uint32, C.c_uint32]),
     "rast_set_band": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "rast_set_output_plane_stride": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "rast_device_alloc": (C.c_void_p, [C.c_void_p, C.c_uint64]),
+    "rast_device_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rast_device_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "rast_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rast_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "rast_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rast_draw_frame": (C.c_int, [C.c_void_p, C.POINTER(RastArgs), C.c_void_p, C.c_void_p, C.POINTER(RastLight)]),
     "rast_draw_frame_device": (C.c_int, [C.c_void_p, C.POINTER(RastArgs), C.c_void_p, C.c_void_p]),
     "rast_draw_frames": (C.c_int, [C.c_void_p, C.POINTER(RastArgs), C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]),

@@ -138,6 +138,39 @@ class Renderer:
         self._check(self._lib.rast_set_band(self._h, int(y0), int(y1)), "rast_set_band")
         self._band = (int(y0), int(y1)) if y1 > y0 else None
 
+    def set_output_plane_stride(self, pixels):
+        """Device-pointer draws write planes `pixels` apart (0 = one band): a band rendered straight into its rows of a full-size image."""
+        self._check(self._lib.rast_set_output_plane_stride(self._h, int(pixels)), "rast_set_output_plane_stride")
+
+    # ---- peer memory (one process per GPU; include/rast.h "peer memory") ----
+    def device_alloc(self, nbytes):
+        p = self._lib.rast_device_alloc(self._h, int(nbytes))
+        if not p:
+            raise RastError("rast_device_alloc: " + (self._lib.rast_last_error(self._h) or b"").decode())
+        return int(p)
+
+    def device_free(self, ptr):
+        self._check(self._lib.rast_device_free(self._h, C.c_void_p(int(ptr))), "rast_device_free")
+
+    def device_read(self, ptr, out):
+        """Copy out.nbytes bytes from device address `ptr` into the numpy array `out`."""
+        self._check(self._lib.rast_device_read(self._h, out.ctypes.data, C.c_void_p(int(ptr)), out.nbytes), "rast_device_read")
+        return out
+
+    def ipc_export(self, ptr):
+        h = (C.c_ubyte * 64)()
+        self._check(self._lib.rast_ipc_export(self._h, C.c_void_p(int(ptr)), h), "rast_ipc_export")
+        return bytes(h)
+
+    def ipc_open(self, handle):
+        h = (C.c_ubyte * 64)(*handle)
+        p = C.c_void_p()
+        self._check(self._lib.rast_ipc_open(self._h, h, C.byref(p)), "rast_ipc_open")
+        return int(p.value)
+
+    def ipc_close(self, ptr):
+        self._check(self._lib.rast_ipc_close(self._h, C.c_void_p(int(ptr))), "rast_ipc_close")
+
     def set_stream(self, cuda_stream):
         """Launch on this cudaStream_t handle (int; 0 = the legacy default stream)."""
         self._check(self._lib.rast_set_stream(self._h, C.c_void_p(int(cuda_stream))), "rast_set_stream")

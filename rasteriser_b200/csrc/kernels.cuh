@@ -78,6 +78,8 @@ struct View {
     uint32_t W, H;            // image size (arguments.h:8-9)
     uint32_t y0, y1;          // band of rows rendered by this context, [y0,y1)
     uint32_t band_pixels;     // W * (y1 - y0)
+    uint32_t out_plane;       // pixels between the R, G and B planes (and between frames' depth planes) of the OUTPUT: band_pixels, or the
+                              // whole frame's W * H when a band is written straight into a full-size image (rast_set_output_plane_stride)
 };
 
 struct Batch {
@@ -950,9 +952,10 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View 
     constexpr int GROUPS = shade_groups(PX);
     const uint32_t xb = blockIdx.x * (STRIDE * GROUPS) + threadIdx.x * PX;
     const uint32_t row = blockIdx.y, f = blockIdx.z;
-    const uint32_t P = vw.band_pixels;
-    const size_t i0 = (size_t)f * P + (size_t)row * vw.W + xb;          // into vis / depth
-    const size_t o0 = (size_t)f * 3 * P + (size_t)row * vw.W + xb;      // into the R plane of frame f
+    const uint32_t P = vw.out_plane;
+    const size_t i0 = (size_t)f * vw.band_pixels + (size_t)row * vw.W + xb; // into vis
+    const size_t d0 = (size_t)f * P + (size_t)row * vw.W + xb;              // into depth
+    const size_t o0 = (size_t)f * 3 * P + (size_t)row * vw.W + xb;          // into the R plane of frame f
     unsigned long long *vis = bt.vis + i0;
     const bool reset = f != keep_frame; // hand the keys back as VIS_EMPTY (the next batch then needs no clear pass)
 
@@ -1002,7 +1005,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View 
                 }
             }
         }
-        const size_t o = o0 + g * STRIDE, i = i0 + g * STRIDE;
+        const size_t o = o0 + g * STRIDE, i = d0 + g * STRIDE;
         if (PX == 4) {
             *reinterpret_cast<uchar4 *>(rgb + o) = make_uchar4(px[0].r, px[PX > 1 ? 1 : 0].r, px[PX > 2 ? 2 : 0].r, px[PX > 3 ? 3 : 0].r);
             *reinterpret_cast<uchar4 *>(rgb + o + P) = make_uchar4(px[0].g, px[PX > 1 ? 1 : 0].g, px[PX > 2 ? 2 : 0].g, px[PX > 3 ? 3 : 0].g);

@@ -74,6 +74,7 @@ struct rast_ctx {
     bool mesh_materials_dirty = false; // material indices in d_attr still have to be clamped against n_materials
     uint32_t n_materials = 0;
     bool pre_normals = false;
+    uint64_t out_plane_stride = 0; // rast_set_output_plane_stride (0 = the band's own pixel count)
     bool flat_face = false; // extension mode of the current call (rast_args.flat == RAST_FLAT_FACE)
     int shade_px = 1; // adjacent pixels per group in the shade pass: 1 measured faster than 4 (uchar4/float4 stores) on B200
     rk::LightTable light_table{}; // first PARAM_LIGHTS lights, passed to the shade kernel by value
@@ -144,6 +145,7 @@ rk::View make_view(const rast_ctx *ctx, uint32_t W, uint32_t H) {
         v.y1 = ctx->band_y1 < H ? ctx->band_y1 : H;
     }
     v.band_pixels = W * (v.y1 - v.y0);
+    v.out_plane = v.band_pixels;
     return v;
 }
 
@@ -303,9 +305,15 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
         }
         ctx->mesh_materials_dirty = false;
     }
-    const rk::View vw = make_view(ctx, W, H);
-    const size_t P = vw.band_pixels;
-    if (P == 0) return RAST_OK; // empty band: nothing to render or copy
+    rk::View vw = make_view(ctx, W, H);
+    if (vw.band_pixels == 0) return RAST_OK; // empty band: nothing to render or copy
+    // P = pixels between output planes.  Device-pointer draws may write a band into a larger image (the full frame of a
+    // sort-first gather target, possibly another GPU's memory): then the planes are the larger image's.
+    if (device_ptrs && ctx->out_plane_stride) {
+        if (ctx->out_plane_stride < vw.band_pixels) return fail(ctx, RAST_EINVAL, "rast_draw_frames: output plane stride smaller than the band");
+        vw.out_plane = (uint32_t)ctx->out_plane_stride;
+    }
+    const size_t P = vw.out_plane;
     const uint32_t B = batch_capacity(ctx, vw);
     const uint32_t nb = n < B ? n : B;
 
@@ -662,6 +670,63 @@ void rast_transform_lights(const float view[16], rast_light *lights, uint32_t n_
 }
 
 float rast_spin_angle(float ry0, uint32_t k, uint32_t n_frames) { return ry0 + (float)k * (6.2831853f / (float)n_frames); }
+
+int rast_set_output_plane_stride(rast_ctx *ctx, uint64_t pixels) {
+    if (!ctx) return RAST_EINVAL;
+    if (pixels > 0xFFFFFFFFull) return fail(ctx, RAST_EINVAL, "rast_set_output_plane_stride: more than 2^32 pixels");
+    ctx->out_plane_stride = pixels;
+    return RAST_OK;
+}
+
+// ---- device memory shared between the processes of one node (one process per GPU) -----------------------------
+void *rast_device_alloc(rast_ctx *ctx, uint64_t bytes) {
+    if (!ctx) return nullptr;
+    void *p = nullptr;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { fail(ctx, RAST_ENOMEM, "rast_device_alloc", cudaGetLastError()); return nullptr; }
+    return p;
+}
+
+int rast_device_free(rast_ctx *ctx, void *device_ptr) {
+    if (!ctx) return RAST_EINVAL;
+    RAST_CUDA(ctx, cudaSetDevice(ctx->device));
+    RAST_CUDA(ctx, cudaFree(device_ptr));
+    return RAST_OK;
+}
+
+int rast_device_read(rast_ctx *ctx, void *host_dst, const void *device_src, uint64_t bytes) {
+    if (!ctx) return RAST_EINVAL;
+    RAST_CUDA(ctx, cudaSetDevice(ctx->device));
+    RAST_CUDA(ctx, cudaMemcpyAsync(host_dst, device_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RAST_OK;
+}
+
+int rast_ipc_export(rast_ctx *ctx, void *device_ptr, unsigned char handle[RAST_IPC_HANDLE_BYTES]) {
+    if (!ctx || !handle) return RAST_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == RAST_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    RAST_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    RAST_CUDA(ctx, cudaIpcGetMemHandle(&h, device_ptr));
+    memcpy(handle, &h, sizeof h);
+    return RAST_OK;
+}
+
+int rast_ipc_open(rast_ctx *ctx, const unsigned char handle[RAST_IPC_HANDLE_BYTES], void **device_ptr) {
+    if (!ctx || !handle || !device_ptr) return RAST_EINVAL;
+    RAST_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    RAST_CUDA(ctx, cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess)); // maps the peer's memory (NVLink P2P)
+    return RAST_OK;
+}
+
+int rast_ipc_close(rast_ctx *ctx, void *device_ptr) {
+    if (!ctx) return RAST_EINVAL;
+    RAST_CUDA(ctx, cudaSetDevice(ctx->device));
+    RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RAST_CUDA(ctx, cudaIpcCloseMemHandle(device_ptr));
+    return RAST_OK;
+}
 
 int rast_set_band(rast_ctx *ctx, uint32_t y0, uint32_t y1) {
     if (!ctx) return RAST_EINVAL;

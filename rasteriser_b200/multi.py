@@ -66,3 +66,86 @@ def gather_bands(local_band, height, dst=0, group=None):
         return out if planar else out[0]
     dist.gather(x, None, dst=dst, group=group)
     return None
+
+
+class PeerImage:
+    """A full-size image (RGB8 planes + f32 depth, `frames` of them) that lives in rank `dst`'s device memory and is
+    mapped into every other rank of the node (CUDA IPC over NVLink): each rank's shade pass stores its band -- or its
+    frames of a sequence -- straight into it, so the gather is the kernel's own store and needs no staging buffer, no
+    stitching copy and no collective; one barrier at the end tells rank `dst` that the image is complete.
+
+        img = PeerImage(renderer, W, H)                  # collective: every rank calls it
+        img.draw_band(args)                              # this rank's rows of one frame, into rank dst's image
+        img.draw_frames(args_list, first_index, stride)  # frames first_index, +stride, ... of a sequence
+        img.barrier(); rgb, depth = img.read()           # rank dst: numpy copies (other ranks: None)
+    """
+
+    def __init__(self, renderer, width, height, frames=1, dst=0, group=None):
+        self.r, self.W, self.H, self.frames, self.dst, self.group = renderer, int(width), int(height), int(frames), dst, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        P = self.W * self.H
+        self.rgb_bytes, self.depth_bytes = self.frames * 3 * P, self.frames * 4 * P
+        self._owned = self.rank == dst
+        self._flag = None
+        handles = [None, None]
+        if self._owned:
+            self.rgb, self.depth = renderer.device_alloc(self.rgb_bytes), renderer.device_alloc(self.depth_bytes)
+            handles = [renderer.ipc_export(self.rgb), renderer.ipc_export(self.depth)]
+        if self.world > 1:
+            dist.broadcast_object_list(handles, src=dst, group=group)
+            if not self._owned:
+                self.rgb, self.depth = renderer.ipc_open(handles[0]), renderer.ipc_open(handles[1])
+
+    def draw_band(self, args, frame=0):
+        """Render this rank's row band of one frame (rast_set_band must hold band_of_rank) into the shared image.
+        args: one Args / RastArgs, or a one-element list / ctypes array of them."""
+        import ctypes
+        y0, _ = band_of_rank(self.H, self.rank, self.world)
+        P = self.W * self.H
+        one = args if isinstance(args, (list, tuple, ctypes.Array)) else [args]
+        self.r.set_output_plane_stride(P)
+        try:
+            self.r.draw_frames_device(one, self.rgb + frame * 3 * P + y0 * self.W, self.depth + (frame * P + y0 * self.W) * 4)
+        finally:
+            self.r.set_output_plane_stride(0)
+
+    def draw_frames(self, args_list, first_index, stride):
+        """Render frames first_index, first_index + stride, ... of the sequence into their slots of the shared image."""
+        P = self.W * self.H
+        for i, a in enumerate(args_list):  # slots are `stride` frames apart: one call per frame keeps the ABI's dense layout
+            k = first_index + i * stride
+            self.r.draw_frames_device([a], self.rgb + k * 3 * P, self.depth + k * P * 4)
+
+    def barrier(self):
+        """Orders "every rank's kernels have finished" before whatever rank dst enqueues next on its stream: a one-element
+        all-reduce on the current stream (NCCL runs it after each rank's preceding kernels; it does not block the host)."""
+        if self.world > 1:
+            if self._flag is None:
+                self._flag = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+            dist.all_reduce(self._flag, group=self.group)
+
+    def read(self):
+        """Rank dst: (rgb [frames,3,H,W] uint8, depth [frames,H,W] float32) as numpy arrays; call after barrier()."""
+        if not self._owned:
+            return None
+        import numpy as np
+        rgb = np.empty((self.frames, 3, self.H, self.W), np.uint8)
+        depth = np.empty((self.frames, self.H, self.W), np.float32)
+        self.r.sync()
+        self.r.device_read(self.rgb, rgb)
+        self.r.device_read(self.depth, depth)
+        return rgb, depth
+
+    def close(self):
+        """Collective.  Peers unmap first, then the owner frees (exported memory must outlive every mapping)."""
+        if self.world > 1:
+            dist.barrier(group=self.group)  # nobody unmaps while a peer may still write
+        if not self._owned:
+            self.r.ipc_close(self.rgb)
+            self.r.ipc_close(self.depth)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        if self._owned:
+            self.r.device_free(self.rgb)
+            self.r.device_free(self.depth)
