@@ -310,7 +310,7 @@ def main():
     def step_device():
         if peer is not None:
             peer.draw_band(arr)
-            peer.barrier()
+            peer.barrier(sync=False)  # the renderer launches on torch's current stream (set_stream above)
             return
         r.draw_frames_device(arr, frames_dev.data_ptr(), depths_dev.data_ptr())
         if band_mode:  # NCCL over NVLink: band slabs to rank 0, on the same stream as the kernels

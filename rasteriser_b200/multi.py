@@ -117,13 +117,20 @@ class PeerImage:
             k = first_index + i * stride
             self.r.draw_frames_device([a], self.rgb + k * 3 * P, self.depth + k * P * 4)
 
-    def barrier(self):
-        """Orders "every rank's kernels have finished" before whatever rank dst enqueues next on its stream: a one-element
-        all-reduce on the current stream (NCCL runs it after each rank's preceding kernels; it does not block the host)."""
+    def barrier(self, sync=True):
+        """After it returns on rank dst (and the current stream has passed it), every rank's band is in the image.
+        sync=True first waits on the host for this rank's own kernels (the renderer may launch on a stream of its own);
+        sync=False is for callers whose renderer shares torch's current stream (Renderer.set_stream): the completion is
+        then ordered purely on the device by a one-element all-reduce -- NCCL runs it after each rank's preceding
+        kernels -- and the host is never blocked."""
+        if sync:
+            self.r.sync()
         if self.world > 1:
             if self._flag is None:
                 self._flag = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
             dist.all_reduce(self._flag, group=self.group)
+            if sync:
+                torch.cuda.current_stream().synchronize()
 
     def read(self):
         """Rank dst: (rgb [frames,3,H,W] uint8, depth [frames,H,W] float32) as numpy arrays; call after barrier()."""
