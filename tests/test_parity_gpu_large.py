@@ -101,3 +101,39 @@ def test_queue_overflow_is_correct():
         assert st["queued_chunks"] > (1 << 23)
     finally:
         r.close()
+
+
+def _large_case(name):
+    import json
+    import os
+    return json.load(open(os.path.join(S.GOLDEN, "large_cases.json")))[name]
+
+
+def test_config4_full_size_overdraw_8k_equals_reference_hashes():
+    """200 000 triangles R = 80 px at 7680x4320 (depth complexity ~50, every pixel covered): frame and depth hashes the
+    REFERENCE produced on this input (tests/golden/make_golden_large.py), winning-triangle ids of the oracle."""
+    want = _large_case("config4_overdraw_8k")
+    scene = orc.Scene(*synth.overdraw_scene(200000, 7680, 4320), [{"kd": (0.8, 0.8, 0.8), "texels": None}])
+    assert len(scene.tris) == want["triangles"]
+    r = make_renderer(scene, S.lights("threepoint"))
+    try:
+        f, d, t = gpu_draw(r, orc.make_args(7680, 4320))
+        assert int((t != orc.NO_TRIANGLE).sum()) == want["visible_pixels"]
+        assert orc.fnv(t) == want["tri_fnv"] and orc.fnv(d) == want["depth_fnv"] and orc.fnv(f) == want["frame_fnv"]
+    finally:
+        r.close()
+
+
+def test_config5_full_size_50m_triangles_64_lights_equals_reference_hashes():
+    """49 880 072 triangles, 64 lights, 3840x2160: same hashes as the reference's own frame on this input."""
+    want = _large_case("config5_tess227_64lights_4k")
+    scene = _tess_scene(227)
+    assert len(scene.tris) == want["triangles"] == 49880072
+    r = make_renderer(scene, synth.random_lights(64))
+    try:
+        f, d, t = gpu_draw(r, orc.make_args(3840, 2160))
+        assert int((t != orc.NO_TRIANGLE).sum()) == want["visible_pixels"]
+        assert orc.fnv(t) == want["tri_fnv"] and orc.fnv(d) == want["depth_fnv"] and orc.fnv(f) == want["frame_fnv"]
+        assert r.stats()["triangles"] == 49880072
+    finally:
+        r.close()
