@@ -432,19 +432,23 @@ def main():
     avg_ms = pass_ms[dominant] / launches_per_pass
     achieved = alg / (avg_ms * 1e-3) / 1e9
     total_alg = sum(ab.values())
-    traffic = None
+    traffic, issue = None, None
     try:  # DRAM bytes per launch of this kernel from the committed ncu --set full capture (profiles/), scaled to this launch size
         tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(opts.workload, {})
         kname = {"vertex": "k_vertex", "setup": "k_setup", "raster": "k_raster_chunks", "shade": "k_resolve_shade", "clear": "k_clear"}[dominant]
         if kname in tr:
             traffic = tr[kname]["dram_bytes_per_launch"] * frames_per_launch / tr[kname]["frames_per_launch"]
+            if "issue_active_pct" in tr[kname]:  # what actually limits the kernel (same capture): issue slots, not DRAM
+                issue = {"issue_active_pct": tr[kname]["issue_active_pct"], "l1tex_throughput_pct": tr[kname].get("l1tex_throughput_pct"),
+                         "warp_instructions_per_launch": tr[kname].get("warp_instructions_per_launch"),
+                         "source": "ncu --set full capture under profiles/ (smsp__issue_active.avg.pct_of_peak_sustained_active)"}
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": {"vertex": "k_vertex", "setup": "k_setup", "raster": "k_raster_chunks", "shade": "k_resolve_shade", "clear": "k_clear"}[dominant],
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms, "frames_per_launch": frames_per_launch,
                 "pass_ms_per_step": {k: v / prof_steps for k, v in pass_ms.items()},
-                "whole_frame_algorithmic_bytes": total_alg, "whole_frame_achieved_GBs": total_alg * n * world * opts.steps / (ms_total * 1e-3) / 1e9}
+                "limiter": issue, "whole_frame_algorithmic_bytes": total_alg, "whole_frame_achieved_GBs": total_alg * n * world * opts.steps / (ms_total * 1e-3) / 1e9}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     cpu = None
