@@ -953,9 +953,12 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View 
     const uint32_t xb = blockIdx.x * (STRIDE * GROUPS) + threadIdx.x * PX;
     const uint32_t row = blockIdx.y, f = blockIdx.z;
     const uint32_t P = vw.out_plane;
-    const size_t i0 = (size_t)f * vw.band_pixels + (size_t)row * vw.W + xb; // into vis
-    const size_t d0 = (size_t)f * P + (size_t)row * vw.W + xb;              // into depth
-    const size_t o0 = (size_t)f * 3 * P + (size_t)row * vw.W + xb;          // into the R plane of frame f
+    // One per-thread index serves the keys and both outputs: the frame's offset into each output (which differs from the
+    // offset into the keys: 3 planes per frame, and planes that may be larger than the band) is folded into block-uniform
+    // base pointers.  (A second per-thread 64-bit index cost 4 registers = one resident CTA per SM = 3.6 % of the pass.)
+    const size_t i0 = (size_t)f * vw.band_pixels + (size_t)row * vw.W + xb;
+    rgb += (size_t)f * (3 * (size_t)P - vw.band_pixels);      // rgb[i0] = R plane of frame f, this thread's first pixel
+    if (depth) depth += (size_t)f * ((size_t)P - vw.band_pixels);
     unsigned long long *vis = bt.vis + i0;
     const bool reset = f != keep_frame; // hand the keys back as VIS_EMPTY (the next batch then needs no clear pass)
 
@@ -972,6 +975,9 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View 
             //  33 % SLOWER: 8.20 -> 10.92 ms per 720 frames -- the records are L1 / L2 hits anyway and the prefetches only load the LSU)
         }
     }
+
+    // (A straight-line exit for warps whose pixels are all background -- 4 stores per group at immediate offsets instead
+    //  of a trip through the loop below -- measured 14 % SLOWER at equal register count: 8.29 -> 9.49 ms per 720 frames.)
 
     // phase 2.  The per-frame base pointers are made opaque so that a gather is "base + index * 16" (one
     // IMAD.WIDE) instead of a 64-bit add of the frame offset to every index followed by the address computation.
@@ -1005,7 +1011,7 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View 
                 }
             }
         }
-        const size_t o = o0 + g * STRIDE, i = d0 + g * STRIDE;
+        const size_t o = i0 + g * STRIDE, i = o;
         if (PX == 4) {
             *reinterpret_cast<uchar4 *>(rgb + o) = make_uchar4(px[0].r, px[PX > 1 ? 1 : 0].r, px[PX > 2 ? 2 : 0].r, px[PX > 3 ? 3 : 0].r);
             *reinterpret_cast<uchar4 *>(rgb + o + P) = make_uchar4(px[0].g, px[PX > 1 ? 1 : 0].g, px[PX > 2 ? 2 : 0].g, px[PX > 3 ? 3 : 0].g);
