@@ -364,7 +364,7 @@ double seconds_since(const std::chrono::steady_clock::time_point &t0) {
 void set_obj_piece_bytes(size_t bytes) { g_piece_bytes = bytes; }
 
 bool load_obj(const std::string &obj_file, const std::string &materials_directory, Model &model, std::string &error, bool verbose,
-              unsigned threads, LoadStats *stats) {
+              unsigned threads, LoadStats *stats, bool decode_textures) {
     const auto t_start = std::chrono::steady_clock::now();
     if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
     const int fd = ::open(obj_file.c_str(), O_RDONLY);
@@ -598,10 +598,16 @@ bool load_obj(const std::string &obj_file, const std::string &materials_director
         m.kd[0] = e.kd[0]; m.kd[1] = e.kd[1]; m.kd[2] = e.kd[2];
         if (!e.map_kd.empty()) {
             std::string terr;
-            if (!load_texture(materials_directory + e.map_kd, m, terr, verbose)) { error += terr; return false; }
+            if (decode_textures) {
+                if (!load_texture(materials_directory + e.map_kd, m, terr, verbose)) { error += terr; return false; }
+            } else {
+                m.has_texture = true;
+                m.texture_file = materials_directory + e.map_kd; // fileloader.cpp:55
+            }
         }
         model.materials.push_back(m);
     }
+    model.shape_triangles = shape_tris;
     // load_triangles per shape (fileloader.cpp:60-77,116-118)
     if (verbose) {
         for (uint64_t n : shape_tris) std::cout << "Loading " << n << " triangles..." << std::endl;

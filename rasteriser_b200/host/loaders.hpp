@@ -76,6 +76,7 @@ struct Model {
     Pod<float> positions, normals, uvs;
     Pod<int32_t> tris; // 10 per triangle
     std::vector<MaterialData> materials;
+    std::vector<uint64_t> shape_triangles; // triangles of each exported shape, in file order (the "Loading N triangles..." lines)
     size_t n_tris() const { return tris.size() / 10; }
 };
 
@@ -89,8 +90,10 @@ struct LoadStats {          // filled by load_obj when non-null (tools/bench_loa
 // `error` set when the .obj cannot be read; warnings (missing .mtl) go to `error` with a true return.
 // The file is read into memory once and parsed by `threads` workers (0 = all hardware threads) in two passes:
 // count, then parse straight into the final arrays.  The result is independent of the thread count.
+// decode_textures = false leaves MaterialData::texels empty (texture_file, has_texture are still set): for callers that
+// construct the reference's own Material objects from the file names (include/rast_load_obj.hpp).
 bool load_obj(const std::string &obj_file, const std::string &materials_directory, Model &model, std::string &error, bool verbose = true,
-              unsigned threads = 0, LoadStats *stats = nullptr);
+              unsigned threads = 0, LoadStats *stats = nullptr, bool decode_textures = true);
 
 void set_obj_piece_bytes(size_t bytes); // test hook: 0 = automatic
 

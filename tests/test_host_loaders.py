@@ -334,3 +334,29 @@ def test_animated_png_frames_decode_identically():
         dims, out = np.zeros(3, np.uint32), np.zeros(w * h * 3, np.uint8)
         assert l.rasth_png_read(p.encode(), dims.ctypes.data, out.ctypes.data, out.size) == 0
         assert np.array_equal(out.reshape(h, w, 3), frames[0].transpose(1, 2, 0))
+
+
+def test_load_obj_shim_with_reference_signature(tmp_path):
+    """include/rast_load_obj.hpp: the reference's load_obj signature (fileloader.h:16) on the parallel reader, compiled
+    with stand-in types; same vectors as the reference's loader produced (golden scenes), same stdout lines."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "rasteriser_b200", "host")
+    exe = str(tmp_path / "shim")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-o", exe, os.path.join(root, "tests", "shim_load_obj_main.cpp"),
+                           os.path.join(host, "loaders.cpp"), os.path.join(host, "png.cpp"), "-lz", "-lpthread"])
+    out = subprocess.run([exe, os.path.join(DATA, "Suzanne.obj"), DATA + "/"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[0].startswith("Loaded texture ") and lines[1] == "Loading 968 triangles..." and lines[2].startswith("Loaded model ")
+    f = lines[-1].split()
+    z = np.load(os.path.join(S.GOLDEN, "scenes.npz"))
+
+    def fnv(a):
+        h = 1469598103934665603
+        for b in np.ascontiguousarray(a).view(np.uint8).ravel().tolist():
+            h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return "%016x" % h
+    assert [int(x) for x in f[1:6]] == [len(z["suzanne_pos"]), len(z["suzanne_nrm"]), len(z["suzanne_uv"]), len(z["suzanne_tris"]), 1]
+    assert f[6] == fnv(z["suzanne_pos"]) and f[7] == fnv(z["suzanne_tris"]) and f[8].endswith("SuzanneTex.png")
+    assert subprocess.run([exe, "/nonexistent.obj"], capture_output=True).returncode == 1   # fileloader.cpp:98-100
