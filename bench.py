@@ -363,17 +363,19 @@ def main():
 
         step_host()
         barrier()
+        bytes0 = r.d2h_bytes()
         t0 = time.perf_counter()
         for _ in range(opts.steps):
             step_host()
         barrier()
         wall = time.perf_counter() - t0
+        d2h_step = (r.d2h_bytes() - bytes0) // opts.steps  # what actually crossed PCIe (the library counts its copies)
         t = torch.tensor([wall], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": (1 if band_mode else world) * n * opts.steps / float(t.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(n * 208 + len(chunks) * len(wl["lights"]) * 32), "d2h_bytes_per_step": int(n * 7 * P),
-               "note": "rast_draw_frames with pinned host outputs, %d frames per call: RGB8 + f32 depth of every frame copied D2H inside the timed region (wall clock, max over ranks)" % chunk}
+               "h2d_bytes_per_step": int(n * 208 + len(chunks) * len(wl["lights"]) * 32), "d2h_bytes_per_step": int(d2h_step), "host_bytes_delivered_per_step": int(n * 7 * P),
+               "note": "rast_draw_frames with pinned host outputs, %d frames per call: RGB8 + f32 depth of every frame delivered complete in host memory inside the timed region (wall clock, max over ranks); the library copies each frame's covered rectangle over PCIe (d2h_bytes_per_step, counted by the library) and writes the constant background of the host buffers itself on 4 host threads (RAST_SPARSE_COPY=0 copies whole frames)" % chunk}
         checksum = int(frames_host[len(chunks[-1]) // 2].astype(np.uint64).sum())
         # the same with colour only (the reference's spin loop shows frames; its depth buffer is scratch)
         def step_host_rgb():
@@ -381,6 +383,7 @@ def main():
                 r.draw_frames(c, frames_host[:len(c)], None)
         step_host_rgb()
         barrier()
+        bytes0 = r.d2h_bytes()
         t0 = time.perf_counter()
         for _ in range(opts.steps):
             step_host_rgb()
@@ -388,7 +391,7 @@ def main():
         t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e["frames_only"] = {"value": (1 if band_mode else world) * n * opts.steps / float(t.item()), "d2h_bytes_per_step": int(n * 3 * P),
+        e2e["frames_only"] = {"value": (1 if band_mode else world) * n * opts.steps / float(t.item()), "d2h_bytes_per_step": int((r.d2h_bytes() - bytes0) // opts.steps), "host_bytes_delivered_per_step": int(n * 3 * P),
                               "note": "same call with depths=NULL: only the RGB8 frames cross PCIe"}
         lib.rast_host_free(fb)
         lib.rast_host_free(db)

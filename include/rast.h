@@ -175,6 +175,12 @@ int rast_set_profiling(rast_ctx *ctx, int enabled);
 int rast_get_pass_ms(rast_ctx *ctx, float ms[RAST_PASS_COUNT]);
 /* number of kernel launches issued by this context since creation */
 uint64_t rast_launch_count(const rast_ctx *ctx);
+/* Bytes of frame / depth data this context has copied device -> host so far.  Host-buffer draws copy only the
+ * rectangle of each frame that holds drawn pixels and write the constant rest of the caller's buffers (frame 0,
+ * depth 1.0f: the clear of renderer.cpp:85-86) on the host, so this can be well below 7 bytes per pixel and frame;
+ * the buffers the caller sees are the same bytes either way.  RAST_SPARSE_COPY=0 in the environment copies whole
+ * frames; RAST_HOST_THREADS sets the threads that write the background (default min(4, hardware / 2)). */
+uint64_t rast_d2h_bytes(rast_ctx *ctx);
 /* Diagnostic: the kernels divide several numerators by one divisor with a shared reciprocal (the compiler's
  * own div.rn.f32 fast-path sequence, csrc/exact.cuh).  This compares that against IEEE division on the GPU
  * for about n_samples pseudo-random quotients and returns how many differ in any bit (expected: 0). */

@@ -64,6 +64,7 @@ SYMBOLS = {
     "rast_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "rast_get_pass_ms": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rast_launch_count": (C.c_uint64, [C.c_void_p]),
+    "rast_d2h_bytes": (C.c_uint64, [C.c_void_p]),
     "rast_selftest_division": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
     "rast_host_alloc": (C.c_void_p, [C.c_uint64]),
     "rast_host_free": (None, [C.c_void_p]),

@@ -209,6 +209,10 @@ class Renderer:
         self._check(self._lib.rast_draw_frames(self._h, arr, n, C.c_void_p(frames_ptr) if frames_ptr else None,
                                                C.c_void_p(depths_ptr) if depths_ptr else None, 1), "rast_draw_frames")
 
+    def d2h_bytes(self):
+        """Bytes of frame / depth data copied device -> host by this renderer so far (sparse copies count what they move)."""
+        return int(self._lib.rast_d2h_bytes(self._h))
+
     def sync(self):
         self._check(self._lib.rast_sync(self._h), "rast_sync")
 

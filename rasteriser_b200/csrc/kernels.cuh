@@ -93,6 +93,9 @@ struct Batch {
     uint32_t queue_cap;
     uint32_t tiny_max_pixels; // bboxes up to this many pixels are rasterised by the setup thread itself
     unsigned long long *counters; // [0] queue count (may exceed queue_cap), [1] queue cursor, [2] overflow flag
+    uint32_t *bbox;           // [n_frames][4] or nullptr: covered rectangle of each frame, written by the shade pass as
+                              // atomicMin of (x, y, W-1-x, rows-1-y) over the covered pixels (all 0xFFFFFFFF = nothing covered);
+                              // the host copies only that rectangle back and fills the rest itself
 };
 
 // Screen-tile bins of the binned raster schedule (k_plan_tiles / k_fill_tiles / k_raster_tiles).
@@ -973,6 +976,27 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View 
             for (int k = 0; k < PX; ++k) covered |= (keys[k] != VIS_EMPTY ? 1u : 0u) << (g * PX + k);
             // (prefetch.global.L1 of the winning triangle's record from here, while the key is in a register, measured
             //  33 % SLOWER: 8.20 -> 10.92 ms per 720 frames -- the records are L1 / L2 hits anyway and the prefetches only load the LSU)
+        }
+    }
+
+    // Covered rectangle of the frame (for the sparse device-to-host copy): one warp-wide min per bound, and an atomic
+    // only when the warp would move that bound (the plain read may be stale -- then the atomic is merely redundant).
+    if (bt.bbox != nullptr && __any_sync(0xFFFFFFFFu, covered != 0u)) {
+        uint32_t lo = 0xFFFFFFFFu, hic = 0xFFFFFFFFu;
+        if (covered) {
+            const uint32_t b0 = (uint32_t)__ffs((int)covered) - 1u, b1 = 31u - (uint32_t)__clz((int)covered); // bit = group * PX + pixel
+            lo = xb + (b0 / PX) * STRIDE + (b0 % PX);
+            hic = vw.W - 1u - (xb + (b1 / PX) * STRIDE + (b1 % PX));
+        }
+        lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+        hic = __reduce_min_sync(0xFFFFFFFFu, hic);
+        if ((threadIdx.x & 31u) == 0u) {
+            uint32_t *bb = bt.bbox + 4u * f;
+            const uint32_t rows = vw.y1 - vw.y0;
+            if (lo < bb[0]) atomicMin(bb + 0, lo);
+            if (row < bb[1]) atomicMin(bb + 1, row);
+            if (hic < bb[2]) atomicMin(bb + 2, hic);
+            if (rows - 1u - row < bb[3]) atomicMin(bb + 3, rows - 1u - row);
         }
     }
 

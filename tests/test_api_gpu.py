@@ -103,3 +103,45 @@ def test_shared_reciprocal_division_is_ieee_exact():
         assert r.selftest_division(1 << 30, seed=987654321) == 0
     finally:
         r.close()
+
+
+def test_sparse_host_copy_delivers_the_same_bytes(monkeypatch):
+    """Host-buffer draws copy only each frame's covered rectangle over PCIe and write the background on the host: the
+    caller's buffers -- pre-filled with garbage here -- must end up byte-identical to whole-frame copies, for single
+    frames, batches, bands, an empty frame and a frame that is covered edge to edge."""
+    from rasteriser_b200 import api
+    scene, lights = S.scene("suzanne"), S.lights("threepoint")
+    poses = [api.Args(641, 483, tait_bryan_angles=(0.1 * k, 0.9 * k, 0.0), displacement=(0.3 * (k % 3) - 0.3, 0.0, 0.0)) for k in range(5)]
+    poses.append(api.Args(641, 483, displacement=(40.0, 0.0, 0.0)))             # nothing on screen
+    poses.append(api.Args(641, 483, scale=6.0, displacement=(0.0, 0.0, 1.0)))    # camera inside the model: covered edge to edge
+    results = {}
+    for sparse in ("0", "1"):
+        monkeypatch.setenv("RAST_SPARSE_COPY", sparse)
+        r = make_renderer(scene, lights)
+        try:
+            out = []
+            b0 = r.d2h_bytes()
+            for a in poses:  # single frames
+                f, d = np.full((3, 483, 641), 0xAB, np.uint8), np.full((483, 641), -7.0, np.float32)
+                r.draw_frame(a, f, d)
+                out.append((f, d))
+            fs, ds = np.full((len(poses), 3, 483, 641), 0xCD, np.uint8), np.full((len(poses), 483, 641), 5.0, np.float32)
+            r.draw_frames(poses, fs, ds)  # one batch
+            out.append((fs, ds))
+            fs2 = np.full((len(poses), 3, 483, 641), 0xEF, np.uint8)
+            r.draw_frames(poses, fs2, None)  # colour only
+            out.append((fs2, None))
+            r.set_band(100, 333)
+            fb, db = np.full((3, 233, 641), 0x11, np.uint8), np.full((233, 641), 9.0, np.float32)
+            r.draw_frame(poses[1], fb, db)
+            out.append((fb, db))
+            results[sparse] = (out, r.d2h_bytes() - b0)
+        finally:
+            r.close()
+    whole, sparse = results["0"], results["1"]
+    for (f0, d0), (f1, d1) in zip(whole[0], sparse[0]):
+        assert np.array_equal(f0, f1)
+        assert (d0 is None and d1 is None) or np.array_equal(d0.view(np.uint32), d1.view(np.uint32))
+    f_empty, d_empty = sparse[0][5]
+    assert not f_empty.any() and (d_empty == 1.0).all()
+    assert sparse[1] < 0.9 * whole[1]  # fewer bytes crossed PCIe (two of the seven poses cover most of the frame)
