@@ -147,7 +147,17 @@ struct rast_ctx {
     uint32_t band_y0 = 0, band_y1 = 0; // 0,0 = whole frame
 
     // per-call / per-batch buffers
-    DeviceBuffer d_frames, d_lights, d_rv, d_cn, d_vis, d_queue, d_counters, d_aux, d_tiles, d_list, d_items;
+    DeviceBuffer d_frames, d_lights, d_queue, d_counters, d_aux, d_tiles, d_list, d_items;
+    // What the shade pass of batch b reads while vertex / setup / raster of batch b+1 write it exists twice (pipeline slot =
+    // batch parity): the front passes of the next batch run on a high-priority stream of their own while the shade pass of
+    // this batch runs on the context's stream -- both are issue-bound at 66-76 % and fill each other's gaps (two contexts
+    // on one GPU measured +13 %; RAST_OVERLAP=0 serialises).
+    DeviceBuffer d_rv[2], d_cn[2], d_vis[2];
+    cudaStream_t front_stream = nullptr;
+    cudaEvent_t ev_raster[2] = {nullptr, nullptr}, ev_shade[2] = {nullptr, nullptr};
+    bool shade_pending[2] = {false, false};
+    bool overlap = true;
+    int last_ps = 0; // pipeline slot of the most recent batch (rast_read_triangle_ids / rast_get_stats)
     DeviceBuffer d_rgb[2], d_depth[2];
     PinnedBuffer h_frames, h_lights, h_status, h_bbox[2];
     DeviceBuffer d_bbox[2];
@@ -165,8 +175,8 @@ struct rast_ctx {
     uint32_t list_cap = 1u << 22, items_cap = 1u << 25;
     // visibility-buffer bookkeeping: slots [0, vis_clean_slots) of band size vis_clean_pixels hold VIS_EMPTY,
     // except vis_dirty_slot (the last frame of the previous call, kept for inspection)
-    uint32_t vis_clean_slots = 0, vis_clean_pixels = 0;
-    int vis_dirty_slot = -1;
+    uint32_t vis_clean_slots[2] = {0, 0}, vis_clean_pixels[2] = {0, 0};
+    int vis_dirty_slot[2] = {-1, -1};
 
     // most recent frame (for rast_read_triangle_ids / rast_depth_to_u8 / stats)
     rk::View last_view{};
@@ -240,41 +250,47 @@ uint32_t batch_capacity(const rast_ctx *ctx, const rk::View &vw) {
 }
 
 // Launch the five passes for frames [first, first+count) of the uploaded parameter block.
+// ps = pipeline slot (which copy of rv / cn / vis); two_streams: the shade pass goes to ctx->front_stream, ordered after this
+// batch's raster pass by an event.  *done_stream receives the stream on which the batch's last kernel was launched.
 int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count, uint8_t *rgb_dev, float *depth_dev, uint32_t keep_frame,
-                 uint32_t *bbox_dev = nullptr) {
+                 uint32_t *bbox_dev, int ps, bool two_streams, cudaStream_t *done_stream) {
     rk::Batch bt;
     bt.bbox = bbox_dev;
     bt.frames = ctx->d_frames.as<rk::FrameParams>() + first;
     bt.n_frames = count;
-    bt.rv = ctx->d_rv.as<float4>();
-    bt.cn = ctx->pre_normals ? ctx->d_cn.as<float4>() : nullptr;
-    bt.vis = ctx->d_vis.as<unsigned long long>();
+    bt.rv = ctx->d_rv[ps].as<float4>();
+    bt.cn = ctx->pre_normals ? ctx->d_cn[ps].as<float4>() : nullptr;
+    bt.vis = ctx->d_vis[ps].as<unsigned long long>();
     bt.queue = ctx->d_queue.as<uint2>();
     bt.queue_cap = ctx->queue_cap;
     bt.tiny_max_pixels = ctx->tiny_max_pixels;
     bt.counters = ctx->d_counters.as<unsigned long long>();
     const rk::Scene &sc = ctx->scene;
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = two_streams ? ctx->front_stream : ctx->stream;
     const bool prof = ctx->profiling;
     const size_t n_vis = (size_t)count * vw.band_pixels;
 
+    if (ctx->shade_pending[ps]) { // the shade pass that last read this slot's rv / cn / vis must be done before they are rewritten
+        RAST_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_shade[ps], 0));
+        ctx->shade_pending[ps] = false;
+    }
     if (prof) cudaEventRecord(ctx->ev_pass[0], st);
     // Visibility slots known to be empty (handed back by the previous shade pass) are not cleared again.
     uint32_t n_clear_launches = 0;
-    if (ctx->vis_clean_pixels != vw.band_pixels) { ctx->vis_clean_slots = 0; ctx->vis_dirty_slot = -1; }
-    if (ctx->vis_dirty_slot >= 0 && (uint32_t)ctx->vis_dirty_slot < ctx->vis_clean_slots) { // only one dirty slot is tracked: settle it now
-        rk::k_clear<<<grid_for(((size_t)vw.band_pixels + 1) / 2, 256), 256, 0, st>>>(bt.vis + (size_t)ctx->vis_dirty_slot * vw.band_pixels, vw.band_pixels);
-        ctx->vis_dirty_slot = -1;
+    if (ctx->vis_clean_pixels[ps] != vw.band_pixels) { ctx->vis_clean_slots[ps] = 0; ctx->vis_dirty_slot[ps] = -1; }
+    if (ctx->vis_dirty_slot[ps] >= 0 && (uint32_t)ctx->vis_dirty_slot[ps] < ctx->vis_clean_slots[ps]) { // only one dirty slot is tracked: settle it now
+        rk::k_clear<<<grid_for(((size_t)vw.band_pixels + 1) / 2, 256), 256, 0, st>>>(bt.vis + (size_t)ctx->vis_dirty_slot[ps] * vw.band_pixels, vw.band_pixels);
+        ctx->vis_dirty_slot[ps] = -1;
         n_clear_launches++;
     }
-    if (count > ctx->vis_clean_slots) {
-        const size_t from = (size_t)ctx->vis_clean_slots * vw.band_pixels;
+    if (count > ctx->vis_clean_slots[ps]) {
+        const size_t from = (size_t)ctx->vis_clean_slots[ps] * vw.band_pixels;
         rk::k_clear<<<grid_for((n_vis - from + 1) / 2, 256), 256, 0, st>>>(bt.vis + from, n_vis - from);
-        if (ctx->vis_dirty_slot >= (int)ctx->vis_clean_slots) ctx->vis_dirty_slot = -1;
-        ctx->vis_clean_slots = count;
+        if (ctx->vis_dirty_slot[ps] >= (int)ctx->vis_clean_slots[ps]) ctx->vis_dirty_slot[ps] = -1;
+        ctx->vis_clean_slots[ps] = count;
         n_clear_launches++;
     }
-    ctx->vis_clean_pixels = vw.band_pixels;
+    ctx->vis_clean_pixels[ps] = vw.band_pixels;
     if (prof) cudaEventRecord(ctx->ev_pass[1], st);
     if (sc.V) rk::k_vertex<<<dim3(grid_for((size_t)sc.V + (bt.cn ? sc.Nn : 0u), 256), count), 256, 0, st>>>(sc, vw, bt);
     if (prof) cudaEventRecord(ctx->ev_pass[2], st);
@@ -317,6 +333,11 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
         n_tile_launches += 1;
     }
     if (prof) cudaEventRecord(ctx->ev_pass[4], st);
+    if (two_streams) { // the shade pass runs on the context's stream, after this batch's raster pass
+        RAST_CUDA(ctx, cudaEventRecord(ctx->ev_raster[ps], st));
+        st = ctx->stream;
+        RAST_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_raster[ps], 0));
+    }
     if (bbox_dev) cudaMemsetAsync(bbox_dev, 0xFF, (size_t)count * 16, st);
     if (vw.band_pixels) {
         // 4 adjacent pixels per lane (uchar4 / float4 stores) is slower into local memory but faster when
@@ -340,7 +361,13 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     }
     if (prof) cudaEventRecord(ctx->ev_pass[5], st);
     ctx->launches += n_tile_launches + n_clear_launches + (sc.V ? 1 : 0) + ((sc.T && vw.band_pixels) ? 2 : 0) + (vw.band_pixels ? 1 : 0);
-    if (keep_frame < count) ctx->vis_dirty_slot = (int)keep_frame; // that slot still holds its keys (rast_read_triangle_ids)
+    if (keep_frame < count) ctx->vis_dirty_slot[ps] = (int)keep_frame; // that slot still holds its keys (rast_read_triangle_ids)
+    if (two_streams) {
+        RAST_CUDA(ctx, cudaEventRecord(ctx->ev_shade[ps], st));
+        ctx->shade_pending[ps] = true;
+    }
+    ctx->last_ps = ps;
+    *done_stream = st;
     RAST_CUDA(ctx, cudaGetLastError());
     if (prof) {
         RAST_CUDA(ctx, cudaEventSynchronize(ctx->ev_pass[5]));
@@ -522,13 +549,17 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
     // buffers
     RAST_CUDA(ctx, ctx->d_frames.reserve((size_t)n * sizeof(rk::FrameParams)));
     RAST_CUDA(ctx, ctx->d_lights.reserve((ctx->lights.size() + 1) * sizeof(rk::LightDev)));
-    RAST_CUDA(ctx, ctx->d_rv.reserve((size_t)nb * ctx->scene.V * sizeof(float4)));
+    const uint32_t n_batches = (n + nb - 1) / nb;
+    const bool two_streams = ctx->overlap && !ctx->profiling && n_batches > 1; // a single batch has nothing to overlap with
+    for (int ps = 0; ps < (n_batches > 1 ? 2 : 1); ++ps) {
+        RAST_CUDA(ctx, ctx->d_rv[ps].reserve((size_t)nb * ctx->scene.V * sizeof(float4)));
+        if ((size_t)ctx->scene.Nn * 8 <= P) RAST_CUDA(ctx, ctx->d_cn[ps].reserve((size_t)nb * ctx->scene.Nn * sizeof(float4)));
+        if ((size_t)nb * P * 8 > ctx->d_vis[ps].bytes) { ctx->vis_clean_slots[ps] = 0; ctx->vis_dirty_slot[ps] = -1; }
+        RAST_CUDA(ctx, ctx->d_vis[ps].reserve((size_t)nb * P * 8));
+    }
     // camera-space normals are precomputed per frame when there are few of them relative to the image;
     // for huge meshes the shade pass transforms only the normals of winning triangles instead
     ctx->pre_normals = (size_t)ctx->scene.Nn * 8 <= P;
-    if (ctx->pre_normals) RAST_CUDA(ctx, ctx->d_cn.reserve((size_t)nb * ctx->scene.Nn * sizeof(float4)));
-    if ((size_t)nb * P * 8 > ctx->d_vis.bytes) { ctx->vis_clean_slots = 0; ctx->vis_dirty_slot = -1; }
-    RAST_CUDA(ctx, ctx->d_vis.reserve((size_t)nb * P * 8));
     RAST_CUDA(ctx, ctx->d_queue.reserve((size_t)ctx->queue_cap * sizeof(uint2)));
     RAST_CUDA(ctx, ctx->d_counters.reserve(128));
 
@@ -565,12 +596,13 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
     if (!ctx->lights.empty())
         RAST_CUDA(ctx, cudaMemcpyAsync(ctx->d_lights.p, ctx->h_lights.p, ctx->lights.size() * sizeof(rk::LightDev), cudaMemcpyHostToDevice, ctx->stream));
     RAST_CUDA(ctx, cudaEventRecord(ctx->ev_params, ctx->stream));
+    if (two_streams) RAST_CUDA(ctx, cudaStreamWaitEvent(ctx->front_stream, ctx->ev_params, 0)); // also orders it behind everything earlier on the context's stream
 
     if (ctx->profiling) memset(ctx->pass_ms, 0, sizeof ctx->pass_ms);
 
-    int slot = 0;
+    int slot = 0, ps = 0;
     PendingBatch pending;
-    for (uint32_t first = 0; first < n; first += nb) {
+    for (uint32_t first = 0; first < n; first += nb, ps ^= (n_batches > 1 ? 1 : 0)) {
         const uint32_t count = (n - first) < nb ? (n - first) : nb;
         // outputs: the caller's device buffers, or the context's own (double-buffered when a D2H copy follows)
         uint8_t *rgb_dst;
@@ -599,7 +631,8 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
             RAST_CUDA(ctx, ctx->h_bbox[slot].reserve((size_t)nb * 16));
             bbox_dev = ctx->d_bbox[slot].as<uint32_t>();
         }
-        int rc = launch_batch(ctx, vw, first, count, rgb_dst, depth_dst, keep_frame, bbox_dev);
+        cudaStream_t done_stream = ctx->stream;
+        int rc = launch_batch(ctx, vw, first, count, rgb_dst, depth_dst, keep_frame, bbox_dev, ps, two_streams, &done_stream);
         if (rc != RAST_OK) return rc;
 
         ctx->last_view = vw;
@@ -610,8 +643,8 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
         ctx->have_frame = true;
 
         if (!device_ptrs) {
-            if (bbox_dev) RAST_CUDA(ctx, cudaMemcpyAsync(ctx->h_bbox[slot].p, bbox_dev, (size_t)count * 16, cudaMemcpyDeviceToHost, ctx->stream));
-            RAST_CUDA(ctx, cudaEventRecord(ctx->ev_done[slot], ctx->stream));
+            if (bbox_dev) RAST_CUDA(ctx, cudaMemcpyAsync(ctx->h_bbox[slot].p, bbox_dev, (size_t)count * 16, cudaMemcpyDeviceToHost, done_stream));
+            RAST_CUDA(ctx, cudaEventRecord(ctx->ev_done[slot], done_stream));
             // the previous batch is brought back now, with this one already queued behind it on the GPU
             if (pending.valid) { rc = finish_batch(ctx, pending, vw, frames, depths); if (rc != RAST_OK) return rc; }
             pending.valid = true; pending.slot = slot; pending.first = first; pending.count = count;
@@ -620,6 +653,7 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
         }
     }
     if (pending.valid) { int rc = finish_batch(ctx, pending, vw, frames, depths); if (rc != RAST_OK) return rc; }
+    ctx->shade_pending[0] = ctx->shade_pending[1] = false; // the next call's front passes start behind its parameter upload, which is behind these shade passes
     // queue statistics of the last batch travel back asynchronously (overflow => grow next time)
     RAST_CUDA(ctx, cudaMemcpyAsync(ctx->h_status.p, ctx->d_counters.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
     if (!device_ptrs) {
@@ -653,10 +687,17 @@ int rast_create(int device, rast_ctx **out) {
     bool ok = cudaSetDevice(device) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    {
+        int least = 0, greatest = 0;
+        ok = ok && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(&ctx->front_stream, cudaStreamNonBlocking, greatest) == cudaSuccess;
+    }
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_params, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i) {
         ok = ok && cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_raster[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_shade[i], cudaEventDisableTiming) == cudaSuccess;
     }
     for (int i = 0; i <= RAST_PASS_COUNT && ok; ++i) ok = ok && cudaEventCreate(&ctx->ev_pass[i]) == cudaSuccess;
     ok = ok && ctx->h_status.reserve(64) == cudaSuccess;
@@ -665,6 +706,7 @@ int rast_create(int device, rast_ctx **out) {
         int sms = 0, per_sm = 0;
         ok = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
         ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rk::k_raster_chunks, rk::RASTER_WARPS * 32, 0) == cudaSuccess;
+        if (const char *e = getenv("RAST_RASTER_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
         ctx->raster_grid = (unsigned)(sms > 0 ? sms : 148) * (unsigned)(per_sm > 0 ? per_sm : 1);
     }
     if (!ok) {
@@ -675,6 +717,7 @@ int rast_create(int device, rast_ctx **out) {
     ctx->stream = ctx->own_stream;
     if (const char *e = getenv("RAST_SHADE_PX")) ctx->shade_px = atoi(e) == 4 ? 4 : 1;
     if (const char *e = getenv("RAST_SPARSE_COPY")) ctx->sparse_copy = atoi(e) != 0;
+    if (const char *e = getenv("RAST_OVERLAP")) ctx->overlap = atoi(e) != 0;
     {
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
         ctx->host_threads = std::min(4u, std::max(1u, hw / 2u)) - 1u; // measured on the 16-core host: 4 / 8 / 16 threads -> 5.49 / 5.38 / 5.30 k frames/s (memory-bound)
@@ -691,21 +734,27 @@ void rast_destroy(rast_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->front_stream) cudaStreamSynchronize(ctx->front_stream);
     DeviceBuffer *dev[] = {&ctx->d_pos, &ctx->d_nrm, &ctx->d_uv, &ctx->d_vidx, &ctx->d_attr, &ctx->d_mats, &ctx->d_texels, &ctx->d_frames, &ctx->d_lights,
-                           &ctx->d_rv, &ctx->d_cn, &ctx->d_tiles, &ctx->d_list, &ctx->d_items, &ctx->d_vis, &ctx->d_queue, &ctx->d_counters, &ctx->d_aux, &ctx->d_rgb[0], &ctx->d_rgb[1], &ctx->d_depth[0], &ctx->d_depth[1]};
+                           &ctx->d_rv[0], &ctx->d_rv[1], &ctx->d_cn[0], &ctx->d_cn[1], &ctx->d_tiles, &ctx->d_list, &ctx->d_items, &ctx->d_vis[0], &ctx->d_vis[1], &ctx->d_bbox[0], &ctx->d_bbox[1], &ctx->d_queue, &ctx->d_counters, &ctx->d_aux, &ctx->d_rgb[0], &ctx->d_rgb[1], &ctx->d_depth[0], &ctx->d_depth[1]};
     for (DeviceBuffer *b : dev) b->release();
     ctx->h_frames.release();
     ctx->h_lights.release();
     ctx->h_status.release();
+    ctx->h_bbox[0].release();
+    ctx->h_bbox[1].release();
     if (ctx->ev_params) cudaEventDestroy(ctx->ev_params);
     for (int i = 0; i < 2; ++i) {
         if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+        if (ctx->ev_raster[i]) cudaEventDestroy(ctx->ev_raster[i]);
+        if (ctx->ev_shade[i]) cudaEventDestroy(ctx->ev_shade[i]);
     }
     for (int i = 0; i <= RAST_PASS_COUNT; ++i)
         if (ctx->ev_pass[i]) cudaEventDestroy(ctx->ev_pass[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->front_stream) cudaStreamDestroy(ctx->front_stream);
     delete ctx;
 }
 
@@ -964,7 +1013,7 @@ int rast_read_triangle_ids(rast_ctx *ctx, uint32_t *tri_ids) {
     RAST_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint32_t P = ctx->last_view.band_pixels;
     RAST_CUDA(ctx, ctx->d_aux.reserve((size_t)P * 4 + 64));
-    const unsigned long long *vis = ctx->d_vis.as<unsigned long long>() + (size_t)ctx->last_slot_frame * P;
+    const unsigned long long *vis = ctx->d_vis[ctx->last_ps].as<unsigned long long>() + (size_t)ctx->last_slot_frame * P;
     rk::k_extract_tri_ids<<<grid_for(P, 256), 256, 0, ctx->stream>>>(vis, ctx->d_aux.as<uint32_t>(), P);
     ctx->launches++;
     RAST_CUDA(ctx, cudaMemcpyAsync(tri_ids, ctx->d_aux.p, (size_t)P * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1000,8 +1049,8 @@ int rast_get_stats(rast_ctx *ctx, rast_stats *out) {
     const uint32_t P = ctx->last_view.band_pixels;
     rk::Batch bt{};
     bt.frames = ctx->d_frames.as<rk::FrameParams>() + (ctx->last_frames_offset - ctx->last_slot_frame);
-    bt.rv = ctx->d_rv.as<float4>();
-    rk::k_count_visible<<<148 * 4, 256, 0, ctx->stream>>>(ctx->d_vis.as<unsigned long long>() + (size_t)ctx->last_slot_frame * P, P, cnt);
+    bt.rv = ctx->d_rv[ctx->last_ps].as<float4>();
+    rk::k_count_visible<<<148 * 4, 256, 0, ctx->stream>>>(ctx->d_vis[ctx->last_ps].as<unsigned long long>() + (size_t)ctx->last_slot_frame * P, P, cnt);
     rk::k_count_front<<<148 * 4, 256, 0, ctx->stream>>>(ctx->scene, bt, ctx->last_slot_frame, cnt + 1);
     ctx->launches += 2;
     unsigned long long host[2] = {0, 0};
