@@ -147,7 +147,13 @@ struct rast_ctx {
     uint32_t band_y0 = 0, band_y1 = 0; // 0,0 = whole frame
 
     // per-call / per-batch buffers
-    DeviceBuffer d_frames, d_lights, d_queue, d_counters, d_aux, d_tiles, d_list, d_items;
+    DeviceBuffer d_queue, d_counters, d_aux, d_tiles, d_list, d_items;
+    // per-call parameter blocks, alternating between calls (cs = call slot): the front passes of call k+1 -- parameter upload
+    // included -- may run while the shade pass of call k still reads its own block
+    DeviceBuffer d_frames[2], d_lights[2];
+    cudaEvent_t ev_call_done[2] = {nullptr, nullptr};
+    bool call_done_pending[2] = {false, false};
+    int cs = 0, next_ps = 0;
     // What the shade pass of batch b reads while vertex / setup / raster of batch b+1 write it exists twice (pipeline slot =
     // batch parity): the front passes of the next batch run on a high-priority stream of their own while the shade pass of
     // this batch runs on the context's stream -- both are issue-bound at 66-76 % and fill each other's gaps (two contexts
@@ -256,7 +262,7 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
                  uint32_t *bbox_dev, int ps, bool two_streams, cudaStream_t *done_stream) {
     rk::Batch bt;
     bt.bbox = bbox_dev;
-    bt.frames = ctx->d_frames.as<rk::FrameParams>() + first;
+    bt.frames = ctx->d_frames[ctx->cs].as<rk::FrameParams>() + first;
     bt.n_frames = count;
     bt.rv = ctx->d_rv[ps].as<float4>();
     bt.cn = ctx->pre_normals ? ctx->d_cn[ps].as<float4>() : nullptr;
@@ -333,6 +339,9 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
         n_tile_launches += 1;
     }
     if (prof) cudaEventRecord(ctx->ev_pass[4], st);
+    // queue statistics of the call's last batch travel back from here (overflow => the queue grows before the next call): the
+    // next call's front passes reset the counters and may start before this call's shade pass has finished
+    if (keep_frame < count) RAST_CUDA(ctx, cudaMemcpyAsync(ctx->h_status.p, ctx->d_counters.p, 64, cudaMemcpyDeviceToHost, st));
     if (two_streams) { // the shade pass runs on the context's stream, after this batch's raster pass
         RAST_CUDA(ctx, cudaEventRecord(ctx->ev_raster[ps], st));
         st = ctx->stream;
@@ -345,7 +354,7 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
         // (8K overdraw frame on 8 GPUs: 1.13 -> 1.05 ms)
         const bool want_vec = ctx->shade_px == 4 || vw.out_plane != vw.band_pixels;
         const bool vec = !ctx->flat_face && want_vec && (vw.W % 4u == 0u) && (((uintptr_t)rgb_dev & 15u) == 0u) && (((uintptr_t)depth_dev & 15u) == 0u);
-        const rk::LightDev *lights = ctx->d_lights.as<rk::LightDev>();
+        const rk::LightDev *lights = ctx->d_lights[ctx->cs].as<rk::LightDev>();
         const uint32_t rows = vw.y1 - vw.y0;
         const dim3 grid(grid_for(vw.W, rk::SHADE_THREADS * rk::shade_groups(vec ? 4 : 1) * (vec ? 4 : 1)), rows, count);
         const rk::LightTable &lt = ctx->light_table;
@@ -547,11 +556,14 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
     }
 
     // buffers
-    RAST_CUDA(ctx, ctx->d_frames.reserve((size_t)n * sizeof(rk::FrameParams)));
-    RAST_CUDA(ctx, ctx->d_lights.reserve((ctx->lights.size() + 1) * sizeof(rk::LightDev)));
-    const uint32_t n_batches = (n + nb - 1) / nb;
-    const bool two_streams = ctx->overlap && !ctx->profiling && n_batches > 1; // a single batch has nothing to overlap with
-    for (int ps = 0; ps < (n_batches > 1 ? 2 : 1); ++ps) {
+    ctx->cs ^= 1;
+    RAST_CUDA(ctx, ctx->d_frames[ctx->cs].reserve((size_t)n * sizeof(rk::FrameParams)));
+    RAST_CUDA(ctx, ctx->d_lights[ctx->cs].reserve((ctx->lights.size() + 1) * sizeof(rk::LightDev)));
+    // The front passes (parameter upload, clear, vertex, setup, raster) go to the high-priority front stream and the shade pass
+    // stays on the context's stream: inside a call batch b+1's front passes overlap batch b's shade pass, and across calls
+    // the next call's front passes overlap this call's shade pass (they depend on nothing the context's stream produces).
+    const bool two_streams = ctx->overlap && !ctx->profiling;
+    for (int ps = 0; ps < 2; ++ps) {
         RAST_CUDA(ctx, ctx->d_rv[ps].reserve((size_t)nb * ctx->scene.V * sizeof(float4)));
         if ((size_t)ctx->scene.Nn * 8 <= P) RAST_CUDA(ctx, ctx->d_cn[ps].reserve((size_t)nb * ctx->scene.Nn * sizeof(float4)));
         if ((size_t)nb * P * 8 > ctx->d_vis[ps].bytes) { ctx->vis_clean_slots[ps] = 0; ctx->vis_dirty_slot[ps] = -1; }
@@ -592,17 +604,21 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
         }
         ctx->light_table.n = (uint32_t)ctx->lights.size();
     }
-    RAST_CUDA(ctx, cudaMemcpyAsync(ctx->d_frames.p, hp, (size_t)n * sizeof(rk::FrameParams), cudaMemcpyHostToDevice, ctx->stream));
+    cudaStream_t up = two_streams ? ctx->front_stream : ctx->stream;
+    if (ctx->call_done_pending[ctx->cs]) { // the call that last used this parameter block (two calls ago) must have finished shading
+        RAST_CUDA(ctx, cudaStreamWaitEvent(up, ctx->ev_call_done[ctx->cs], 0));
+        ctx->call_done_pending[ctx->cs] = false;
+    }
+    RAST_CUDA(ctx, cudaMemcpyAsync(ctx->d_frames[ctx->cs].p, hp, (size_t)n * sizeof(rk::FrameParams), cudaMemcpyHostToDevice, up));
     if (!ctx->lights.empty())
-        RAST_CUDA(ctx, cudaMemcpyAsync(ctx->d_lights.p, ctx->h_lights.p, ctx->lights.size() * sizeof(rk::LightDev), cudaMemcpyHostToDevice, ctx->stream));
-    RAST_CUDA(ctx, cudaEventRecord(ctx->ev_params, ctx->stream));
-    if (two_streams) RAST_CUDA(ctx, cudaStreamWaitEvent(ctx->front_stream, ctx->ev_params, 0)); // also orders it behind everything earlier on the context's stream
+        RAST_CUDA(ctx, cudaMemcpyAsync(ctx->d_lights[ctx->cs].p, ctx->h_lights.p, ctx->lights.size() * sizeof(rk::LightDev), cudaMemcpyHostToDevice, up));
+    RAST_CUDA(ctx, cudaEventRecord(ctx->ev_params, up));
 
     if (ctx->profiling) memset(ctx->pass_ms, 0, sizeof ctx->pass_ms);
 
-    int slot = 0, ps = 0;
+    int slot = 0, ps = ctx->next_ps;
     PendingBatch pending;
-    for (uint32_t first = 0; first < n; first += nb, ps ^= (n_batches > 1 ? 1 : 0)) {
+    for (uint32_t first = 0; first < n; first += nb, ps ^= 1) {
         const uint32_t count = (n - first) < nb ? (n - first) : nb;
         // outputs: the caller's device buffers, or the context's own (double-buffered when a D2H copy follows)
         uint8_t *rgb_dst;
@@ -653,9 +669,9 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
         }
     }
     if (pending.valid) { int rc = finish_batch(ctx, pending, vw, frames, depths); if (rc != RAST_OK) return rc; }
-    ctx->shade_pending[0] = ctx->shade_pending[1] = false; // the next call's front passes start behind its parameter upload, which is behind these shade passes
-    // queue statistics of the last batch travel back asynchronously (overflow => grow next time)
-    RAST_CUDA(ctx, cudaMemcpyAsync(ctx->h_status.p, ctx->d_counters.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->next_ps = ps;
+    RAST_CUDA(ctx, cudaEventRecord(ctx->ev_call_done[ctx->cs], ctx->stream));
+    ctx->call_done_pending[ctx->cs] = true;
     if (!device_ptrs) {
         RAST_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
         RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -698,6 +714,7 @@ int rast_create(int device, rast_ctx **out) {
         ok = ok && cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&ctx->ev_raster[i], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&ctx->ev_shade[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_call_done[i], cudaEventDisableTiming) == cudaSuccess;
     }
     for (int i = 0; i <= RAST_PASS_COUNT && ok; ++i) ok = ok && cudaEventCreate(&ctx->ev_pass[i]) == cudaSuccess;
     ok = ok && ctx->h_status.reserve(64) == cudaSuccess;
@@ -735,7 +752,7 @@ void rast_destroy(rast_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->front_stream) cudaStreamSynchronize(ctx->front_stream);
-    DeviceBuffer *dev[] = {&ctx->d_pos, &ctx->d_nrm, &ctx->d_uv, &ctx->d_vidx, &ctx->d_attr, &ctx->d_mats, &ctx->d_texels, &ctx->d_frames, &ctx->d_lights,
+    DeviceBuffer *dev[] = {&ctx->d_pos, &ctx->d_nrm, &ctx->d_uv, &ctx->d_vidx, &ctx->d_attr, &ctx->d_mats, &ctx->d_texels, &ctx->d_frames[0], &ctx->d_frames[1], &ctx->d_lights[0], &ctx->d_lights[1],
                            &ctx->d_rv[0], &ctx->d_rv[1], &ctx->d_cn[0], &ctx->d_cn[1], &ctx->d_tiles, &ctx->d_list, &ctx->d_items, &ctx->d_vis[0], &ctx->d_vis[1], &ctx->d_bbox[0], &ctx->d_bbox[1], &ctx->d_queue, &ctx->d_counters, &ctx->d_aux, &ctx->d_rgb[0], &ctx->d_rgb[1], &ctx->d_depth[0], &ctx->d_depth[1]};
     for (DeviceBuffer *b : dev) b->release();
     ctx->h_frames.release();
@@ -749,6 +766,7 @@ void rast_destroy(rast_ctx *ctx) {
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
         if (ctx->ev_raster[i]) cudaEventDestroy(ctx->ev_raster[i]);
         if (ctx->ev_shade[i]) cudaEventDestroy(ctx->ev_shade[i]);
+        if (ctx->ev_call_done[i]) cudaEventDestroy(ctx->ev_call_done[i]);
     }
     for (int i = 0; i <= RAST_PASS_COUNT; ++i)
         if (ctx->ev_pass[i]) cudaEventDestroy(ctx->ev_pass[i]);
@@ -1048,7 +1066,7 @@ int rast_get_stats(rast_ctx *ctx, rast_stats *out) {
     RAST_CUDA(ctx, cudaMemsetAsync(cnt, 0, 16, ctx->stream));
     const uint32_t P = ctx->last_view.band_pixels;
     rk::Batch bt{};
-    bt.frames = ctx->d_frames.as<rk::FrameParams>() + (ctx->last_frames_offset - ctx->last_slot_frame);
+    bt.frames = ctx->d_frames[ctx->cs].as<rk::FrameParams>() + (ctx->last_frames_offset - ctx->last_slot_frame);
     bt.rv = ctx->d_rv[ctx->last_ps].as<float4>();
     rk::k_count_visible<<<148 * 4, 256, 0, ctx->stream>>>(ctx->d_vis[ctx->last_ps].as<unsigned long long>() + (size_t)ctx->last_slot_frame * P, P, cnt);
     rk::k_count_front<<<148 * 4, 256, 0, ctx->stream>>>(ctx->scene, bt, ctx->last_slot_frame, cnt + 1);
