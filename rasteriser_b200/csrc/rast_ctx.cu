@@ -338,10 +338,10 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
         rk::k_raster_tiles<<<dim3(tb.tiles_x * tb.tiles_y, count), rk::RASTER_WARPS * 32, 0, st>>>(sc, vw, bt, tb);
         n_tile_launches += 1;
     }
-    if (prof) cudaEventRecord(ctx->ev_pass[4], st);
     // queue statistics of the call's last batch travel back from here (overflow => the queue grows before the next call): the
     // next call's front passes reset the counters and may start before this call's shade pass has finished
     if (keep_frame < count) RAST_CUDA(ctx, cudaMemcpyAsync(ctx->h_status.p, ctx->d_counters.p, 64, cudaMemcpyDeviceToHost, st));
+    if (prof) cudaEventRecord(ctx->ev_pass[4], st);
     if (two_streams) { // the shade pass runs on the context's stream, after this batch's raster pass
         RAST_CUDA(ctx, cudaEventRecord(ctx->ev_raster[ps], st));
         st = ctx->stream;
