@@ -14,16 +14,6 @@
 
 #include "exact.cuh"
 
-#ifndef RAST_SHADE_OPAQUE_TEX
-#define RAST_SHADE_OPAQUE_TEX 1
-#endif
-#ifndef RAST_SHADE_LIGHT_SWITCH
-#define RAST_SHADE_LIGHT_SWITCH 1
-#endif
-#ifndef RAST_SHADE_TEX_FIRST
-#define RAST_SHADE_TEX_FIRST 1 // texel loads before the normal's division / square root: 8.20 -> 8.14 ms per 720 frames (1080p spin)
-#endif
-
 namespace rk {
 
 constexpr unsigned long long VIS_EMPTY = ~0ull;
@@ -219,52 +209,6 @@ __device__ __forceinline__ void test_and_commit(const TriSetup &s, uint32_t x, u
     atomicMin(vis_row0 + (size_t)(y - vw.y0) * vw.W + x, key);
 }
 
-// The pixel loops of draw_triangle (drawing.cpp:190-201) over a small bbox, walked by ONE thread as 2x2 quads:
-// the differences (p - a) and the products of edge() are shared between the four pixels (36 operations per
-// quad instead of 60), each edge value is still mul(d, py - yk) - mul(d', px - xk) evaluated from scratch, so
-// the bits are those of edges().  The quads are visited in one flat loop so that the lanes of a warp -- each
-// with its own bbox -- stay in lockstep for min(count) iterations instead of diverging at every row end.
-__device__ __forceinline__ void raster_bbox_quads(const TriSetup &s, const BBox &bb, uint32_t tri, unsigned long long *vis_row0, const View &vw) {
-    using namespace exact;
-    uint32_t x = bb.x0, y = bb.y0;
-    for (;;) {
-        const float pxa = (float)x, pxb = (float)(x + 1u), pya = (float)y, pyb = (float)(y + 1u);
-        const float a0a = mul(s.d12x, sub(pya, s.y1)), a0b = mul(s.d12x, sub(pyb, s.y1));
-        const float a1a = mul(s.d20x, sub(pya, s.y2)), a1b = mul(s.d20x, sub(pyb, s.y2));
-        const float a2a = mul(s.d01x, sub(pya, s.y0)), a2b = mul(s.d01x, sub(pyb, s.y0));
-        const float c0a = mul(s.d12y, sub(pxa, s.x1)), c0b = mul(s.d12y, sub(pxb, s.x1));
-        const float c1a = mul(s.d20y, sub(pxa, s.x2)), c1b = mul(s.d20y, sub(pxb, s.x2));
-        const float c2a = mul(s.d01y, sub(pxa, s.x0)), c2b = mul(s.d01y, sub(pxb, s.x0));
-        // (xa,ya) (xb,ya) (xa,yb) (xb,yb)
-        const float m0 = fminf(fminf(sub(a0a, c0a), sub(a1a, c1a)), sub(a2a, c2a));
-        const float m1 = fminf(fminf(sub(a0a, c0b), sub(a1a, c1b)), sub(a2a, c2b));
-        const float m2 = fminf(fminf(sub(a0b, c0a), sub(a1b, c1a)), sub(a2b, c2a));
-        const float m3 = fminf(fminf(sub(a0b, c0b), sub(a1b, c1b)), sub(a2b, c2b));
-        const bool xb_in = x + 1u <= bb.x1, yb_in = y + 1u <= bb.y1;
-        uint32_t mask = (s.literal || m0 >= -EDGE_SLACK) ? 1u : 0u; // candidate()
-        if (xb_in && (s.literal || m1 >= -EDGE_SLACK)) mask |= 2u;
-        if (yb_in && (s.literal || m2 >= -EDGE_SLACK)) mask |= 4u;
-        if (xb_in && yb_in && (s.literal || m3 >= -EDGE_SLACK)) mask |= 8u;
-        while (mask) { // survivors: the literal divisions and the strict depth test
-            const uint32_t k = __ffs(mask) - 1u;
-            mask &= mask - 1u;
-            const float aa0 = (k & 2u) ? a0b : a0a, aa1 = (k & 2u) ? a1b : a1a, aa2 = (k & 2u) ? a2b : a2a;
-            const float cc0 = (k & 1u) ? c0b : c0a, cc1 = (k & 1u) ? c1b : c1a, cc2 = (k & 1u) ? c2b : c2a;
-            float b0, b1, b2, z;
-            if (fragment(s, sub(aa0, cc0), sub(aa1, cc1), sub(aa2, cc2), b0, b1, b2, z)) {
-                const unsigned long long key = ((unsigned long long)depth_key(z) << 32) | tri;
-                atomicMin(vis_row0 + (size_t)(y + (k >> 1) - vw.y0) * vw.W + x + (k & 1u), key);
-            }
-        }
-        x += 2u;
-        if (x > bb.x1) {
-            x = bb.x0;
-            y += 2u;
-            if (y > bb.y1) break;
-        }
-    }
-}
-
 // ---- K0: clear ------------------------------------------------------------------------------
 // renderer.cpp:85-86 / :107-108 (frame = 0, depth = 1.0f) become "no triangle" in the visibility buffer.
 // Only needed for slots that are not known to be empty: the shade pass hands every key it consumes
@@ -319,11 +263,6 @@ constexpr int SETUP_TRIS = RAST_SETUP_TRIS; // triangles per thread: all index a
                                             //  4 -> 0.225 / 1.011, 8 -> 0.323 / 1.422; inlined body: 1 -> 0.154 / 0.706, 2 -> 0.175 / 0.817.  Once the queue
                                             //  reservation is one atomic per warp, more triangles per thread only cost registers.)
 
-#ifndef RAST_SETUP_QUADS
-#define RAST_SETUP_QUADS 0 // 1: small bboxes are walked as 2x2 quads (raster_bbox_quads).  Measured slower on B200 (k_setup, 8 M / 50 M
-                           // triangles: 0.173 / 0.844 ms vs 0.156 / 0.710 ms pixel by pixel): sub-pixel triangles have 2-3 pixel wide bboxes,
-                           // so quads test 28 % more pixels and the kernel is latency-bound on the index -> vertex gathers, not on the loop
-#endif
 #ifndef RAST_SETUP_INLINE
 #define RAST_SETUP_INLINE __forceinline__
 #endif
@@ -381,12 +320,10 @@ __device__ RAST_SETUP_INLINE void setup_triangle(uint32_t t, uint32_t f, float4 
     if (inline_raster) {
         TriSetup s;
         tri_setup(s, v0, v1, v2);
-#if RAST_SETUP_QUADS
-        raster_bbox_quads(s, bb, t, vis, vw);
-#else
+        // (walking the bbox as 2x2 quads with shared differences in one flat loop measured slower: 0.173 / 0.844 ms against
+        //  0.156 / 0.710 ms on 8 M / 50 M triangles -- sub-pixel triangles have 2-3 pixel wide bboxes, quads test 28 % more pixels)
         for (uint32_t y = bb.y0; y <= bb.y1; ++y)
             for (uint32_t x = bb.x0; x <= bb.x1; ++x) test_and_commit(s, x, y, t, vis, vw);
-#endif
     }
 }
 
@@ -822,10 +759,9 @@ __device__ __forceinline__ Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t
     const float i0 = mul(v0.w, b0), i1 = mul(v1.w, b1), i2 = mul(v2.w, b2);
     const float d = div(1.f, add(add(i0, i1), i2));
 
-#if RAST_SHADE_TEX_FIRST
-    // the texel loads are issued before the normal is interpolated and normalised (a division and a square root,
-    // ~80 instructions) so that their latency is covered by this warp's own arithmetic
-    // Material::sample (material.cpp:11-26)
+    // Material::sample (material.cpp:11-26).  The texel loads are issued before the normal is interpolated and normalised (a
+    // division and a square root, ~80 instructions) so that their latency is covered by this warp's own arithmetic
+    // (8.20 -> 8.14 ms per 720 frames on the 1080p spin).
     float ar = mk.x, ag = mk.y, ab = mk.z;
     if (__float_as_int(mk.w) != 0) {
         const float2 uv0 = __ldg(sc.uv + r1.z), uv1 = __ldg(sc.uv + r1.w), uv2 = __ldg(sc.uv + r2.x);
@@ -833,9 +769,7 @@ __device__ __forceinline__ Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t
         const float v = mul(d, add(add(mul(i0, uv0.y), mul(i1, uv1.y)), mul(i2, uv2.y)));
         const long long toff = ((long long)(uint32_t)mt.z) | ((long long)mt.w << 32);
         unsigned long long tex_base = (unsigned long long)(sc.texels + toff);
-#if RAST_SHADE_OPAQUE_TEX
         asm volatile("" : "+l"(tex_base)); // opaque base: each corner becomes one IMAD.WIDE instead of a 64-bit add + LEA pair
-#endif
         sample_texture(reinterpret_cast<const float4 *>(tex_base), mt.x, mt.y, mul(u, (float)mt.x), mul(sub(1.f, v), (float)mt.y), ar, ag, ab);
     }
 
@@ -847,30 +781,6 @@ __device__ __forceinline__ Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t
     float nx = mul(mx, inv), ny = mul(my, inv), nz = mul(mz, inv);
     if (wind_clockwise) { nx = -nx; ny = -ny; nz = -nz; }
 
-#else
-    // perspective_interpolate + normalize (drawing.cpp:64-75,131-132)
-    const float mx = FLAT ? fx : mul(d, add(add(mul(i0, n0.x), mul(i1, n1.x)), mul(i2, n2.x)));
-    const float my = FLAT ? fy : mul(d, add(add(mul(i0, n0.y), mul(i1, n1.y)), mul(i2, n2.y)));
-    const float mz = FLAT ? fz : mul(d, add(add(mul(i0, n0.z), mul(i1, n1.z)), mul(i2, n2.z)));
-    const float inv = div(1.f, fsqrt(add(add(mul(mx, mx), mul(my, my)), mul(mz, mz))));
-    float nx = mul(mx, inv), ny = mul(my, inv), nz = mul(mz, inv);
-    if (wind_clockwise) { nx = -nx; ny = -ny; nz = -nz; }
-
-    // Material::sample (material.cpp:11-26)
-    float ar = mk.x, ag = mk.y, ab = mk.z;
-    if (__float_as_int(mk.w) != 0) {
-        const float2 uv0 = __ldg(sc.uv + r1.z), uv1 = __ldg(sc.uv + r1.w), uv2 = __ldg(sc.uv + r2.x);
-        const float u = mul(d, add(add(mul(i0, uv0.x), mul(i1, uv1.x)), mul(i2, uv2.x))); // drawing.cpp:135
-        const float v = mul(d, add(add(mul(i0, uv0.y), mul(i1, uv1.y)), mul(i2, uv2.y)));
-        const long long toff = ((long long)(uint32_t)mt.z) | ((long long)mt.w << 32);
-        unsigned long long tex_base = (unsigned long long)(sc.texels + toff);
-#if RAST_SHADE_OPAQUE_TEX
-        asm volatile("" : "+l"(tex_base)); // opaque base: each corner becomes one IMAD.WIDE instead of a 64-bit add + LEA pair
-#endif
-        sample_texture(reinterpret_cast<const float4 *>(tex_base), mt.x, mt.y, mul(u, (float)mt.x), mul(sub(1.f, v), (float)mt.y), ar, ag, ab);
-    }
-
-#endif
     // shade / light_contribution (shading.cpp:20-34)
     float sr = 0.f, sg = 0.f, sb = 0.f;
     const uint32_t n_p = lt.n < PARAM_LIGHTS ? lt.n : PARAM_LIGHTS;
@@ -882,7 +792,6 @@ __device__ __forceinline__ Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t
         sg = add(sg, mul(mul(mul(c.x, ag), k), 0.318309886183790671537767526745028724f));
         sb = add(sb, mul(mul(mul(c.y, ab), k), 0.318309886183790671537767526745028724f));
     };
-#if RAST_SHADE_LIGHT_SWITCH
     // the light count is uniform over the launch: the common small counts run straight-line code with the
     // light constants at immediate constant-bank offsets (same lights, same order, same operations)
     if (n_p == 3u) {
@@ -900,10 +809,6 @@ __device__ __forceinline__ Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t
 #pragma unroll 1
         for (; l < n_p; ++l) one_light(l);
     }
-#else
-#pragma unroll 1
-    for (uint32_t l = 0; l < n_p; ++l) one_light(l);
-#endif
 #pragma unroll 1
     for (uint32_t l = n_p; l < lt.n; ++l) { // beyond the parameter table: straight from global memory
         const LightDev L = lights[l];
