@@ -451,7 +451,9 @@ def main():
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms, "frames_per_launch": frames_per_launch,
                 "pass_ms_per_step": {k: v / prof_steps for k, v in pass_ms.items()},
-                "limiter": issue, "whole_frame_algorithmic_bytes": total_alg, "whole_frame_achieved_GBs": total_alg * n * world * opts.steps / (ms_total * 1e-3) / 1e9}
+                "limiter": issue, "whole_frame_algorithmic_bytes": total_alg, "whole_frame_achieved_GBs": total_alg * n * world * opts.steps / (ms_total * 1e-3) / 1e9,
+                # all passes of a frame against the HBM roofline (SURVEY.md 8d frame total B / t_frame, per GPU): the passes overlap on two streams
+                "whole_frame_frac": total_alg * n * opts.steps / (ms_total * 1e-3) / 1e9 / peak}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     cpu = None
