@@ -95,7 +95,11 @@ const char *rast_version(void);
 /* Launch on this cudaStream_t (passed as void*; NULL is the legacy default stream) instead of the
  * context's own non-blocking stream.  Lets a host that owns streams (e.g.
  * torch.cuda.current_stream().cuda_stream) time and order the kernels itself.
- * rast_use_own_stream switches back. */
+ * rast_use_own_stream switches back.
+ * The passes that come before shading (parameter upload, vertex, setup, raster) run on an internal high-priority
+ * stream so that they overlap the previous batch's / call's shade pass; the shade pass, the only one that writes the
+ * caller's buffers, runs on this stream behind an event, so everything the caller observes is ordered on this stream.
+ * RAST_OVERLAP=0 in the environment keeps every pass on this stream. */
 int rast_set_stream(rast_ctx *ctx, void *cuda_stream);
 int rast_use_own_stream(rast_ctx *ctx);
 
