@@ -85,11 +85,12 @@ def spin_args(api, wl, rank, world, flat=True):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons, sampled every 50 ms by a process started before the warm-up; the samples that
+    arrive between the two mark() calls around the timed region are the ones reported."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.marks = index, None, [], []
 
     def start(self):
         try:
@@ -102,7 +103,11 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line)
+            self.lines.append((time.perf_counter(), line))
+
+    def mark(self):
+        """Call at the start and at the end of the timed region: samples are attributed by their arrival time."""
+        self.marks.append(time.perf_counter())
 
     def stop(self):
         if not self.proc:
@@ -114,7 +119,12 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for line in self.lines:
+        lines = self.lines
+        if len(self.marks) >= 2:  # samples that arrived inside the timed region (one sampling period of slack after it);
+            t0, t1 = self.marks[0], self.marks[-1] + 0.06  # a region shorter than the period falls back to the nearest sample
+            inside = [x for x in lines if t0 <= x[0] <= t1]
+            lines = inside or sorted(lines, key=lambda x: min(abs(x[0] - t0), abs(x[0] - t1)))[:1]
+        for _, line in lines:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
@@ -240,7 +250,7 @@ def algorithmic_bytes(wl, visible_tris, P):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="spin1080p")
@@ -321,21 +331,23 @@ def main():
                 multi.gather_frames(frames_dev[c:c + 120], min(120, n - c) * world)
 
     # ---- value: device-resident ----
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()  # before the warm-up, so that it is sampling by the time the timed region starts
     for _ in range(max(3, opts.warmup)):
         step_device()
         r.sync()  # lets the library see the previous call's queue statistics (it grows its work queue lazily)
     barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     launches0 = r.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    clocks.mark()
     e0.record(stream)
     for _ in range(opts.steps):
         step_device()
     e1.record(stream)
     barrier()
+    clocks.mark()
     ms = e0.elapsed_time(e1)
     launches = r.launch_count() - launches0
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
