@@ -14,6 +14,15 @@
 
 #include "exact.cuh"
 
+// Variant switch (tools/build_variants.py): drop provably empty border columns / rows of small bboxes in k_setup
+// (tight_bbox.h).  Off in the default build until it has been timed on a B200; parity is by proof, not by measurement.
+#ifndef RAST_TIGHT_TINY
+#define RAST_TIGHT_TINY 0
+#endif
+#if RAST_TIGHT_TINY
+#include "tight_bbox.h"
+#endif
+
 namespace rk {
 
 constexpr unsigned long long VIS_EMPTY = ~0ull;
@@ -322,8 +331,15 @@ __device__ RAST_SETUP_INLINE void setup_triangle(uint32_t t, uint32_t f, float4 
         tri_setup(s, v0, v1, v2);
         // (walking the bbox as 2x2 quads with shared differences in one flat loop measured slower: 0.173 / 0.844 ms against
         //  0.156 / 0.710 ms on 8 M / 50 M triangles -- sub-pixel triangles have 2-3 pixel wide bboxes, quads test 28 % more pixels)
-        for (uint32_t y = bb.y0; y <= bb.y1; ++y)
-            for (uint32_t x = bb.x0; x <= bb.x1; ++x) test_and_commit(s, x, y, t, vis, vw);
+        uint32_t wx0 = bb.x0, wy0 = bb.y0, wx1 = bb.x1, wy1 = bb.y1;
+#if RAST_TIGHT_TINY
+        // border columns / rows of the bbox that lie outside the triangle's extent by more than the rounding error of the
+        // reference's own test can hold no candidate pixel (tight_bbox.h: proof + CPU brute-force check); a sub-pixel
+        // triangle between sample points is dropped here without a single pixel test
+        if (!rast_tight_bbox(v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, s.literal ? 0.f : s.area, &wx0, &wy0, &wx1, &wy1)) return;
+#endif
+        for (uint32_t y = wy0; y <= wy1; ++y)
+            for (uint32_t x = wx0; x <= wx1; ++x) test_and_commit(s, x, y, t, vis, vw);
     }
 }
 

@@ -6,7 +6,7 @@ import re
 import subprocess
 import sys
 
-so = "rasteriser_b200/librast_b200.so"
+so = __import__("os").environ.get("RAST_LIB") or "rasteriser_b200/librast_b200.so"
 pat = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else ""
 txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 name, funcs = None, collections.OrderedDict()
