@@ -18,7 +18,7 @@ HOST_LIB = os.path.join(PKG, "librast_host.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false",  # the reference's fp32 ops are never fused
-              "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall"]
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-Wno-unknown-pragmas"]  # (#pragma unroll reaches the host pass through the __host__ __device__ functions)
 
 
 def _nvcc():

@@ -23,6 +23,18 @@
 #include "tight_bbox.h"
 #endif
 
+// Device-only primitives used inside the RAST_HD functions, with single-lane host stand-ins for tests/emu_device_fns.cu
+// (a host "warp" is one lane at a time: a vote is the lane's own predicate, an atomic min a plain min).
+#ifdef __CUDA_ARCH__
+#define RAST_ANY(p) __any_sync(0xFFFFFFFFu, (p))
+#define RAST_ATOMIC_MIN64(ptr, v) atomicMin((ptr), (v))
+#define RAST_LDCG32(ptr) __ldcg(ptr)
+#else
+#define RAST_ANY(p) (p)
+#define RAST_ATOMIC_MIN64(ptr, v) do { unsigned long long *p__ = (ptr); const unsigned long long v__ = (v); if (v__ < *p__) *p__ = v__; } while (0)
+#define RAST_LDCG32(ptr) (*(ptr))
+#endif
+
 namespace rk {
 
 constexpr unsigned long long VIS_EMPTY = ~0ull;
@@ -114,8 +126,8 @@ enum { CNT_QUEUE = 0, CNT_CURSOR = 1, CNT_QUEUE_OVERFLOW = 2, CNT_BBOX_AREA = 3,
 // ---- visibility key ------------------------------------------------------------------------
 // Order-preserving map of a finite float below 1.0 to u32.  -0 is canonicalised so that it ties
 // with +0 (the reference's strict '<' treats them as equal, drawing.cpp:119).
-__device__ __forceinline__ uint32_t depth_key(float z) {
-    uint32_t b = __float_as_uint(z);
+RAST_HD uint32_t depth_key(float z) {
+    uint32_t b = exact::f2u(z);
     if (z == 0.f) b = 0u;
     return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
 }
@@ -134,7 +146,7 @@ struct TriSetup {
 // The six differences and the area are multiplied by sign(area).  Negation is exact and every IEEE
 // operation is sign-symmetric, so each edge value becomes exactly sign(area) * e_k and each quotient
 // e_k / area keeps its bits; what changes is that "inside" now simply reads e_k >= 0.
-__device__ __forceinline__ void tri_setup(TriSetup &s, const float4 &v0, const float4 &v1, const float4 &v2) {
+RAST_HD void tri_setup(TriSetup &s, const float4 &v0, const float4 &v1, const float4 &v2) {
     s.x0 = v0.x; s.y0 = v0.y; s.z0 = v0.z;
     s.x1 = v1.x; s.y1 = v1.y; s.z1 = v1.z;
     s.x2 = v2.x; s.y2 = v2.y; s.z2 = v2.z;
@@ -142,7 +154,7 @@ __device__ __forceinline__ void tri_setup(TriSetup &s, const float4 &v0, const f
     s.d20x = exact::sub(v0.x, v2.x); s.d20y = exact::sub(v0.y, v2.y);
     s.d01x = exact::sub(v1.x, v0.x); s.d01y = exact::sub(v1.y, v0.y);
     s.area = exact::sub(exact::mul(s.d01x, exact::sub(v2.y, v0.y)), exact::mul(s.d01y, exact::sub(v2.x, v0.x)));
-    s.literal = !(fabsf(s.area) > 0.f && fabsf(s.area) < __int_as_float(0x7f800000));
+    s.literal = !(fabsf(s.area) > 0.f && fabsf(s.area) < exact::i2f(0x7f800000));
     if (!s.literal && s.area < 0.f) {
         s.d12x = -s.d12x; s.d12y = -s.d12y; s.d20x = -s.d20x; s.d20y = -s.d20y; s.d01x = -s.d01x; s.d01y = -s.d01y;
         s.area = -s.area;
@@ -152,7 +164,7 @@ __device__ __forceinline__ void tri_setup(TriSetup &s, const float4 &v0, const f
 }
 
 // signed_area_2d (geometry.cpp:76-83), left to right
-__device__ __forceinline__ float signed_area_2d(const float4 &v0, const float4 &v1, const float4 &v2) {
+RAST_HD float signed_area_2d(const float4 &v0, const float4 &v1, const float4 &v2) {
     float a = exact::sub(exact::mul(v0.x, v1.y), exact::mul(v1.x, v0.y));
     a = exact::add(a, exact::mul(v1.x, v2.y));
     a = exact::sub(a, exact::mul(v2.x, v1.y));
@@ -164,7 +176,7 @@ __device__ __forceinline__ float signed_area_2d(const float4 &v0, const float4 &
 struct BBox { uint32_t x0, y0, x1, y1; bool empty; };
 
 // bounding_box (drawing.cpp:77-93) intersected with the band [vy0, vy1)
-__device__ __forceinline__ BBox bounding_box(const float4 &v0, const float4 &v1, const float4 &v2, const View &vw) {
+RAST_HD BBox bounding_box(const float4 &v0, const float4 &v1, const float4 &v2, const View &vw) {
     using namespace exact;
     const float brx = (float)(vw.W - 1u), bry = (float)(vw.H - 1u);
     const float minx = glm_min(glm_min(v0.x, v1.x), v2.x), miny = glm_min(glm_min(v0.y, v1.y), v2.y);
@@ -182,7 +194,7 @@ __device__ __forceinline__ BBox bounding_box(const float4 &v0, const float4 &v1,
 
 // The three edge functions of one pixel, each a fresh evaluation in the reference's order
 // (drawing.cpp:36-39); incremental stepping would round differently.
-__device__ __forceinline__ void edges(const TriSetup &s, float px, float py, float &e0, float &e1, float &e2) {
+RAST_HD void edges(const TriSetup &s, float px, float py, float &e0, float &e1, float &e2) {
     using namespace exact;
     e0 = sub(mul(s.d12x, sub(py, s.y1)), mul(s.d12y, sub(px, s.x1)));
     e1 = sub(mul(s.d20x, sub(py, s.y2)), mul(s.d20y, sub(px, s.x2)));
@@ -195,13 +207,13 @@ __device__ __forceinline__ void edges(const TriSetup &s, float px, float py, flo
 // sign folding that is "e_k >= -2^-22 for all k": it never rejects a pixel the exact test accepts
 // (fminf drops a NaN operand, which only widens the superset); survivors take the literal divisions,
 // which the depth needs anyway.
-__device__ __forceinline__ bool candidate(const TriSetup &s, float e0, float e1, float e2) {
+RAST_HD bool candidate(const TriSetup &s, float e0, float e1, float e2) {
     return s.literal || fminf(fminf(e0, e1), e2) >= -EDGE_SLACK;
 }
 
 // barycentric + inside + depth (drawing.cpp:41-49,111,115-119).  True iff the fragment is inside
 // and nearer than the cleared depth 1.0f (a fragment at z >= 1 or NaN can never pass the strict '<').
-__device__ __forceinline__ bool fragment(const TriSetup &s, float e0, float e1, float e2, float &b0, float &b1, float &b2, float &z) {
+RAST_HD bool fragment(const TriSetup &s, float e0, float e1, float e2, float &b0, float &b1, float &b2, float &z) {
     using namespace exact;
     div3(e0, e1, e2, s.area, s.rcp1, s.div_ok, b0, b1, b2);
     if (!(b0 >= 0.f && b1 >= 0.f && b2 >= 0.f)) return false;
@@ -209,13 +221,13 @@ __device__ __forceinline__ bool fragment(const TriSetup &s, float e0, float e1, 
     return z < 1.0f;
 }
 
-__device__ __forceinline__ void test_and_commit(const TriSetup &s, uint32_t x, uint32_t y, uint32_t tri, unsigned long long *vis_row0, const View &vw) {
+RAST_HD void test_and_commit(const TriSetup &s, uint32_t x, uint32_t y, uint32_t tri, unsigned long long *vis_row0, const View &vw) {
     float e0, e1, e2, b0, b1, b2, z;
     edges(s, (float)x, (float)y, e0, e1, e2);
     if (!candidate(s, e0, e1, e2)) return;
     if (!fragment(s, e0, e1, e2, b0, b1, b2, z)) return;
     const unsigned long long key = ((unsigned long long)depth_key(z) << 32) | tri;
-    atomicMin(vis_row0 + (size_t)(y - vw.y0) * vw.W + x, key);
+    RAST_ATOMIC_MIN64(vis_row0 + (size_t)(y - vw.y0) * vw.W + x, key);
 }
 
 // ---- K0: clear ------------------------------------------------------------------------------
@@ -234,6 +246,18 @@ __global__ void k_clear(unsigned long long *vis, size_t n) {
 // ---- K1: vertex stage -----------------------------------------------------------------------
 // transform_point + z_divide + ndc_to_raster (geometry.cpp:44-74, drawing.cpp:241-247) fused: one
 // thread per vertex, 12 B in, one float4 out.
+RAST_HD float4 raster_vertex(const float *cam, float x, float y, float z, uint32_t W, uint32_t H) {
+    using namespace exact;
+    const float4 clip = mat_vec(cam, x, y, z, 1.f);
+    const float nx = div(clip.x, clip.w), ny = div(clip.y, clip.w), nz = div(clip.z, clip.w), nw = div(1.f, clip.w);
+    float4 r;
+    r.x = mul(mul(0.5f, add(nx, 1.0f)), (float)(int)W);   // remap_ndc(x, width)
+    r.y = mul(mul(0.5f, add(-ny, 1.0f)), (float)(int)H);  // remap_ndc(-y, height)
+    r.z = nz;
+    r.w = nw;
+    return r;
+}
+
 __global__ void __launch_bounds__(256) k_vertex(Scene sc, View vw, Batch bt) {
     __shared__ float cam[16], nm[16];
     const uint32_t f = blockIdx.y;
@@ -245,14 +269,7 @@ __global__ void __launch_bounds__(256) k_vertex(Scene sc, View vw, Batch bt) {
     using namespace exact;
     if (i < sc.V) {
         const float x = sc.pos[3 * (size_t)i], y = sc.pos[3 * (size_t)i + 1], z = sc.pos[3 * (size_t)i + 2];
-        const float4 clip = mat_vec(cam, x, y, z, 1.f);
-        const float nx = div(clip.x, clip.w), ny = div(clip.y, clip.w), nz = div(clip.z, clip.w), nw = div(1.f, clip.w);
-        float4 r;
-        r.x = mul(mul(0.5f, add(nx, 1.0f)), (float)(int)vw.W);   // remap_ndc(x, width)
-        r.y = mul(mul(0.5f, add(-ny, 1.0f)), (float)(int)vw.H);  // remap_ndc(-y, height)
-        r.z = nz;
-        r.w = nw;
-        bt.rv[(size_t)f * sc.V + i] = r;
+        bt.rv[(size_t)f * sc.V + i] = raster_vertex(cam, x, y, z, vw.W, vw.H);
     } else if (bt.cn != nullptr && i - sc.V < sc.Nn) {
         // transform_normals (geometry.cpp:97-108): transpose(inverse(modelview)) * (n, 0), xyz kept, not normalised
         const uint32_t j = i - sc.V;
@@ -395,7 +412,7 @@ constexpr unsigned long long EARLY_Z_OVERDRAW = 6;
 //   e(p) <= max_corners e(c) + 2*err   for every pixel p of the block,
 // and if that bound is below the candidate threshold -2^-22 no pixel of the block can be a candidate.
 // 8 ulp-units (2^-21) are used for 2*err = 6.02; NaN / inf make the comparison false (no rejection).
-__device__ __forceinline__ bool block_outside_edge(float dx, float dy, float xk, float yk, float xa, float xb, float ya, float yb) {
+RAST_HD bool block_outside_edge(float dx, float dy, float xk, float yk, float xa, float xb, float ya, float yb) {
     using namespace exact;
     const float ua = sub(ya, yk), ub = sub(yb, yk), va = sub(xa, xk), vb = sub(xb, xk);
     const float pa = mul(dx, ua), pb = mul(dx, ub), qa = mul(dy, va), qb = mul(dy, vb);
@@ -411,14 +428,14 @@ struct StagedTris {
 
 // Stage one item (this lane's) : triangle `tri` of frame `f`, to be rasterised inside the pixel rectangle
 // [rx0,rx1] x [ry0,ry1] (already intersected with its bbox) on the 4 x 2 block grid anchored at (ox, oy).
-__device__ __forceinline__ void stage_item(StagedTris &stg, uint32_t lane, uint32_t tri, uint32_t f, const float4 &v0, const float4 &v1, const float4 &v2,
+RAST_HD void stage_item(StagedTris &stg, uint32_t lane, uint32_t tri, uint32_t f, const float4 &v0, const float4 &v1, const float4 &v2,
                                            uint32_t rx0, uint32_t ry0, uint32_t rx1, uint32_t ry1, uint32_t ox, uint32_t oy) {
     TriSetup s = {};
     s.literal = true;
     if (tri != INVALID_TRI) tri_setup(s, v0, v1, v2);
     const float fl[16] = {s.x0, s.y0, s.x1, s.y1, s.x2, s.y2, s.z0, s.z1, s.z2, s.d12x, s.d12y, s.d20x, s.d20y, s.d01x, s.d01y, s.area};
 #pragma unroll
-    for (int k = 0; k < 16; ++k) stg.w[k][lane] = __float_as_uint(fl[k]);
+    for (int k = 0; k < 16; ++k) stg.w[k][lane] = exact::f2u(fl[k]);
     stg.w[16][lane] = s.literal ? 1u : 0u;
     stg.w[17][lane] = rx0 | (ry0 << 16);
     stg.w[18][lane] = rx1 | (ry1 << 16);
@@ -427,9 +444,9 @@ __device__ __forceinline__ void stage_item(StagedTris &stg, uint32_t lane, uint3
     // early depth rejection (see raster_item): 1/area and an error margin, both only used to SKIP work
     const float zmax = fmaxf(fmaxf(fabsf(s.z0), fabsf(s.z1)), fabsf(s.z2));
     const float rcp = 1.0f / s.area;
-    const bool usable = !s.literal && rcp > 0.f && rcp < __int_as_float(0x7f800000) && zmax < __int_as_float(0x7f800000);
-    stg.w[21][lane] = __float_as_uint(usable ? rcp : 0.f);
-    stg.w[22][lane] = __float_as_uint(usable ? fmaf(zmax, 1.9073486328125e-06f /* 2^-19 */, 1e-37f) : __int_as_float(0x7f800000));
+    const bool usable = !s.literal && rcp > 0.f && rcp < exact::i2f(0x7f800000) && zmax < exact::i2f(0x7f800000);
+    stg.w[21][lane] = exact::f2u(usable ? rcp : 0.f);
+    stg.w[22][lane] = exact::f2u(usable ? fmaf(zmax, 1.9073486328125e-06f /* 2^-19 */, 1e-37f) : exact::i2f(0x7f800000));
     // which of the 4 x 2 blocks can contain a candidate pixel at all (bit = strip * 2 + column)
     uint32_t live = 0u;
     if (tri != INVALID_TRI) {
@@ -447,7 +464,7 @@ __device__ __forceinline__ void stage_item(StagedTris &stg, uint32_t lane, uint3
     }
     stg.w[23][lane] = live;
     stg.w[24][lane] = ox | (oy << 16);
-    stg.w[25][lane] = __float_as_uint(s.rcp1);
+    stg.w[25][lane] = exact::f2u(s.rcp1);
     stg.w[26][lane] = s.div_ok ? 1u : 0u;
 }
 
@@ -455,7 +472,7 @@ __device__ __forceinline__ void stage_item(StagedTris &stg, uint32_t lane, uint3
 // (global atomicMin; early-z reads it through L2 when `early_z`).  TILE_MODE = true: keys go to the CTA's
 // shared-memory tile `tile_keys` (TILE x TILE, anchored at the item's block origin); early-z always on.
 template <bool TILE_MODE>
-__device__ __forceinline__ void raster_item(const StagedTris &stg, uint32_t it, uint32_t lane, const View &vw, unsigned long long *vis_all,
+RAST_HD void raster_item(const StagedTris &stg, uint32_t it, uint32_t lane, const View &vw, unsigned long long *vis_all,
                                             unsigned long long *tile_keys, bool early_z) {
     using namespace exact;
     const uint32_t tri = stg.w[19][it];
@@ -463,18 +480,18 @@ __device__ __forceinline__ void raster_item(const StagedTris &stg, uint32_t it, 
     if (tri == INVALID_TRI || live == 0u) return;
     const uint32_t qx = (lane & 7u) * 2u, qy = (lane >> 3) * 2u;
     TriSetup s;
-    s.x0 = __uint_as_float(stg.w[0][it]); s.y0 = __uint_as_float(stg.w[1][it]);
-    s.x1 = __uint_as_float(stg.w[2][it]); s.y1 = __uint_as_float(stg.w[3][it]);
-    s.x2 = __uint_as_float(stg.w[4][it]); s.y2 = __uint_as_float(stg.w[5][it]);
-    s.z0 = __uint_as_float(stg.w[6][it]); s.z1 = __uint_as_float(stg.w[7][it]); s.z2 = __uint_as_float(stg.w[8][it]);
-    s.d12x = __uint_as_float(stg.w[9][it]); s.d12y = __uint_as_float(stg.w[10][it]);
-    s.d20x = __uint_as_float(stg.w[11][it]); s.d20y = __uint_as_float(stg.w[12][it]);
-    s.d01x = __uint_as_float(stg.w[13][it]); s.d01y = __uint_as_float(stg.w[14][it]);
-    s.area = __uint_as_float(stg.w[15][it]);
+    s.x0 = exact::u2f(stg.w[0][it]); s.y0 = exact::u2f(stg.w[1][it]);
+    s.x1 = exact::u2f(stg.w[2][it]); s.y1 = exact::u2f(stg.w[3][it]);
+    s.x2 = exact::u2f(stg.w[4][it]); s.y2 = exact::u2f(stg.w[5][it]);
+    s.z0 = exact::u2f(stg.w[6][it]); s.z1 = exact::u2f(stg.w[7][it]); s.z2 = exact::u2f(stg.w[8][it]);
+    s.d12x = exact::u2f(stg.w[9][it]); s.d12y = exact::u2f(stg.w[10][it]);
+    s.d20x = exact::u2f(stg.w[11][it]); s.d20y = exact::u2f(stg.w[12][it]);
+    s.d01x = exact::u2f(stg.w[13][it]); s.d01y = exact::u2f(stg.w[14][it]);
+    s.area = exact::u2f(stg.w[15][it]);
     s.literal = stg.w[16][it] != 0u;
-    s.rcp1 = __uint_as_float(stg.w[25][it]);
+    s.rcp1 = exact::u2f(stg.w[25][it]);
     s.div_ok = stg.w[26][it] != 0u;
-    const float rcp_area = __uint_as_float(stg.w[21][it]), z_margin = __uint_as_float(stg.w[22][it]);
+    const float rcp_area = exact::u2f(stg.w[21][it]), z_margin = exact::u2f(stg.w[22][it]);
     const uint32_t rect0 = stg.w[17][it], rect1 = stg.w[18][it], org = stg.w[24][it];
     const uint32_t rx0 = rect0 & 0xFFFFu, ry0 = rect0 >> 16, rx1 = rect1 & 0xFFFFu, ry1 = rect1 >> 16, ox = org & 0xFFFFu, oy = org >> 16;
     unsigned long long *vis = TILE_MODE ? nullptr : vis_all + (size_t)stg.w[20][it] * vw.band_pixels;
@@ -507,7 +524,7 @@ __device__ __forceinline__ void raster_item(const StagedTris &stg, uint32_t it, 
             for (int k = 0; k < 4; ++k)
                 if (candidate(s, e0[k], e1[k], e2[k])) mask |= 1u << k;
             mask &= inrect;
-            if (!__any_sync(0xFFFFFFFFu, mask != 0u)) continue;
+            if (!RAST_ANY(mask != 0u)) continue;
             // Early depth rejection.  z_est approximates the fragment depth to within z_margin
             // (|z_est - z| <= (2^-22 + 8 ulp) * max|z_k| < z_margin / 2 for a candidate pixel), and a stored depth
             // only ever decreases, so "z_est > stored + margin" proves the exact depth would lose the atomicMin:
@@ -519,15 +536,15 @@ __device__ __forceinline__ void raster_item(const StagedTris &stg, uint32_t it, 
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { // all four reads in flight together (global: L2, bypassing L1)
                     const uint32_t *hi = reinterpret_cast<const uint32_t *>(pix0 + (k >> 1) * row_stride + (k & 1)) + 1;
-                    cur_hi[k] = (mask & (1u << k)) ? (TILE_MODE ? *reinterpret_cast<const volatile uint32_t *>(hi) : __ldcg(hi)) : 0xFFFFFFFFu;
+                    cur_hi[k] = (mask & (1u << k)) ? (TILE_MODE ? *reinterpret_cast<const volatile uint32_t *>(hi) : RAST_LDCG32(hi)) : 0xFFFFFFFFu;
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const float z_est = fmaf(s.z2, e2[k], fmaf(s.z1, e1[k], s.z0 * e0[k])) * rcp_area;
                     const uint32_t cur_bits = (cur_hi[k] & 0x80000000u) ? (cur_hi[k] ^ 0x80000000u) : ~cur_hi[k]; // inverse of depth_key
-                    if (cur_hi[k] != 0xFFFFFFFFu && z_est > __uint_as_float(cur_bits) + z_margin) mask &= ~(1u << k);
+                    if (cur_hi[k] != 0xFFFFFFFFu && z_est > exact::u2f(cur_bits) + z_margin) mask &= ~(1u << k);
                 }
-                if (!__any_sync(0xFFFFFFFFu, mask != 0u)) continue;
+                if (!RAST_ANY(mask != 0u)) continue;
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -535,7 +552,7 @@ __device__ __forceinline__ void raster_item(const StagedTris &stg, uint32_t it, 
                     float b0, b1, b2, z;
                     if (fragment(s, e0[k], e1[k], e2[k], b0, b1, b2, z)) {
                         const unsigned long long key = ((unsigned long long)depth_key(z) << 32) | tri;
-                        atomicMin(pix0 + (k >> 1) * row_stride + (k & 1), key);
+                        RAST_ATOMIC_MIN64(pix0 + (k >> 1) * row_stride + (k & 1), key);
                     }
                 }
             }
@@ -686,7 +703,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_tiles(Scene sc, Vi
 // (CImg.h:13475-13492) at the same position.  The position arithmetic is shared between the channels and
 // the texels are stored interleaved (r, g, b, -) on the device, so the four corners are four 16-byte loads
 // instead of twelve 4-byte ones; the per-channel arithmetic is CImg's, unchanged.
-__device__ __forceinline__ void sample_texture(const float4 *__restrict__ tex, int w, int h, float fx, float fy, float &r, float &g, float &b) {
+RAST_HD void sample_texture(const float4 *__restrict__ tex, int w, int h, float fx, float fy, float &r, float &g, float &b) {
     using namespace exact;
     const float hx = (float)(w - 1), hy = (float)(h - 1);
     const float nfx = fx < 0.f ? 0.f : (fx > hx ? hx : fx); // cimg::cut (CImg.h:5184-5186)
@@ -694,8 +711,8 @@ __device__ __forceinline__ void sample_texture(const float4 *__restrict__ tex, i
     const uint32_t x = to_uint(nfx), y = to_uint(nfy);
     const float dx = sub(nfx, (float)x), dy = sub(nfy, (float)y);
     const uint32_t nx = dx > 0.f ? x + 1u : x, ny = dy > 0.f ? y + 1u : y;
-    const float4 cc = __ldg(tex + (x + y * (uint32_t)w)), nc = __ldg(tex + (nx + y * (uint32_t)w));
-    const float4 cn = __ldg(tex + (x + ny * (uint32_t)w)), nn = __ldg(tex + (nx + ny * (uint32_t)w));
+    const float4 cc = exact::ldg(tex + (x + y * (uint32_t)w)), nc = exact::ldg(tex + (nx + y * (uint32_t)w));
+    const float4 cn = exact::ldg(tex + (x + ny * (uint32_t)w)), nn = exact::ldg(tex + (nx + ny * (uint32_t)w));
     // Icc + dx*(Inc - Icc + dy*(Icc + Inn - Icn - Inc)) + dy*(Icn - Icc)
     r = add(add(cc.x, mul(dx, add(sub(nc.x, cc.x), mul(dy, sub(sub(add(cc.x, nn.x), cn.x), nc.x))))), mul(dy, sub(cn.x, cc.x)));
     g = add(add(cc.y, mul(dx, add(sub(nc.y, cc.y), mul(dy, sub(sub(add(cc.y, nn.y), cn.y), nc.y))))), mul(dy, sub(cn.y, cc.y)));
@@ -717,15 +734,15 @@ struct LightTable {
 
 // The shading half of update_pixel (drawing.cpp:121-146) for the winning triangle of one pixel.
 template <bool PRE_NORMALS, bool FLAT>
-__device__ __forceinline__ Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t y, const Scene &sc, const float4 *__restrict__ rv,
+RAST_HD Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t y, const Scene &sc, const float4 *__restrict__ rv,
                                               const float4 *__restrict__ cn, const float *__restrict__ normal_m, bool wind_clockwise,
                                               const LightTable &lt, const LightDev *__restrict__ lights) {
     using namespace exact;
     Shaded out;
     const uint4 *rec = reinterpret_cast<const uint4 *>(sc.tri_rec) + 3 * (size_t)tri; // indices are non-negative after upload
-    const uint4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
-    const uint2 r2 = __ldg(reinterpret_cast<const uint2 *>(rec + 2));
-    const float4 v0 = __ldg(rv + r0.x), v1 = __ldg(rv + r0.y), v2 = __ldg(rv + r0.z); // written by k_vertex, read-only here
+    const uint4 r0 = exact::ldg(rec), r1 = exact::ldg(rec + 1);
+    const uint2 r2 = exact::ldg(reinterpret_cast<const uint2 *>(rec + 2));
+    const float4 v0 = exact::ldg(rv + r0.x), v1 = exact::ldg(rv + r0.y), v2 = exact::ldg(rv + r0.z); // written by k_vertex, read-only here
 
     // vertex normals in camera space (transform_direction, geometry.cpp:35-42,97-108)
     float4 n0, n1, n2;
@@ -735,11 +752,11 @@ __device__ __forceinline__ Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t
         // normal_m points at the frame's modelview matrix in this mode
         float mv[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) mv[k] = __ldg(normal_m + k);
+        for (int k = 0; k < 16; ++k) mv[k] = exact::ldg(normal_m + k);
         const float *p0 = sc.pos + 3 * (size_t)r0.x, *p1 = sc.pos + 3 * (size_t)r0.y, *p2 = sc.pos + 3 * (size_t)r0.z;
-        const float4 c0 = mat_vec(mv, __ldg(p0), __ldg(p0 + 1), __ldg(p0 + 2), 1.f);
-        const float4 c1 = mat_vec(mv, __ldg(p1), __ldg(p1 + 1), __ldg(p1 + 2), 1.f);
-        const float4 c2 = mat_vec(mv, __ldg(p2), __ldg(p2 + 1), __ldg(p2 + 2), 1.f);
+        const float4 c0 = mat_vec(mv, exact::ldg(p0), exact::ldg(p0 + 1), exact::ldg(p0 + 2), 1.f);
+        const float4 c1 = mat_vec(mv, exact::ldg(p1), exact::ldg(p1 + 1), exact::ldg(p1 + 2), 1.f);
+        const float4 c2 = mat_vec(mv, exact::ldg(p2), exact::ldg(p2 + 1), exact::ldg(p2 + 2), 1.f);
         const float ax = sub(c1.x, c0.x), ay = sub(c1.y, c0.y), az = sub(c1.z, c0.z);
         const float bx = sub(c2.x, c0.x), by = sub(c2.y, c0.y), bz = sub(c2.z, c0.z);
         fx = sub(mul(ay, bz), mul(by, az)); // glm::cross
@@ -747,19 +764,19 @@ __device__ __forceinline__ Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t
         fz = sub(mul(ax, by), mul(bx, ay));
         n0 = n1 = n2 = make_float4(0.f, 0.f, 0.f, 0.f);
     } else if (PRE_NORMALS) {
-        n0 = __ldg(cn + r0.w); n1 = __ldg(cn + r1.x); n2 = __ldg(cn + r1.y);
+        n0 = exact::ldg(cn + r0.w); n1 = exact::ldg(cn + r1.x); n2 = exact::ldg(cn + r1.y);
     } else {
         const float *m0 = sc.nrm + 3 * (size_t)r0.w, *m1 = sc.nrm + 3 * (size_t)r1.x, *m2 = sc.nrm + 3 * (size_t)r1.y;
         float nm[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) nm[k] = __ldg(normal_m + k);
-        n0 = mat_vec(nm, __ldg(m0), __ldg(m0 + 1), __ldg(m0 + 2), 0.f);
-        n1 = mat_vec(nm, __ldg(m1), __ldg(m1 + 1), __ldg(m1 + 2), 0.f);
-        n2 = mat_vec(nm, __ldg(m2), __ldg(m2 + 1), __ldg(m2 + 2), 0.f);
+        for (int k = 0; k < 16; ++k) nm[k] = exact::ldg(normal_m + k);
+        n0 = mat_vec(nm, exact::ldg(m0), exact::ldg(m0 + 1), exact::ldg(m0 + 2), 0.f);
+        n1 = mat_vec(nm, exact::ldg(m1), exact::ldg(m1 + 1), exact::ldg(m1 + 2), 0.f);
+        n2 = mat_vec(nm, exact::ldg(m2), exact::ldg(m2 + 1), exact::ldg(m2 + 2), 0.f);
     }
     const MaterialDev *mp = sc.mats + r2.y;
-    const float4 mk = __ldg(reinterpret_cast<const float4 *>(mp));      // kd.rgb, has_texture
-    const int4 mt = __ldg(reinterpret_cast<const int4 *>(mp) + 1);      // tex_w, tex_h, texel_offset (lo, hi)
+    const float4 mk = exact::ldg(reinterpret_cast<const float4 *>(mp));      // kd.rgb, has_texture
+    const int4 mt = exact::ldg(reinterpret_cast<const int4 *>(mp) + 1);      // tex_w, tex_h, texel_offset (lo, hi)
 
     // barycentric + depth, the same operations as the raster pass => the same bits (drawing.cpp:41-49,115-116)
     const float px = (float)x, py = (float)y;
@@ -779,8 +796,8 @@ __device__ __forceinline__ Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t
     // division and a square root, ~80 instructions) so that their latency is covered by this warp's own arithmetic
     // (8.20 -> 8.14 ms per 720 frames on the 1080p spin).
     float ar = mk.x, ag = mk.y, ab = mk.z;
-    if (__float_as_int(mk.w) != 0) {
-        const float2 uv0 = __ldg(sc.uv + r1.z), uv1 = __ldg(sc.uv + r1.w), uv2 = __ldg(sc.uv + r2.x);
+    if (exact::f2u(mk.w) != 0u) {
+        const float2 uv0 = exact::ldg(sc.uv + r1.z), uv1 = exact::ldg(sc.uv + r1.w), uv2 = exact::ldg(sc.uv + r2.x);
         const float u = mul(d, add(add(mul(i0, uv0.x), mul(i1, uv1.x)), mul(i2, uv2.x))); // drawing.cpp:135
         const float v = mul(d, add(add(mul(i0, uv0.y), mul(i1, uv1.y)), mul(i2, uv2.y)));
         const long long toff = ((long long)(uint32_t)mt.z) | ((long long)mt.w << 32);

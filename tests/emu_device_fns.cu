@@ -1,0 +1,158 @@
+// emu_device_fns.cu -- TEST ONLY.  Runs the per-thread functions of rasteriser_b200/csrc/kernels.cuh ON THE HOST.
+//
+// The development container has no GPU.  The arithmetic of the frame path lives in RAST_HD (__host__ __device__) functions
+// -- raster_vertex, signed_area_2d, bounding_box, tri_setup, edges / candidate / fragment, stage_item / raster_item (the warp
+// rasteriser's inner loop, one lane at a time), shade_pixel, sample_texture -- so this file, compiled by nvcc for the host,
+// drives those very functions serially in the order the kernels launch them and tests/test_emu_device_fns.py compares the
+// result with the oracle bit for bit.  What it does NOT cover: the __global__ wrappers (grids, staging through shared
+// memory, votes, atomics, streams) and the device flavour of exact:: (the _rn intrinsics and the shared-reciprocal division,
+// which rast_selftest_division checks on the GPU).  It is a checker for kernel-logic changes made without a GPU, never a
+// product path: nothing under rasteriser_b200/ or include/ builds, loads or calls it.
+//
+// Build (tests/test_emu_device_fns.py): nvcc -std=c++17 -O2 -Xcompiler -fPIC,-ffp-contract=off -shared -o libemu.so emu_device_fns.cu
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#ifndef RAST_TIGHT_TINY
+#define RAST_TIGHT_TINY 1 // the host driver below calls rast_tight_bbox only when asked to (flag bit 0)
+#endif
+#include "../rasteriser_b200/csrc/kernels.cuh"
+
+struct EmuMaterial { // = rast_material (include/rast.h): planar normalised texels
+    float kd[3];
+    int32_t has_texture, tex_w, tex_h;
+    const float *texels;
+};
+
+enum { EMU_TIGHT = 1, EMU_PRE_NORMALS = 2, EMU_EARLY_Z = 4, EMU_ALL_CHUNKS = 8, EMU_FLAT_FACE = 16 };
+
+// One frame.  lights: n x 10 floats (rast_light: direction, intensity, colour, trans_dir -- trans_dir already computed by
+// rast_transform_lights).  Outputs: rgb planar [3][rows][W], depth [rows][W], tri_ids [rows][W] for the band [y0, y1).
+extern "C" int emu_draw(const float *pos, uint32_t V, const float *nrm, uint32_t Nn, const float *uv, uint32_t Nuv, const int32_t *tris, uint64_t T,
+                        const EmuMaterial *mats, uint32_t M, const float *lights, uint32_t L, const float *camera, const float *normal_m,
+                        const float *modelview, int wind_clockwise, uint32_t W, uint32_t H, uint32_t y0, uint32_t y1, uint32_t tiny_max_pixels, int flags,
+                        uint8_t *rgb, float *depth, uint32_t *tri_ids) {
+    using namespace rk;
+    View vw;
+    vw.W = W; vw.H = H; vw.y0 = y0; vw.y1 = y1; vw.band_pixels = W * (y1 - y0); vw.out_plane = vw.band_pixels;
+    const size_t P = vw.band_pixels;
+
+    // ---- scene arrays as rast_upload_mesh / k_build_tri_records / rast_upload_materials lay them out ----
+    std::vector<float> nrm_s(nrm, nrm + 3 * (size_t)Nn);
+    nrm_s.insert(nrm_s.end(), {0.f, 0.f, 0.f}); // sentinel normal
+    std::vector<float2> uv_s((size_t)Nuv + 1);
+    for (uint32_t i = 0; i < Nuv; ++i) uv_s[i] = make_float2(uv[2 * i], uv[2 * i + 1]);
+    uv_s[Nuv] = make_float2(0.f, 0.f);
+    std::vector<int4> rec(3 * (size_t)T);
+    for (uint64_t t = 0; t < T; ++t) {
+        const int32_t *f = tris + 10 * t;
+        int n[3], u[3];
+        for (int k = 0; k < 3; ++k) {
+            if (f[k] < 0 || (uint32_t)f[k] >= V) return -1;
+            if (f[3 + k] >= 0 && (uint32_t)f[3 + k] >= Nn) return -1;
+            if (f[6 + k] >= 0 && (uint32_t)f[6 + k] >= Nuv) return -1;
+            n[k] = f[3 + k] >= 0 ? f[3 + k] : (int)Nn;
+            u[k] = f[6 + k] >= 0 ? f[6 + k] : (int)Nuv;
+        }
+        const int mat = (f[9] < 0 || (uint32_t)f[9] >= M) ? (int)M : f[9]; // k_resolve_materials
+        rec[3 * t] = make_int4(f[0], f[1], f[2], n[0]);
+        rec[3 * t + 1] = make_int4(n[1], n[2], u[0], u[1]);
+        rec[3 * t + 2] = make_int4(u[2], mat, f[9], 0);
+    }
+    std::vector<MaterialDev> md((size_t)M + 1);
+    std::vector<float4> texels;
+    for (uint32_t i = 0; i < M; ++i) {
+        md[i].kd[0] = mats[i].kd[0]; md[i].kd[1] = mats[i].kd[1]; md[i].kd[2] = mats[i].kd[2];
+        md[i].has_texture = mats[i].has_texture ? 1 : 0;
+        md[i].tex_w = mats[i].tex_w; md[i].tex_h = mats[i].tex_h;
+        md[i].texel_offset = (long long)texels.size();
+        if (mats[i].has_texture) {
+            const size_t n = (size_t)mats[i].tex_w * mats[i].tex_h;
+            const float *t = mats[i].texels;
+            for (size_t k = 0; k < n; ++k) texels.push_back(make_float4(t[k], t[n + k], t[2 * n + k], 0.f));
+        }
+    }
+    md[M].kd[0] = md[M].kd[1] = md[M].kd[2] = 1.f;
+    md[M].has_texture = 0; md[M].tex_w = md[M].tex_h = 0; md[M].texel_offset = 0;
+    texels.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
+
+    Scene sc{};
+    sc.pos = pos; sc.nrm = nrm_s.data(); sc.uv = uv_s.data();
+    sc.tri_rec = rec.data(); sc.mats = md.data(); sc.texels = texels.data();
+    sc.V = V; sc.Nn = Nn + 1; sc.Nuv = Nuv + 1; sc.M = M + 1; sc.T = T;
+
+    // ---- lights as draw_frames_impl prepares them ----
+    LightTable lt{};
+    std::vector<LightDev> ld((size_t)L + 1);
+    for (uint32_t l = 0; l < L; ++l) {
+        const float *q = lights + 10 * (size_t)l;
+        ld[l].ntx = -q[7]; ld[l].nty = -q[8]; ld[l].ntz = -q[9];
+        ld[l].icr = q[3] * q[4]; ld[l].icg = q[3] * q[5]; ld[l].icb = q[3] * q[6];
+        ld[l].pad0 = ld[l].pad1 = 0.f;
+        if (l < PARAM_LIGHTS) { lt.a[l] = make_float4(ld[l].ntx, ld[l].nty, ld[l].ntz, ld[l].icr); lt.c[l] = make_float2(ld[l].icg, ld[l].icb); }
+    }
+    lt.n = L;
+
+    // ---- k_vertex ----
+    std::vector<float4> rv(V), cn((size_t)Nn + 1);
+    for (uint32_t i = 0; i < V; ++i) rv[i] = raster_vertex(camera, pos[3 * (size_t)i], pos[3 * (size_t)i + 1], pos[3 * (size_t)i + 2], W, H);
+    for (uint32_t j = 0; j <= Nn; ++j) {
+        const float4 t = exact::mat_vec(normal_m, nrm_s[3 * (size_t)j], nrm_s[3 * (size_t)j + 1], nrm_s[3 * (size_t)j + 2], 0.f);
+        cn[j] = make_float4(t.x, t.y, t.z, 0.f);
+    }
+
+    // ---- k_setup (+ k_raster_chunks): cull, bbox, tiny bboxes walked by edges / candidate / fragment, the rest cut into
+    //      CHUNK x CHUNK items that go through stage_item / raster_item lane by lane ----
+    std::vector<unsigned long long> vis(P, VIS_EMPTY);
+    StagedTris *stg = new StagedTris();
+    const bool early_z = (flags & EMU_EARLY_Z) != 0;
+    for (uint64_t t = 0; t < T; ++t) {
+        const float4 v0 = rv[tris[10 * t]], v1 = rv[tris[10 * t + 1]], v2 = rv[tris[10 * t + 2]];
+        const float a2 = signed_area_2d(v0, v1, v2);
+        if (!((a2 > 0.f) != (wind_clockwise != 0))) continue;
+        const BBox bb = bounding_box(v0, v1, v2, vw);
+        if (bb.empty) continue;
+        const uint32_t w = bb.x1 - bb.x0 + 1u, h = bb.y1 - bb.y0 + 1u;
+        const bool inline_raster = !(flags & EMU_ALL_CHUNKS) && (uint64_t)w * h <= tiny_max_pixels;
+        if (inline_raster) {
+            TriSetup s;
+            tri_setup(s, v0, v1, v2);
+            uint32_t wx0 = bb.x0, wy0 = bb.y0, wx1 = bb.x1, wy1 = bb.y1;
+            if ((flags & EMU_TIGHT) && !rast_tight_bbox(v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, s.literal ? 0.f : s.area, &wx0, &wy0, &wx1, &wy1)) continue;
+            for (uint32_t y = wy0; y <= wy1; ++y)
+                for (uint32_t x = wx0; x <= wx1; ++x) test_and_commit(s, x, y, (uint32_t)t, vis.data(), vw);
+        } else {
+            const uint32_t ncx = (w + CHUNK - 1) / CHUNK, ncy = (h + CHUNK - 1) / CHUNK;
+            for (uint32_t cy = 0; cy < ncy; ++cy)
+                for (uint32_t cx = 0; cx < ncx; ++cx) {
+                    const uint32_t rx0 = bb.x0 + cx * CHUNK, ry0 = bb.y0 + cy * CHUNK;
+                    const uint32_t rx1 = min(bb.x1, rx0 + CHUNK - 1u), ry1 = min(bb.y1, ry0 + CHUNK - 1u);
+                    const uint32_t slot = (uint32_t)((t + cx + cy) & 31u); // any staging slot must do
+                    stage_item(*stg, slot, (uint32_t)t, 0u, v0, v1, v2, rx0, ry0, rx1, ry1, rx0, ry0);
+                    for (uint32_t lane = 0; lane < 32u; ++lane) raster_item<false>(*stg, slot, lane, vw, vis.data(), nullptr, early_z);
+                }
+        }
+    }
+    delete stg;
+
+    // ---- k_resolve_shade ----
+    const bool pre = (flags & EMU_PRE_NORMALS) != 0, flat = (flags & EMU_FLAT_FACE) != 0;
+    for (uint32_t y = y0; y < y1; ++y)
+        for (uint32_t x = 0; x < W; ++x) {
+            const size_t i = (size_t)(y - y0) * W + x;
+            Shaded px;
+            px.r = px.g = px.b = 0u; px.depth = 1.0f;
+            uint32_t id = INVALID_TRI;
+            if (vis[i] != VIS_EMPTY) {
+                id = (uint32_t)vis[i];
+                if (flat) px = shade_pixel<false, true>(id, x, y, sc, rv.data(), cn.data(), modelview, wind_clockwise != 0, lt, ld.data());
+                else if (pre) px = shade_pixel<true, false>(id, x, y, sc, rv.data(), cn.data(), normal_m, wind_clockwise != 0, lt, ld.data());
+                else px = shade_pixel<false, false>(id, x, y, sc, rv.data(), cn.data(), normal_m, wind_clockwise != 0, lt, ld.data());
+            }
+            rgb[i] = (uint8_t)px.r; rgb[i + P] = (uint8_t)px.g; rgb[i + 2 * P] = (uint8_t)px.b;
+            depth[i] = px.depth;
+            tri_ids[i] = id;
+        }
+    return 0;
+}

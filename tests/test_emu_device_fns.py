@@ -1,0 +1,118 @@
+"""The kernels' per-thread functions, compiled for the HOST, against the oracle (CPU only, no GPU needed).
+
+tests/emu_device_fns.cu drives the RAST_HD functions of rasteriser_b200/csrc/kernels.cuh -- raster_vertex, signed_area_2d,
+bounding_box, tri_setup, edges / candidate / fragment, stage_item / raster_item (the warp rasteriser's inner loop, lane by
+lane), shade_pixel, sample_texture and, with the `tight` flag, rast_tight_bbox -- in the order the kernels launch them.  The
+result must equal the oracle's bit for bit (winning triangle, depth bits, colour bytes).  This is how kernel-logic changes
+are checked in the development container, which has no GPU; the -m gpu tests remain the parity tests proper."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import orc
+import scenes as S
+from rasteriser_b200 import _lib
+from test_parity_gpu_fuzz import _case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "emu_device_fns.cu")
+CSRC = os.path.join(ROOT, "rasteriser_b200", "csrc")
+TIGHT, PRE_NORMALS, EARLY_Z, ALL_CHUNKS, FLAT_FACE = 1, 2, 4, 8, 16
+
+
+class EmuMaterial(C.Structure):
+    _fields_ = [("kd", C.c_float * 3), ("has_texture", C.c_int32), ("tex_w", C.c_int32), ("tex_h", C.c_int32), ("texels", C.c_void_p)]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    out = os.path.join(ROOT, "build", "libemu.so")
+    deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "-fmad=false",
+                               "-Xcompiler", "-fPIC,-ffp-contract=off,-Wno-unknown-pragmas", "-shared", "-o", out, SRC])
+    lib = C.CDLL(out)
+    lib.emu_draw.restype = C.c_int
+    lib.emu_draw.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64,
+                             C.POINTER(EmuMaterial), C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                             C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    return lib
+
+
+def emu_draw(emu, scene, lights7, oa, flags, tiny_max=16, band=None):
+    """One frame through the host-compiled device functions; matrices and light directions from the product's own host code
+    (rast_frame_matrices / rast_transform_lights run without a GPU)."""
+    rast = _lib.load()
+    ra = _lib.RastArgs()
+    ra.image_width, ra.image_height, ra.aspect_ratio, ra.scale = oa.image_width, oa.image_height, oa.aspect_ratio, oa.scale
+    ra.displacement = oa.displacement
+    ra.tait_bryan_angles = oa.tait_bryan_angles
+    ra.wind_clockwise, ra.flat = oa.wind_clockwise, oa.flat
+    mv, cam, nm, view = (np.zeros(16, np.float32) for _ in range(4))
+    rast.rast_frame_matrices(C.byref(ra), orc.ptr(mv), orc.ptr(cam), orc.ptr(nm), orc.ptr(view))
+    l10 = orc.lights_array(lights7)
+    rast.rast_transform_lights(orc.ptr(view), l10.ctypes.data_as(C.POINTER(_lib.RastLight)), len(l10))
+    mats = (EmuMaterial * max(1, len(scene.materials)))()
+    for i, m in enumerate(scene.materials):
+        mats[i].kd = (C.c_float * 3)(*m["kd"])
+        t = m.get("texels")
+        mats[i].has_texture = 0 if t is None else 1
+        if t is not None:
+            mats[i].tex_h, mats[i].tex_w = t.shape[1], t.shape[2]
+            mats[i].texels = t.ctypes.data
+    W, H = oa.image_width, oa.image_height
+    y0, y1 = band if band else (0, H)
+    rows = y1 - y0
+    rgb, depth, ids = np.zeros((3, rows, W), np.uint8), np.zeros((rows, W), np.float32), np.zeros((rows, W), np.uint32)
+    rc = emu.emu_draw(orc.ptr(scene.positions), len(scene.positions), orc.ptr(scene.normals), len(scene.normals), orc.ptr(scene.uvs), len(scene.uvs),
+                      orc.ptr(scene.tris), len(scene.tris), mats, len(scene.materials), orc.ptr(l10), len(l10), orc.ptr(cam), orc.ptr(nm), orc.ptr(mv),
+                      int(oa.wind_clockwise), W, H, y0, y1, tiny_max, flags, orc.ptr(rgb), orc.ptr(depth), orc.ptr(ids))
+    assert rc == 0
+    return rgb, depth, ids
+
+
+def assert_exact(got, want, what):
+    assert np.array_equal(got[2], want[2]), "%s: %d pixels with a different winning triangle" % (what, int((got[2] != want[2]).sum()))
+    assert np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32)), "%s: depth bits differ at %d pixels" % (what, int((got[1].view(np.uint32) != want[1].view(np.uint32)).sum()))
+    assert np.array_equal(got[0], want[0]), "%s: colour differs at %d samples" % (what, int((got[0] != want[0]).sum()))
+
+
+@pytest.mark.parametrize("flags", [PRE_NORMALS, 0, PRE_NORMALS | TIGHT, PRE_NORMALS | ALL_CHUNKS, PRE_NORMALS | ALL_CHUNKS | EARLY_Z])
+def test_golden_cases_on_the_host(emu, flags):
+    """Every golden case of tests/golden/cases.json small enough for the CPU suite: equal to the oracle AND to the hashes the
+    reference itself produced."""
+    n = 0
+    for c in S.golden_cases():
+        if c["width"] * c["height"] > 330000:
+            continue
+        scene, lights = S.scene(c["scene"]), S.lights(c["lights"])
+        oa = S.case_args(c)
+        got = emu_draw(emu, scene, lights, oa, flags)
+        assert_exact(got, orc.oracle_draw(scene, lights, oa), "%s flags %d" % (c["name"], flags))
+        assert orc.fnv(got[0]) == c["frame_fnv"] and orc.fnv(got[1]) == c["depth_fnv"], c["name"]
+        n += 1
+    assert n >= 10
+
+
+@pytest.mark.parametrize("seed", range(1000, 1040))
+def test_fuzz_cases_on_the_host(emu, seed):
+    """The GPU fuzz distribution (tests/test_parity_gpu_fuzz.py::_case): soups through the eye plane, 1x1 images, both windings,
+    up to 70 lights, negative intensities; tiny path with and without the tight-bbox rule, chunk path with and without early z."""
+    scene, lights, oa, mode, kind = _case(seed)
+    want = orc.oracle_draw(scene, lights, oa, threads=2)
+    for flags, tiny in [(PRE_NORMALS, 16), (TIGHT, 64), (PRE_NORMALS | TIGHT, 1 << 30), (ALL_CHUNKS | EARLY_Z, 16)]:
+        assert_exact(emu_draw(emu, scene, lights, oa, flags, tiny), want, "seed %d (%s) flags %d" % (seed, kind, flags))
+
+
+def test_band_and_face_normals_on_the_host(emu):
+    scene, lights = S.scene("suzanne"), S.lights("threepoint")
+    oa = orc.make_args(320, 240, angles=(0.2, 0.7, 0.0))
+    want = orc.oracle_draw(scene, lights, oa)
+    got = emu_draw(emu, scene, lights, oa, PRE_NORMALS | TIGHT, band=(60, 180))
+    assert_exact(got, tuple(a[..., 60:180, :] for a in want), "band")
+    oa.flat = 2  # extension: face normals
+    assert_exact(emu_draw(emu, scene, lights, oa, FLAT_FACE), orc.oracle_draw(scene, lights, oa), "flat face")
