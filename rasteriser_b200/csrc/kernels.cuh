@@ -19,6 +19,15 @@
 #ifndef RAST_TIGHT_TINY
 #define RAST_TIGHT_TINY 0
 #endif
+// Variant switch: the shade pass reads one prepared 160-byte record per (frame, triangle) -- vertices, the pixel-invariant
+// edge differences, area and its refined reciprocal, depths, 1/w, camera normals, uvs, material -- written once per batch by
+// k_prepare_tris, instead of gathering record -> vertices / normals / uvs and recomputing the differences for every pixel
+// (about 44 of the ~330 instructions of a covered pixel and one level of dependent loads).  Hoisting rounded values does not
+// change them, so the bits are the same (tests/test_emu_device_fns.py runs both flavours against the oracle).  Only for
+// meshes whose records fit beside the visibility buffer; off in the default build until timed on a B200.
+#ifndef RAST_SHADE_PREP
+#define RAST_SHADE_PREP 0
+#endif
 #if RAST_TIGHT_TINY
 #include "tight_bbox.h"
 #endif
@@ -107,6 +116,9 @@ struct Batch {
     uint32_t *bbox;           // [n_frames][4] or nullptr: covered rectangle of each frame, written by the shade pass as
                               // atomicMin of (x, y, W-1-x, rows-1-y) over the covered pixels (all 0xFFFFFFFF = nothing covered);
                               // the host copies only that rectangle back and fills the rest itself
+#if RAST_SHADE_PREP
+    float4 *prep;             // prepared shading records [n_frames][T][PREP_QUADS] or nullptr (k_prepare_tris -> k_resolve_shade)
+#endif
 };
 
 // Screen-tile bins of the binned raster schedule (k_plan_tiles / k_fill_tiles / k_raster_tiles).
@@ -856,6 +868,127 @@ RAST_HD Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t y, const Scene &sc
     return out;
 }
 
+#if RAST_SHADE_PREP
+// ---- prepared shading records (variant) -----------------------------------------------------------------------------
+// q0 (v0.x v0.y v1.x v1.y)  q1 (v2.x v2.y area rcp1)  q2 (d12x d12y d20x d20y)  q3 (d01x d01y div_ok material)
+// q4 (z0 z1 z2 w0)  q5 (w1 w2 uv0.x uv0.y)  q6 (uv1.x uv1.y uv2.x uv2.y)  q7 (n0.x n0.y n0.z n1.x)  q8 (n1.y n1.z n2.x n2.y)  q9 (n2.z - - -)
+// with dij = vj - vi exactly as shade_pixel forms them, area = edge(v2; v0, v1) (drawing.cpp:46), rcp1 / div_ok as
+// exact::div3 wants them.  Everything in it is a value shade_pixel would compute or load for every pixel of the triangle.
+constexpr uint32_t PREP_QUADS = 10;
+
+RAST_HD void prepare_triangle(uint32_t tri, const Scene &sc, const float4 *__restrict__ rv, const float4 *__restrict__ cn, float4 *__restrict__ out) {
+    using namespace exact;
+    const uint4 *rec = reinterpret_cast<const uint4 *>(sc.tri_rec) + 3 * (size_t)tri;
+    const uint4 r0 = ldg(rec), r1 = ldg(rec + 1);
+    const uint2 r2 = ldg(reinterpret_cast<const uint2 *>(rec + 2));
+    const float4 v0 = rv[r0.x], v1 = rv[r0.y], v2 = rv[r0.z];
+    const float4 n0 = cn[r0.w], n1 = cn[r1.x], n2 = cn[r1.y];
+    const float2 uv0 = ldg(sc.uv + r1.z), uv1 = ldg(sc.uv + r1.w), uv2 = ldg(sc.uv + r2.x);
+    const float d01x = sub(v1.x, v0.x), d01y = sub(v1.y, v0.y);
+    const float area = sub(mul(d01x, sub(v2.y, v0.y)), mul(d01y, sub(v2.x, v0.x)));
+    out[0] = make_float4(v0.x, v0.y, v1.x, v1.y);
+    out[1] = make_float4(v2.x, v2.y, area, div_reciprocal(area));
+    out[2] = make_float4(sub(v2.x, v1.x), sub(v2.y, v1.y), sub(v0.x, v2.x), sub(v0.y, v2.y));
+    out[3] = make_float4(d01x, d01y, u2f(div_in_range(area) ? 1u : 0u), u2f(r2.y));
+    out[4] = make_float4(v0.z, v1.z, v2.z, v0.w);
+    out[5] = make_float4(v1.w, v2.w, uv0.x, uv0.y);
+    out[6] = make_float4(uv1.x, uv1.y, uv2.x, uv2.y);
+    out[7] = make_float4(n0.x, n0.y, n0.z, n1.x);
+    out[8] = make_float4(n1.y, n1.z, n2.x, n2.y);
+    out[9] = make_float4(n2.z, 0.f, 0.f, 0.f);
+}
+
+// one thread per (triangle, frame); back faces are prepared too (968 x 32 records per batch on the spin sequence: nothing)
+__global__ void __launch_bounds__(128) k_prepare_tris(Scene sc, Batch bt) {
+    const uint64_t t = (uint64_t)blockIdx.x * 128 + threadIdx.x;
+    const uint32_t f = blockIdx.y;
+    if (t >= sc.T) return;
+    prepare_triangle((uint32_t)t, sc, bt.rv + (size_t)f * sc.V, bt.cn + (size_t)f * sc.Nn, bt.prep + ((size_t)f * sc.T + t) * PREP_QUADS);
+}
+
+// shade_pixel for a prepared triangle: the same operations on the same values, in the same order, from the record
+RAST_HD Shaded shade_pixel_prep(uint32_t tri, uint32_t x, uint32_t y, const Scene &sc, const float4 *__restrict__ prep, bool wind_clockwise,
+                                const LightTable &lt, const LightDev *__restrict__ lights) {
+    using namespace exact;
+    Shaded out;
+    const float4 *q = prep + (size_t)tri * PREP_QUADS;
+    const float4 q0 = ldg(q), q1 = ldg(q + 1), q2 = ldg(q + 2), q3 = ldg(q + 3), q4 = ldg(q + 4), q5 = ldg(q + 5);
+    const float4 q7 = ldg(q + 7), q8 = ldg(q + 8);
+    const float n2z = ldg(reinterpret_cast<const float *>(q + 9));
+    const MaterialDev *mp = sc.mats + f2u(q3.w);
+    const float4 mk = ldg(reinterpret_cast<const float4 *>(mp));      // kd.rgb, has_texture
+    const int4 mt = ldg(reinterpret_cast<const int4 *>(mp) + 1);      // tex_w, tex_h, texel_offset (lo, hi)
+
+    // barycentric + depth (drawing.cpp:41-49,115-116): e_k from the prepared differences
+    const float px = (float)x, py = (float)y;
+    const float e0 = sub(mul(q2.x, sub(py, q0.w)), mul(q2.y, sub(px, q0.z)));
+    const float e1 = sub(mul(q2.z, sub(py, q1.y)), mul(q2.w, sub(px, q1.x)));
+    const float e2 = sub(mul(q3.x, sub(py, q0.y)), mul(q3.y, sub(px, q0.x)));
+    float b0, b1, b2;
+    div3(e0, e1, e2, q1.z, q1.w, f2u(q3.z) != 0u, b0, b1, b2);
+    out.depth = add(add(mul(q4.x, b0), mul(q4.y, b1)), mul(q4.z, b2));
+
+    const float i0 = mul(q4.w, b0), i1 = mul(q5.x, b1), i2 = mul(q5.y, b2);
+    const float d = div(1.f, add(add(i0, i1), i2));
+
+    float ar = mk.x, ag = mk.y, ab = mk.z;
+    if (f2u(mk.w) != 0u) {
+        const float4 q6 = ldg(q + 6);
+        const float u = mul(d, add(add(mul(i0, q5.z), mul(i1, q6.x)), mul(i2, q6.z))); // drawing.cpp:135
+        const float v = mul(d, add(add(mul(i0, q5.w), mul(i1, q6.y)), mul(i2, q6.w)));
+        const long long toff = ((long long)(uint32_t)mt.z) | ((long long)mt.w << 32);
+        unsigned long long tex_base = (unsigned long long)(sc.texels + toff);
+        asm volatile("" : "+l"(tex_base));
+        sample_texture(reinterpret_cast<const float4 *>(tex_base), mt.x, mt.y, mul(u, (float)mt.x), mul(sub(1.f, v), (float)mt.y), ar, ag, ab);
+    }
+
+    const float mx = mul(d, add(add(mul(i0, q7.x), mul(i1, q7.w)), mul(i2, q8.z)));
+    const float my = mul(d, add(add(mul(i0, q7.y), mul(i1, q8.x)), mul(i2, q8.w)));
+    const float mz = mul(d, add(add(mul(i0, q7.z), mul(i1, q8.y)), mul(i2, n2z)));
+    const float inv = div(1.f, fsqrt(add(add(mul(mx, mx), mul(my, my)), mul(mz, mz))));
+    float nx = mul(mx, inv), ny = mul(my, inv), nz = mul(mz, inv);
+    if (wind_clockwise) { nx = -nx; ny = -ny; nz = -nz; }
+
+    float sr = 0.f, sg = 0.f, sb = 0.f;
+    const uint32_t n_p = lt.n < PARAM_LIGHTS ? lt.n : PARAM_LIGHTS;
+    auto one_light = [&](uint32_t l) {
+        const float4 a = lt.a[l];
+        const float2 c = lt.c[l];
+        const float k = glm_max(0.f, add(add(mul(nx, a.x), mul(ny, a.y)), mul(nz, a.z)));
+        sr = add(sr, mul(mul(mul(a.w, ar), k), 0.318309886183790671537767526745028724f));
+        sg = add(sg, mul(mul(mul(c.x, ag), k), 0.318309886183790671537767526745028724f));
+        sb = add(sb, mul(mul(mul(c.y, ab), k), 0.318309886183790671537767526745028724f));
+    };
+    if (n_p == 3u) {
+        one_light(0); one_light(1); one_light(2);
+    } else if (n_p == 1u) {
+        one_light(0);
+    } else if (n_p == 2u) {
+        one_light(0); one_light(1);
+    } else if (n_p == 4u) {
+        one_light(0); one_light(1); one_light(2); one_light(3);
+    } else {
+        uint32_t l = 0;
+#pragma unroll 1
+        for (; l + 4u <= n_p; l += 4u) { one_light(l); one_light(l + 1u); one_light(l + 2u); one_light(l + 3u); }
+#pragma unroll 1
+        for (; l < n_p; ++l) one_light(l);
+    }
+#pragma unroll 1
+    for (uint32_t l = n_p; l < lt.n; ++l) {
+        const LightDev L = lights[l];
+        const float k = glm_max(0.f, add(add(mul(nx, L.ntx), mul(ny, L.nty)), mul(nz, L.ntz)));
+        sr = add(sr, mul(mul(mul(L.icr, ar), k), 0.318309886183790671537767526745028724f));
+        sg = add(sg, mul(mul(mul(L.icg, ag), k), 0.318309886183790671537767526745028724f));
+        sb = add(sb, mul(mul(mul(L.icb, ab), k), 0.318309886183790671537767526745028724f));
+    }
+    out.r = to_uint(glm_min(sr, 255.f)) & 0xFFu;
+    out.g = to_uint(glm_min(sg, 255.f)) & 0xFFu;
+    out.b = to_uint(glm_min(sb, 255.f)) & 0xFFu;
+    return out;
+}
+#endif // RAST_SHADE_PREP
+
 // Grid: x = segments of SHADE_THREADS * PX * SHADE_GROUPS pixels along a row, y = row of the band,
 // z = frame of the batch -- no thread divides to find its pixel.  A thread owns SHADE_GROUPS groups of PX
 // adjacent pixels, the groups SHADE_THREADS * PX pixels apart.  Phase 1 issues the key loads of ALL its
@@ -885,7 +1018,11 @@ __device__ __forceinline__ void load_keys(const unsigned long long *p, unsigned 
 }
 
 // (forcing 10 or 12 CTAs per SM -- 48 / 40 registers -- measured 7-10 % slower than the 56 registers the compiler picks)
+#if RAST_SHADE_PREP
+template <int PX, bool PRE_NORMALS, bool FLAT, bool PREP = false>
+#else
 template <int PX, bool PRE_NORMALS, bool FLAT>
+#endif
 __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View vw, Batch bt, const __grid_constant__ LightTable lt,
                                                                  const LightDev *__restrict__ lights, uint8_t *__restrict__ rgb, float *__restrict__ depth,
                                                                  uint32_t keep_frame) {
@@ -952,6 +1089,11 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View 
     const float4 *rv = reinterpret_cast<const float4 *>(rv_base);
     const float4 *cn = reinterpret_cast<const float4 *>(cn_base);
     const FrameParams *fp = bt.frames + f;
+#if RAST_SHADE_PREP
+    unsigned long long prep_base = (unsigned long long)(PREP ? bt.prep + (size_t)f * sc.T * PREP_QUADS : nullptr);
+    asm volatile("" : "+l"(prep_base));
+    const float4 *prep = reinterpret_cast<const float4 *>(prep_base);
+#endif
 #pragma unroll 1
     for (uint32_t g = 0; g < GROUPS; ++g) {
         const uint32_t x0 = xb + g * STRIDE;
@@ -966,7 +1108,13 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View 
             const bool cw = __ldg(&fp->wind_clockwise) != 0u;
 #pragma unroll
             for (int k = 0; k < PX; ++k)
-                if (cov & (1u << k)) px[k] = shade_pixel<PRE_NORMALS, FLAT>((uint32_t)keys[k], x0 + k, vw.y0 + row, sc, rv, cn, FLAT ? fp->modelview : fp->normal_m, cw, lt, lights);
+                if (cov & (1u << k)) {
+#if RAST_SHADE_PREP
+                    if (PREP) px[k] = shade_pixel_prep((uint32_t)keys[k], x0 + k, vw.y0 + row, sc, prep, cw, lt, lights);
+                    else
+#endif
+                    px[k] = shade_pixel<PRE_NORMALS, FLAT>((uint32_t)keys[k], x0 + k, vw.y0 + row, sc, rv, cn, FLAT ? fp->modelview : fp->normal_m, cw, lt, lights);
+                }
             if (reset) {
                 if (PX == 4) {
                     *reinterpret_cast<ulonglong2 *>(vis + g * STRIDE) = make_ulonglong2(VIS_EMPTY, VIS_EMPTY);

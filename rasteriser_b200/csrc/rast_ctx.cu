@@ -159,6 +159,11 @@ struct rast_ctx {
     // this batch runs on the context's stream -- both are issue-bound at 66-76 % and fill each other's gaps (two contexts
     // on one GPU measured +13 %; RAST_OVERLAP=0 serialises).
     DeviceBuffer d_rv[2], d_cn[2], d_vis[2];
+#if RAST_SHADE_PREP
+    DeviceBuffer d_prep[2];   // prepared shading records of a batch (kernels.cuh, k_prepare_tris), by pipeline slot like rv / cn
+    bool use_prep = false;    // this call: records fit (decided in draw_frames_impl)
+    bool prep_enabled = true; // RAST_SHADE_PREP_RUNTIME=0 keeps the variant build on the gather path (A/B inside one library)
+#endif
     cudaStream_t front_stream = nullptr;
     cudaEvent_t ev_raster[2] = {nullptr, nullptr}, ev_shade[2] = {nullptr, nullptr};
     bool shade_pending[2] = {false, false};
@@ -267,6 +272,9 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     bt.rv = ctx->d_rv[ps].as<float4>();
     bt.cn = ctx->pre_normals ? ctx->d_cn[ps].as<float4>() : nullptr;
     bt.vis = ctx->d_vis[ps].as<unsigned long long>();
+#if RAST_SHADE_PREP
+    bt.prep = (ctx->use_prep && bt.cn) ? ctx->d_prep[ps].as<float4>() : nullptr;
+#endif
     bt.queue = ctx->d_queue.as<uint2>();
     bt.queue_cap = ctx->queue_cap;
     bt.tiny_max_pixels = ctx->tiny_max_pixels;
@@ -299,6 +307,9 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     ctx->vis_clean_pixels[ps] = vw.band_pixels;
     if (prof) cudaEventRecord(ctx->ev_pass[1], st);
     if (sc.V) rk::k_vertex<<<dim3(grid_for((size_t)sc.V + (bt.cn ? sc.Nn : 0u), 256), count), 256, 0, st>>>(sc, vw, bt);
+#if RAST_SHADE_PREP
+    if (bt.prep && sc.T) { rk::k_prepare_tris<<<dim3(grid_for(sc.T, 128), count), 128, 0, st>>>(sc, bt); ctx->launches++; }
+#endif
     if (prof) cudaEventRecord(ctx->ev_pass[2], st);
     // Raster schedule of this batch.  The screen-tile binned schedule is implemented and parity-tested but measured
     // slower than the bbox-anchored chunk queue on B200 at both ends (1080p Suzanne batch: 28.9 vs 4.3 ms per 720 frames;
@@ -364,6 +375,10 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
             if (bt.cn) rk::k_resolve_shade<4, true, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
             else rk::k_resolve_shade<4, false, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
         } else {
+#if RAST_SHADE_PREP
+            if (bt.cn && bt.prep) rk::k_resolve_shade<1, true, false, true><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
+            else
+#endif
             if (bt.cn) rk::k_resolve_shade<1, true, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
             else rk::k_resolve_shade<1, false, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
         }
@@ -566,6 +581,11 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
     for (int ps = 0; ps < 2; ++ps) {
         RAST_CUDA(ctx, ctx->d_rv[ps].reserve((size_t)nb * ctx->scene.V * sizeof(float4)));
         if ((size_t)ctx->scene.Nn * 8 <= P) RAST_CUDA(ctx, ctx->d_cn[ps].reserve((size_t)nb * ctx->scene.Nn * sizeof(float4)));
+#if RAST_SHADE_PREP
+        // prepared records only where they are small beside the visibility buffer (160 B per triangle against 8 B per pixel)
+        ctx->use_prep = ctx->prep_enabled && !ctx->flat_face && ctx->scene.T > 0 && (size_t)ctx->scene.Nn * 8 <= P && (size_t)ctx->scene.T * rk::PREP_QUADS * 16 <= (size_t)P * 8;
+        if (ctx->use_prep) RAST_CUDA(ctx, ctx->d_prep[ps].reserve((size_t)nb * ctx->scene.T * rk::PREP_QUADS * sizeof(float4)));
+#endif
         if ((size_t)nb * P * 8 > ctx->d_vis[ps].bytes) { ctx->vis_clean_slots[ps] = 0; ctx->vis_dirty_slot[ps] = -1; }
         RAST_CUDA(ctx, ctx->d_vis[ps].reserve((size_t)nb * P * 8));
     }
@@ -735,6 +755,9 @@ int rast_create(int device, rast_ctx **out) {
     if (const char *e = getenv("RAST_SHADE_PX")) ctx->shade_px = atoi(e) == 4 ? 4 : 1;
     if (const char *e = getenv("RAST_SPARSE_COPY")) ctx->sparse_copy = atoi(e) != 0;
     if (const char *e = getenv("RAST_OVERLAP")) ctx->overlap = atoi(e) != 0;
+#if RAST_SHADE_PREP
+    if (const char *e = getenv("RAST_SHADE_PREP_RUNTIME")) ctx->prep_enabled = atoi(e) != 0;
+#endif
     {
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
         ctx->host_threads = std::min(4u, std::max(1u, hw / 2u)) - 1u; // measured on the 16-core host: 4 / 8 / 16 threads -> 5.49 / 5.38 / 5.30 k frames/s (memory-bound)
@@ -755,6 +778,10 @@ void rast_destroy(rast_ctx *ctx) {
     DeviceBuffer *dev[] = {&ctx->d_pos, &ctx->d_nrm, &ctx->d_uv, &ctx->d_vidx, &ctx->d_attr, &ctx->d_mats, &ctx->d_texels, &ctx->d_frames[0], &ctx->d_frames[1], &ctx->d_lights[0], &ctx->d_lights[1],
                            &ctx->d_rv[0], &ctx->d_rv[1], &ctx->d_cn[0], &ctx->d_cn[1], &ctx->d_tiles, &ctx->d_list, &ctx->d_items, &ctx->d_vis[0], &ctx->d_vis[1], &ctx->d_bbox[0], &ctx->d_bbox[1], &ctx->d_queue, &ctx->d_counters, &ctx->d_aux, &ctx->d_rgb[0], &ctx->d_rgb[1], &ctx->d_depth[0], &ctx->d_depth[1]};
     for (DeviceBuffer *b : dev) b->release();
+#if RAST_SHADE_PREP
+    ctx->d_prep[0].release();
+    ctx->d_prep[1].release();
+#endif
     ctx->h_frames.release();
     ctx->h_lights.release();
     ctx->h_status.release();

@@ -2,7 +2,7 @@
 //
 // The development container has no GPU.  The arithmetic of the frame path lives in RAST_HD (__host__ __device__) functions
 // -- raster_vertex, signed_area_2d, bounding_box, tri_setup, edges / candidate / fragment, stage_item / raster_item (the warp
-// rasteriser's inner loop, one lane at a time), shade_pixel, sample_texture -- so this file, compiled by nvcc for the host,
+// rasteriser's inner loop, one lane at a time), shade_pixel, sample_texture, and the variants' rast_tight_bbox, prepare_triangle / shade_pixel_prep -- so this file, compiled by nvcc for the host,
 // drives those very functions serially in the order the kernels launch them and tests/test_emu_device_fns.py compares the
 // result with the oracle bit for bit.  What it does NOT cover: the __global__ wrappers (grids, staging through shared
 // memory, votes, atomics, streams) and the device flavour of exact:: (the _rn intrinsics and the shared-reciprocal division,
@@ -17,6 +17,9 @@
 #ifndef RAST_TIGHT_TINY
 #define RAST_TIGHT_TINY 1 // the host driver below calls rast_tight_bbox only when asked to (flag bit 0)
 #endif
+#ifndef RAST_SHADE_PREP
+#define RAST_SHADE_PREP 1 // prepare_triangle / shade_pixel_prep are driven only when asked to (flag bit 5)
+#endif
 #include "../rasteriser_b200/csrc/kernels.cuh"
 
 struct EmuMaterial { // = rast_material (include/rast.h): planar normalised texels
@@ -25,7 +28,7 @@ struct EmuMaterial { // = rast_material (include/rast.h): planar normalised texe
     const float *texels;
 };
 
-enum { EMU_TIGHT = 1, EMU_PRE_NORMALS = 2, EMU_EARLY_Z = 4, EMU_ALL_CHUNKS = 8, EMU_FLAT_FACE = 16 };
+enum { EMU_TIGHT = 1, EMU_PRE_NORMALS = 2, EMU_EARLY_Z = 4, EMU_ALL_CHUNKS = 8, EMU_FLAT_FACE = 16, EMU_PREP = 32 };
 
 // One frame.  lights: n x 10 floats (rast_light: direction, intensity, colour, trans_dir -- trans_dir already computed by
 // rast_transform_lights).  Outputs: rgb planar [3][rows][W], depth [rows][W], tri_ids [rows][W] for the band [y0, y1).
@@ -136,6 +139,13 @@ extern "C" int emu_draw(const float *pos, uint32_t V, const float *nrm, uint32_t
     }
     delete stg;
 
+    // ---- k_prepare_tris (variant RAST_SHADE_PREP) ----
+    std::vector<float4> prep;
+    if (flags & EMU_PREP) {
+        prep.resize((size_t)T * PREP_QUADS);
+        for (uint64_t t = 0; t < T; ++t) prepare_triangle((uint32_t)t, sc, rv.data(), cn.data(), prep.data() + t * PREP_QUADS);
+    }
+
     // ---- k_resolve_shade ----
     const bool pre = (flags & EMU_PRE_NORMALS) != 0, flat = (flags & EMU_FLAT_FACE) != 0;
     for (uint32_t y = y0; y < y1; ++y)
@@ -146,7 +156,8 @@ extern "C" int emu_draw(const float *pos, uint32_t V, const float *nrm, uint32_t
             uint32_t id = INVALID_TRI;
             if (vis[i] != VIS_EMPTY) {
                 id = (uint32_t)vis[i];
-                if (flat) px = shade_pixel<false, true>(id, x, y, sc, rv.data(), cn.data(), modelview, wind_clockwise != 0, lt, ld.data());
+                if (flags & EMU_PREP) px = shade_pixel_prep(id, x, y, sc, prep.data(), wind_clockwise != 0, lt, ld.data());
+                else if (flat) px = shade_pixel<false, true>(id, x, y, sc, rv.data(), cn.data(), modelview, wind_clockwise != 0, lt, ld.data());
                 else if (pre) px = shade_pixel<true, false>(id, x, y, sc, rv.data(), cn.data(), normal_m, wind_clockwise != 0, lt, ld.data());
                 else px = shade_pixel<false, false>(id, x, y, sc, rv.data(), cn.data(), normal_m, wind_clockwise != 0, lt, ld.data());
             }

@@ -2,8 +2,8 @@
 
 tests/emu_device_fns.cu drives the RAST_HD functions of rasteriser_b200/csrc/kernels.cuh -- raster_vertex, signed_area_2d,
 bounding_box, tri_setup, edges / candidate / fragment, stage_item / raster_item (the warp rasteriser's inner loop, lane by
-lane), shade_pixel, sample_texture and, with the `tight` flag, rast_tight_bbox -- in the order the kernels launch them.  The
-result must equal the oracle's bit for bit (winning triangle, depth bits, colour bytes).  This is how kernel-logic changes
+lane), shade_pixel, sample_texture and, by flag, the variants' rast_tight_bbox and prepare_triangle / shade_pixel_prep -- in
+the order the kernels launch them.  The result must equal the oracle's bit for bit (winning triangle, depth bits, colour bytes).  This is how kernel-logic changes
 are checked in the development container, which has no GPU; the -m gpu tests remain the parity tests proper."""
 import ctypes as C
 import os
@@ -20,7 +20,7 @@ from test_parity_gpu_fuzz import _case
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "emu_device_fns.cu")
 CSRC = os.path.join(ROOT, "rasteriser_b200", "csrc")
-TIGHT, PRE_NORMALS, EARLY_Z, ALL_CHUNKS, FLAT_FACE = 1, 2, 4, 8, 16
+TIGHT, PRE_NORMALS, EARLY_Z, ALL_CHUNKS, FLAT_FACE, PREP = 1, 2, 4, 8, 16, 32
 
 
 class EmuMaterial(C.Structure):
@@ -81,7 +81,7 @@ def assert_exact(got, want, what):
     assert np.array_equal(got[0], want[0]), "%s: colour differs at %d samples" % (what, int((got[0] != want[0]).sum()))
 
 
-@pytest.mark.parametrize("flags", [PRE_NORMALS, 0, PRE_NORMALS | TIGHT, PRE_NORMALS | ALL_CHUNKS, PRE_NORMALS | ALL_CHUNKS | EARLY_Z])
+@pytest.mark.parametrize("flags", [PRE_NORMALS, 0, PRE_NORMALS | TIGHT, PRE_NORMALS | ALL_CHUNKS, PRE_NORMALS | ALL_CHUNKS | EARLY_Z, PREP, PREP | TIGHT])
 def test_golden_cases_on_the_host(emu, flags):
     """Every golden case of tests/golden/cases.json small enough for the CPU suite: equal to the oracle AND to the hashes the
     reference itself produced."""
@@ -104,7 +104,7 @@ def test_fuzz_cases_on_the_host(emu, seed):
     up to 70 lights, negative intensities; tiny path with and without the tight-bbox rule, chunk path with and without early z."""
     scene, lights, oa, mode, kind = _case(seed)
     want = orc.oracle_draw(scene, lights, oa, threads=2)
-    for flags, tiny in [(PRE_NORMALS, 16), (TIGHT, 64), (PRE_NORMALS | TIGHT, 1 << 30), (ALL_CHUNKS | EARLY_Z, 16)]:
+    for flags, tiny in [(PRE_NORMALS, 16), (TIGHT, 64), (PRE_NORMALS | TIGHT, 1 << 30), (ALL_CHUNKS | EARLY_Z, 16), (PREP | TIGHT, 16)]:
         assert_exact(emu_draw(emu, scene, lights, oa, flags, tiny), want, "seed %d (%s) flags %d" % (seed, kind, flags))
 
 
