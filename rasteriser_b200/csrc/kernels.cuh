@@ -802,7 +802,7 @@ RAST_HD Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t y, const Scene &sc
 
     // interpolation_coords + camera-space depth (drawing.cpp:125-128)
     const float i0 = mul(v0.w, b0), i1 = mul(v1.w, b1), i2 = mul(v2.w, b2);
-    const float d = div(1.f, add(add(i0, i1), i2));
+    const float d = rcp(add(add(i0, i1), i2));
 
     // Material::sample (material.cpp:11-26).  The texel loads are issued before the normal is interpolated and normalised (a
     // division and a square root, ~80 instructions) so that their latency is covered by this warp's own arithmetic
@@ -822,7 +822,7 @@ RAST_HD Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t y, const Scene &sc
     const float mx = FLAT ? fx : mul(d, add(add(mul(i0, n0.x), mul(i1, n1.x)), mul(i2, n2.x)));
     const float my = FLAT ? fy : mul(d, add(add(mul(i0, n0.y), mul(i1, n1.y)), mul(i2, n2.y)));
     const float mz = FLAT ? fz : mul(d, add(add(mul(i0, n0.z), mul(i1, n1.z)), mul(i2, n2.z)));
-    const float inv = div(1.f, fsqrt(add(add(mul(mx, mx), mul(my, my)), mul(mz, mz))));
+    const float inv = rcp(fsqrt(add(add(mul(mx, mx), mul(my, my)), mul(mz, mz))));
     float nx = mul(mx, inv), ny = mul(my, inv), nz = mul(mz, inv);
     if (wind_clockwise) { nx = -nx; ny = -ny; nz = -nz; }
 
@@ -929,7 +929,7 @@ RAST_HD Shaded shade_pixel_prep(uint32_t tri, uint32_t x, uint32_t y, const Scen
     out.depth = add(add(mul(q4.x, b0), mul(q4.y, b1)), mul(q4.z, b2));
 
     const float i0 = mul(q4.w, b0), i1 = mul(q5.x, b1), i2 = mul(q5.y, b2);
-    const float d = div(1.f, add(add(i0, i1), i2));
+    const float d = rcp(add(add(i0, i1), i2));
 
     float ar = mk.x, ag = mk.y, ab = mk.z;
     if (f2u(mk.w) != 0u) {
@@ -945,7 +945,7 @@ RAST_HD Shaded shade_pixel_prep(uint32_t tri, uint32_t x, uint32_t y, const Scen
     const float mx = mul(d, add(add(mul(i0, q7.x), mul(i1, q7.w)), mul(i2, q8.z)));
     const float my = mul(d, add(add(mul(i0, q7.y), mul(i1, q8.x)), mul(i2, q8.w)));
     const float mz = mul(d, add(add(mul(i0, q7.z), mul(i1, q8.y)), mul(i2, n2z)));
-    const float inv = div(1.f, fsqrt(add(add(mul(mx, mx), mul(my, my)), mul(mz, mz))));
+    const float inv = rcp(fsqrt(add(add(mul(mx, mx), mul(my, my)), mul(mz, mz))));
     float nx = mul(mx, inv), ny = mul(my, inv), nz = mul(mz, inv);
     if (wind_clockwise) { nx = -nx; ny = -ny; nz = -nz; }
 
