@@ -27,8 +27,8 @@ class EmuMaterial(C.Structure):
     _fields_ = [("kd", C.c_float * 3), ("has_texture", C.c_int32), ("tex_w", C.c_int32), ("tex_h", C.c_int32), ("texels", C.c_void_p)]
 
 
-@pytest.fixture(scope="module")
-def emu():
+def load_emu():
+    """Build (when stale) and load build/libemu.so."""
     out = os.path.join(ROOT, "build", "libemu.so")
     deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
@@ -41,6 +41,11 @@ def emu():
                              C.POINTER(EmuMaterial), C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                              C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     return lib
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return load_emu()
 
 
 def emu_draw(emu, scene, lights7, oa, flags, tiny_max=16, band=None):
