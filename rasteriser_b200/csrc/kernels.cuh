@@ -19,6 +19,13 @@
 #ifndef RAST_TIGHT_TINY
 #define RAST_TIGHT_TINY 0
 #endif
+// Timing probes (never in a product build; outputs are wrong): k_setup without its atomics / without its pixel loops
+#ifndef RAST_PROBE_NO_ATOMIC
+#define RAST_PROBE_NO_ATOMIC 0
+#endif
+#ifndef RAST_PROBE_NO_WALK
+#define RAST_PROBE_NO_WALK 0
+#endif
 // Variant switch: the shade pass reads one prepared 160-byte record per (frame, triangle) -- vertices, the pixel-invariant
 // edge differences, area and its refined reciprocal, depths, 1/w, camera normals, uvs, material -- written once per batch by
 // k_prepare_tris, instead of gathering record -> vertices / normals / uvs and recomputing the differences for every pixel
@@ -239,6 +246,9 @@ RAST_HD void test_and_commit(const TriSetup &s, uint32_t x, uint32_t y, uint32_t
     if (!candidate(s, e0, e1, e2)) return;
     if (!fragment(s, e0, e1, e2, b0, b1, b2, z)) return;
     const unsigned long long key = ((unsigned long long)depth_key(z) << 32) | tri;
+#if RAST_PROBE_NO_ATOMIC
+    if (key != 0ull) return; // timing probe only (never true for a real key): everything but the atomic
+#endif
     RAST_ATOMIC_MIN64(vis_row0 + (size_t)(y - vw.y0) * vw.W + x, key);
 }
 
@@ -367,13 +377,24 @@ __device__ RAST_SETUP_INLINE void setup_triangle(uint32_t t, uint32_t f, float4 
         // triangle between sample points is dropped here without a single pixel test
         if (!rast_tight_bbox(v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, s.literal ? 0.f : s.area, &wx0, &wy0, &wx1, &wy1)) return;
 #endif
+#if RAST_PROBE_NO_WALK
+        if (wx0 != 0xFFFFFFFFu) return; // timing probe only: the per-triangle cost without any pixel test
+#endif
         for (uint32_t y = wy0; y <= wy1; ++y)
             for (uint32_t x = wx0; x <= wx1; ++x) test_and_commit(s, x, y, t, vis, vw);
     }
 }
 
+#ifndef RAST_SETUP_MIN_BLOCKS
+#define RAST_SETUP_MIN_BLOCKS 0 // variant: resident CTAs per SM asked of the register allocator (0 = the compiler's choice, 48 registers / 5 CTAs)
+#endif
 template <bool BINS>
-__global__ void __launch_bounds__(256) k_setup(const __grid_constant__ Scene sc, const __grid_constant__ View vw, const __grid_constant__ Batch bt,
+#if RAST_SETUP_MIN_BLOCKS > 0
+__global__ void __launch_bounds__(256, RAST_SETUP_MIN_BLOCKS) k_setup(
+#else
+__global__ void __launch_bounds__(256) k_setup(
+#endif
+const __grid_constant__ Scene sc, const __grid_constant__ View vw, const __grid_constant__ Batch bt,
                                                const __grid_constant__ TileBins tb) {
     const uint32_t f = blockIdx.y;
     const uint64_t t0 = (uint64_t)blockIdx.x * (256 * SETUP_TRIS) + threadIdx.x;
