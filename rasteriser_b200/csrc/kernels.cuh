@@ -14,10 +14,11 @@
 
 #include "exact.cuh"
 
-// Variant switch (tools/build_variants.py): drop provably empty border columns / rows of small bboxes in k_setup
-// (tight_bbox.h).  Off in the default build until it has been timed on a B200; parity is by proof, not by measurement.
+// k_setup drops the provably empty border columns / rows of a small bbox before walking it (tight_bbox.h: proof, CPU brute
+// force, host emulation; on a B200: k_setup 0.154 -> 0.128 ms on 8.0 M triangles, 0.709 -> 0.592 ms on 49.9 M, identical
+// frames).  -DRAST_TIGHT_TINY=0 builds the literal walk of the reference's whole bbox.
 #ifndef RAST_TIGHT_TINY
-#define RAST_TIGHT_TINY 0
+#define RAST_TIGHT_TINY 1
 #endif
 // Timing probes (never in a product build; outputs are wrong): k_setup without its atomics / without its pixel loops
 #ifndef RAST_PROBE_NO_ATOMIC
@@ -26,14 +27,15 @@
 #ifndef RAST_PROBE_NO_WALK
 #define RAST_PROBE_NO_WALK 0
 #endif
-// Variant switch: the shade pass reads one prepared 160-byte record per (frame, triangle) -- vertices, the pixel-invariant
-// edge differences, area and its refined reciprocal, depths, 1/w, camera normals, uvs, material -- written once per batch by
-// k_prepare_tris, instead of gathering record -> vertices / normals / uvs and recomputing the differences for every pixel
-// (about 44 of the ~330 instructions of a covered pixel and one level of dependent loads).  Hoisting rounded values does not
-// change them, so the bits are the same (tests/test_emu_device_fns.py runs both flavours against the oracle).  Only for
-// meshes whose records fit beside the visibility buffer; off in the default build until timed on a B200.
+// The shade pass reads one prepared 160-byte record per (frame, triangle) -- vertices, the pixel-invariant edge differences,
+// area and its refined reciprocal, depths, 1/w, camera normals, uvs, material -- written once per batch by k_prepare_tris,
+// instead of gathering record -> vertices / normals / uvs and recomputing the differences for every pixel (about 40 of the
+// ~330 instructions of a covered pixel and one level of dependent loads).  Hoisting rounded values does not change them, so
+// the bits are the same (tests/test_emu_device_fns.py runs both flavours against the oracle; on a B200 the 1080p spin step's
+// shade pass 1.44 -> 1.33 ms per 120 frames with identical frames).  The host enables it per call where the records fit
+// beside the visibility buffer and the extra launch pays (draw_frames_impl).  -DRAST_SHADE_PREP=0 builds without it.
 #ifndef RAST_SHADE_PREP
-#define RAST_SHADE_PREP 0
+#define RAST_SHADE_PREP 1
 #endif
 #if RAST_TIGHT_TINY
 #include "tight_bbox.h"
