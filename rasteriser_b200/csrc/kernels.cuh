@@ -312,6 +312,10 @@ constexpr int SETUP_TRIS = RAST_SETUP_TRIS; // triangles per thread: all index a
                                             // (k_setup on 8 M / 50 M triangles, out-of-line body: 1 -> 0.187 / 0.898 ms, 2 -> 0.188 / 0.847,
                                             //  4 -> 0.225 / 1.011, 8 -> 0.323 / 1.422; inlined body: 1 -> 0.154 / 0.706, 2 -> 0.175 / 0.817.  Once the queue
                                             //  reservation is one atomic per warp, more triangles per thread only cost registers.)
+// With the tight bbox walk the pixel loops are short and the kernel is bound by the latency of its two dependent load stages (ncu: 58 % of
+// the stall samples): two triangles per thread then pay on big meshes (8.0 M triangles: 0.128 -> 0.114 ms; 3 -> 0.120, 4 -> 0.149), while a
+// 968-triangle frame loses a few microseconds -- the host picks k_setup<.., 2> from SETUP_TRIS2_MIN_TRIANGLES triangles on.
+constexpr uint64_t SETUP_TRIS2_MIN_TRIANGLES = 1ull << 20;
 
 #ifndef RAST_SETUP_INLINE
 #define RAST_SETUP_INLINE __forceinline__
@@ -390,7 +394,7 @@ __device__ RAST_SETUP_INLINE void setup_triangle(uint32_t t, uint32_t f, float4 
 #ifndef RAST_SETUP_MIN_BLOCKS
 #define RAST_SETUP_MIN_BLOCKS 0 // variant: resident CTAs per SM asked of the register allocator (0 = the compiler's choice, 48 registers / 5 CTAs)
 #endif
-template <bool BINS>
+template <bool BINS, int TRIS = SETUP_TRIS>
 #if RAST_SETUP_MIN_BLOCKS > 0
 __global__ void __launch_bounds__(256, RAST_SETUP_MIN_BLOCKS) k_setup(
 #else
@@ -399,23 +403,23 @@ __global__ void __launch_bounds__(256) k_setup(
 const __grid_constant__ Scene sc, const __grid_constant__ View vw, const __grid_constant__ Batch bt,
                                                const __grid_constant__ TileBins tb) {
     const uint32_t f = blockIdx.y;
-    const uint64_t t0 = (uint64_t)blockIdx.x * (256 * SETUP_TRIS) + threadIdx.x;
+    const uint64_t t0 = (uint64_t)blockIdx.x * (256 * TRIS) + threadIdx.x;
     const float4 *rv = bt.rv + (size_t)f * sc.V;
     // phase 1: the (coalesced) index loads of all this thread's triangles, then all the vertex gathers
-    int i0[SETUP_TRIS], i1[SETUP_TRIS], i2[SETUP_TRIS];
+    int i0[TRIS], i1[TRIS], i2[TRIS];
 #pragma unroll
-    for (int k = 0; k < SETUP_TRIS; ++k) {
+    for (int k = 0; k < TRIS; ++k) {
         const uint64_t t = t0 + (uint64_t)k * 256;
         const bool in = t < sc.T;
         i0[k] = in ? sc.vidx0[t] : 0; i1[k] = in ? sc.vidx1[t] : 0; i2[k] = in ? sc.vidx2[t] : 0;
     }
-    float4 v0[SETUP_TRIS], v1[SETUP_TRIS], v2[SETUP_TRIS];
+    float4 v0[TRIS], v1[TRIS], v2[TRIS];
 #pragma unroll
-    for (int k = 0; k < SETUP_TRIS; ++k) { v0[k] = rv[i0[k]]; v1[k] = rv[i1[k]]; v2[k] = rv[i2[k]]; }
+    for (int k = 0; k < TRIS; ++k) { v0[k] = rv[i0[k]]; v1[k] = rv[i1[k]]; v2[k] = rv[i2[k]]; }
     const bool cw = bt.frames[f].wind_clockwise != 0u;
     // phase 2
 #pragma unroll
-    for (int k = 0; k < SETUP_TRIS; ++k) {
+    for (int k = 0; k < TRIS; ++k) {
         const uint64_t t = t0 + (uint64_t)k * 256;
         if (t < sc.T) setup_triangle<BINS>((uint32_t)t, f, v0[k], v1[k], v2[k], cw, vw, bt, tb);
     }

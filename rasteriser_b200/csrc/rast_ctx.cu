@@ -336,6 +336,7 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     }
     if (sc.T && vw.band_pixels) {
         if (tile_mode) rk::k_setup<true><<<dim3(grid_for(sc.T, 256 * rk::SETUP_TRIS), count), 256, 0, st>>>(sc, vw, bt, tb);
+        else if (rk::SETUP_TRIS == 1 && sc.T >= rk::SETUP_TRIS2_MIN_TRIANGLES) rk::k_setup<false, 2><<<dim3(grid_for(sc.T, 256 * 2), count), 256, 0, st>>>(sc, vw, bt, tb);
         else rk::k_setup<false><<<dim3(grid_for(sc.T, 256 * rk::SETUP_TRIS), count), 256, 0, st>>>(sc, vw, bt, tb);
     }
     if (prof) cudaEventRecord(ctx->ev_pass[3], st);
