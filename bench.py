@@ -457,6 +457,8 @@ def main():
                 issue = {"issue_active_pct": tr[kname]["issue_active_pct"], "l1tex_throughput_pct": tr[kname].get("l1tex_throughput_pct"),
                          "warp_instructions_per_launch": tr[kname].get("warp_instructions_per_launch"),
                          "source": "ncu --set full capture under profiles/ (smsp__issue_active.avg.pct_of_peak_sustained_active)"}
+                if "note" in tr[kname]:
+                    issue["note"] = tr[kname]["note"]
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": {"vertex": "k_vertex", "setup": "k_setup", "raster": "k_raster_chunks", "shade": "k_resolve_shade", "clear": "k_clear"}[dominant],
