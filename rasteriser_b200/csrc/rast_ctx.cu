@@ -272,8 +272,13 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     bt.rv = ctx->d_rv[ps].as<float4>();
     bt.cn = ctx->pre_normals ? ctx->d_cn[ps].as<float4>() : nullptr;
     bt.vis = ctx->d_vis[ps].as<unsigned long long>();
+    // 4 adjacent pixels per lane (uchar4 / float4 stores) is slower into local memory but faster when
+    // the output is a band of a larger -- typically another GPU's -- image: 128-byte instead of 32-byte stores over NVLink
+    // (8K overdraw frame on 8 GPUs: 1.13 -> 1.05 ms)
+    const bool want_vec = ctx->shade_px == 4 || vw.out_plane != vw.band_pixels;
+    const bool vec = !ctx->flat_face && want_vec && (vw.W % 4u == 0u) && (((uintptr_t)rgb_dev & 15u) == 0u) && (((uintptr_t)depth_dev & 15u) == 0u);
 #if RAST_SHADE_PREP
-    bt.prep = (ctx->use_prep && bt.cn) ? ctx->d_prep[ps].as<float4>() : nullptr;
+    bt.prep = (ctx->use_prep && bt.cn && !vec) ? ctx->d_prep[ps].as<float4>() : nullptr; // the 4-pixel shade variant gathers; no records for it
 #endif
     bt.queue = ctx->d_queue.as<uint2>();
     bt.queue_cap = ctx->queue_cap;
@@ -361,11 +366,6 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     }
     if (bbox_dev) cudaMemsetAsync(bbox_dev, 0xFF, (size_t)count * 16, st);
     if (vw.band_pixels) {
-        // 4 adjacent pixels per lane (uchar4 / float4 stores) is slower into local memory but faster when
-        // the output is a band of a larger -- typically another GPU's -- image: 128-byte instead of 32-byte stores over NVLink
-        // (8K overdraw frame on 8 GPUs: 1.13 -> 1.05 ms)
-        const bool want_vec = ctx->shade_px == 4 || vw.out_plane != vw.band_pixels;
-        const bool vec = !ctx->flat_face && want_vec && (vw.W % 4u == 0u) && (((uintptr_t)rgb_dev & 15u) == 0u) && (((uintptr_t)depth_dev & 15u) == 0u);
         const rk::LightDev *lights = ctx->d_lights[ctx->cs].as<rk::LightDev>();
         const uint32_t rows = vw.y1 - vw.y0;
         const dim3 grid(grid_for(vw.W, rk::SHADE_THREADS * rk::shade_groups(vec ? 4 : 1) * (vec ? 4 : 1)), rows, count);
