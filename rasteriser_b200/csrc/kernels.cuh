@@ -43,6 +43,15 @@
 
 // Device-only primitives used inside the RAST_HD functions, with single-lane host stand-ins for tests/emu_device_fns.cu
 // (a host "warp" is one lane at a time: a vote is the lane's own predicate, an atomic min a plain min).
+// Variant switch (off by default, not yet timed): block-level early depth rejection in the chunk rasteriser (raster_item).
+#ifndef RAST_BLOCK_Z
+#define RAST_BLOCK_Z 0
+#endif
+#ifdef __CUDA_ARCH__
+#define RAST_WARP_MAX_U32(v) __reduce_max_sync(0xFFFFFFFFu, (v))
+#else
+#define RAST_WARP_MAX_U32(v) (v)
+#endif
 #ifdef __CUDA_ARCH__
 #define RAST_ANY(p) __any_sync(0xFFFFFFFFu, (p))
 #define RAST_ATOMIC_MIN64(ptr, v) atomicMin((ptr), (v))
@@ -441,7 +450,7 @@ const __grid_constant__ Scene sc, const __grid_constant__ View vw, const __grid_
 // Lanes own 2x2 pixel quads of a 16x8 block, so the per-pixel differences (p - a) and half of the products
 // of edge() are shared inside the quad; a ballot skips blocks no lane may cover.
 constexpr int RASTER_WARPS = 8;
-constexpr int STAGE_FIELDS = 27;
+constexpr int STAGE_FIELDS = RAST_BLOCK_Z ? 31 : 27;
 constexpr unsigned long long EARLY_Z_OVERDRAW = 6;
 
 // Conservative rejection of one 16x8 block (pixel extent [xa,xb] x [ya,yb]) against one sign-folded edge.
@@ -486,6 +495,38 @@ RAST_HD void stage_item(StagedTris &stg, uint32_t lane, uint32_t tri, uint32_t f
     const bool usable = !s.literal && rcp > 0.f && rcp < exact::i2f(0x7f800000) && zmax < exact::i2f(0x7f800000);
     stg.w[21][lane] = exact::f2u(usable ? rcp : 0.f);
     stg.w[22][lane] = exact::f2u(usable ? fmaf(zmax, 1.9073486328125e-06f /* 2^-19 */, 1e-37f) : exact::i2f(0x7f800000));
+#if RAST_BLOCK_Z
+    // Depth plane of the item for the block-level rejection in raster_item: z as an affine function of the pixel, anchored at the
+    // rectangle's first pixel, and a margin M that covers every rounding between this plane and the depth the exact path would
+    // compute for an ACCEPTED pixel p of the rectangle:  z(p) >= Zo + gx (p.x - rx0) + gy (p.y - ry0) - M.
+    // Derivation (u = 2^-24, A = folded area, S = wt DY + ht DX as in tight_bbox.h, Q = (S + wt ht + 32 (wt + ht)) / A):
+    //   exact z(p) against the real-arithmetic plane: numerators off by <= errE ~ 4uS, area by errA ~ 8u wt ht, three
+    //   divisions, five rounded operations, accepted pixels have 0 <= b_k <= 1 + 3 errE / A       -> zmax u (108.3 Q + 16)
+    //   Zo = z_est at the anchor, which may lie far outside the triangle (|e_k| <= S)                -> zmax u (29.8 Q + 26.5 Q^2)
+    //   the two gradients (fma chains of z_k d_k, times 1/A), over at most 31 pixels each            -> zmax u (39.6 Q + 53 Q^2)
+    //   evaluating the plane in fp32 at a corner                                                      -> zmax u 20 Q
+    // M = zmax u (256 Q + 128 Q^2 + 32) + 1e-30 bounds the sum with room to spare; ill-conditioned items (Q > 1000, unusable
+    // reciprocal, non-finite depths) get M = inf, i.e. are never rejected by the block test.  Only used to SKIP work.
+    {
+        const float minx = fminf(fminf(s.x0, s.x1), s.x2), maxx = fmaxf(fmaxf(s.x0, s.x1), s.x2);
+        const float miny = fminf(fminf(s.y0, s.y1), s.y2), maxy = fmaxf(fmaxf(s.y0, s.y1), s.y2);
+        const float wt = maxx - minx, ht = maxy - miny;
+        const float fx0 = (float)rx0, fx1 = (float)rx1, fy0 = (float)ry0, fy1 = (float)ry1;
+        const float DX = fmaxf(fx1 - minx, maxx - fx0), DY = fmaxf(fy1 - miny, maxy - fy0);
+        const float Q = (wt * DY + ht * DX + wt * ht + 32.f * (wt + ht)) * rcp;
+        float e0, e1, e2;
+        edges(s, fx0, fy0, e0, e1, e2);
+        const float Zo = fmaf(s.z2, e2, fmaf(s.z1, e1, s.z0 * e0)) * rcp;
+        const float gx = -fmaf(s.z2, s.d01y, fmaf(s.z1, s.d20y, s.z0 * s.d12y)) * rcp; // d e_k / d px = -d_ky
+        const float gy = fmaf(s.z2, s.d01x, fmaf(s.z1, s.d20x, s.z0 * s.d12x)) * rcp;  // d e_k / d py = +d_kx
+        const bool ok = usable && Q <= 1000.f && Zo == Zo && fabsf(Zo) < exact::i2f(0x7f800000) && fabsf(gx) < exact::i2f(0x7f800000) && fabsf(gy) < exact::i2f(0x7f800000);
+        const float M = ok ? fmaf(zmax * 5.9604644775390625e-08f /* u */, fmaf(Q, fmaf(Q, 128.f, 256.f), 32.f), 1e-30f) : exact::i2f(0x7f800000);
+        stg.w[27][lane] = exact::f2u(ok ? Zo : 0.f);
+        stg.w[28][lane] = exact::f2u(ok ? gx : 0.f);
+        stg.w[29][lane] = exact::f2u(ok ? gy : 0.f);
+        stg.w[30][lane] = exact::f2u(M);
+    }
+#endif
     // which of the 4 x 2 blocks can contain a candidate pixel at all (bit = strip * 2 + column)
     uint32_t live = 0u;
     if (tri != INVALID_TRI) {
@@ -531,6 +572,9 @@ RAST_HD void raster_item(const StagedTris &stg, uint32_t it, uint32_t lane, cons
     s.rcp1 = exact::u2f(stg.w[25][it]);
     s.div_ok = stg.w[26][it] != 0u;
     const float rcp_area = exact::u2f(stg.w[21][it]), z_margin = exact::u2f(stg.w[22][it]);
+#if RAST_BLOCK_Z
+    const float bz_o = exact::u2f(stg.w[27][it]), bz_gx = exact::u2f(stg.w[28][it]), bz_gy = exact::u2f(stg.w[29][it]), bz_m = exact::u2f(stg.w[30][it]);
+#endif
     const uint32_t rect0 = stg.w[17][it], rect1 = stg.w[18][it], org = stg.w[24][it];
     const uint32_t rx0 = rect0 & 0xFFFFu, ry0 = rect0 >> 16, rx1 = rect1 & 0xFFFFu, ry1 = rect1 >> 16, ox = org & 0xFFFFu, oy = org >> 16;
     unsigned long long *vis = TILE_MODE ? nullptr : vis_all + (size_t)stg.w[20][it] * vw.band_pixels;
@@ -549,6 +593,38 @@ RAST_HD void raster_item(const StagedTris &stg, uint32_t it, uint32_t lane, cons
         for (uint32_t column = 0; column < 2u; ++column) {
             if (((live >> (strip * 2u + column)) & 1u) == 0u) continue;
             const uint32_t x = ox + column * 16u + qx;
+#if RAST_BLOCK_Z
+            // Block-level depth rejection: if the smallest depth the item's plane can take on this block, less the margin, is
+            // behind the LARGEST depth stored at the block's pixels (a stored depth only ever decreases, so a stale read is
+            // conservative), every fragment of the block would lose its atomicMin: the edge evaluation is skipped for all 128 pixels.
+            uint32_t bz_hi[4] = {0u, 0u, 0u, 0u};
+            bool bz_loaded = false;
+            if (!TILE_MODE && early_z) {
+                const uint32_t in4 = ymask & (((x >= rx0 && x <= rx1) ? 5u : 0u) | ((x + 1u >= rx0 && x + 1u <= rx1) ? 10u : 0u));
+                const unsigned long long *q0 = vis + (size_t)(y - vw.y0) * vw.W + x;
+                uint32_t mine = 0u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (in4 & (1u << k)) {
+                        bz_hi[k] = RAST_LDCG32(reinterpret_cast<const uint32_t *>(q0 + (k >> 1) * (size_t)vw.W + (k & 1)) + 1);
+                        mine = bz_hi[k] > mine ? bz_hi[k] : mine;
+                    }
+                }
+                bz_loaded = true;
+                const uint32_t kmax = RAST_WARP_MAX_U32(mine); // empty pixel = 0xFFFFFFFF: nothing is rejected
+                if (kmax != 0xFFFFFFFFu) {
+                    const uint32_t bxa = max(ox + column * 16u, rx0), bxb = min(ox + column * 16u + 15u, rx1);
+                    const uint32_t bya = max(oy + strip * 8u, ry0), byb = min(oy + strip * 8u + 7u, ry1);
+                    const float dxa = (float)(bxa - rx0), dxb = (float)(bxb - rx0), dya = (float)(bya - ry0), dyb = (float)(byb - ry0);
+#ifndef RAST_BLOCK_Z_TEST_BIAS
+#define RAST_BLOCK_Z_TEST_BIAS 0.f // tests/test_emu_device_fns.py builds with a positive bias to show that a wrong bound is caught
+#endif
+                    const float lb = bz_o + fminf(bz_gx * dxa, bz_gx * dxb) + fminf(bz_gy * dya, bz_gy * dyb) - bz_m + RAST_BLOCK_Z_TEST_BIAS;
+                    const uint32_t far_bits = (kmax & 0x80000000u) ? (kmax ^ 0x80000000u) : ~kmax; // inverse of depth_key
+                    if (lb > exact::u2f(far_bits)) continue;
+                }
+            }
+#endif
             const float pxa = (float)x, pxb = (float)(x + 1u);
             const float c0a = mul(s.d12y, sub(pxa, s.x1)), c0b = mul(s.d12y, sub(pxb, s.x1));
             const float c1a = mul(s.d20y, sub(pxa, s.x2)), c1b = mul(s.d20y, sub(pxb, s.x2));
@@ -575,6 +651,9 @@ RAST_HD void raster_item(const StagedTris &stg, uint32_t it, uint32_t lane, cons
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { // all four reads in flight together (global: L2, bypassing L1)
                     const uint32_t *hi = reinterpret_cast<const uint32_t *>(pix0 + (k >> 1) * row_stride + (k & 1)) + 1;
+#if RAST_BLOCK_Z
+                    if (bz_loaded) { cur_hi[k] = (mask & (1u << k)) ? bz_hi[k] : 0xFFFFFFFFu; continue; } // read once, for the block test
+#endif
                     cur_hi[k] = (mask & (1u << k)) ? (TILE_MODE ? *reinterpret_cast<const volatile uint32_t *>(hi) : RAST_LDCG32(hi)) : 0xFFFFFFFFu;
                 }
 #pragma unroll
