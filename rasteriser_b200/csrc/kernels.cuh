@@ -37,6 +37,9 @@
 #ifndef RAST_SHADE_PREP
 #define RAST_SHADE_PREP 1
 #endif
+#ifndef RAST_SHADE_PTRS
+#define RAST_SHADE_PTRS 0
+#endif
 #if RAST_TIGHT_TINY
 #include "tight_bbox.h"
 #endif
@@ -1195,6 +1198,10 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View 
     const float4 *rv = reinterpret_cast<const float4 *>(rv_base);
     const float4 *cn = reinterpret_cast<const float4 *>(cn_base);
     const FrameParams *fp = bt.frames + f;
+#if RAST_SHADE_PTRS
+    uint8_t *out_r = rgb + i0;
+    float *out_d = depth + i0; // only dereferenced when depth != nullptr
+#endif
 #if RAST_SHADE_PREP
     unsigned long long prep_base = (unsigned long long)(PREP ? bt.prep + (size_t)f * sc.T * PREP_QUADS : nullptr);
     asm volatile("" : "+l"(prep_base));
@@ -1230,6 +1237,15 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View 
                 }
             }
         }
+#if RAST_SHADE_PTRS
+        // variant (not yet timed): two running per-thread pointers instead of one index re-based on three planes every group
+        if (PX == 1) {
+            out_r[0] = (uint8_t)px[0].r; out_r[P] = (uint8_t)px[0].g; out_r[2 * (size_t)P] = (uint8_t)px[0].b;
+            if (depth) *out_d = px[0].depth;
+            out_r += STRIDE; out_d += STRIDE;
+            continue;
+        }
+#endif
         const size_t o = i0 + g * STRIDE, i = o;
         if (PX == 4) {
             *reinterpret_cast<uchar4 *>(rgb + o) = make_uchar4(px[0].r, px[PX > 1 ? 1 : 0].r, px[PX > 2 ? 2 : 0].r, px[PX > 3 ? 3 : 0].r);
