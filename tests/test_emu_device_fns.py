@@ -7,6 +7,7 @@ the order the kernels launch them.  The result must equal the oracle's bit for b
 are checked in the development container, which has no GPU; the -m gpu tests remain the parity tests proper."""
 import ctypes as C
 import os
+import shutil
 import subprocess
 
 import numpy as np
@@ -18,6 +19,7 @@ from rasteriser_b200 import _lib
 from test_parity_gpu_fuzz import _case
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 SRC = os.path.join(ROOT, "tests", "emu_device_fns.cu")
 CSRC = os.path.join(ROOT, "rasteriser_b200", "csrc")
 TIGHT, PRE_NORMALS, EARLY_Z, ALL_CHUNKS, FLAT_FACE, PREP = 1, 2, 4, 8, 16, 32
@@ -33,7 +35,7 @@ def load_emu(name="libemu.so", defines=()):
     deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "-fmad=false",
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "-fmad=false",
                                "-Xcompiler", "-fPIC,-ffp-contract=off,-Wno-unknown-pragmas", "-shared", "-o", out, SRC] + ["-D" + d for d in defines])
     lib = C.CDLL(out)
     lib.emu_draw.restype = C.c_int
@@ -174,7 +176,7 @@ def test_block_level_depth_bound_brute_force(tmp_path):
     has z >= plane - M (the bound the block test relies on); the worst pixel uses a small fraction of the margin."""
     import json
     exe = str(tmp_path / "blockz_rule_check")
-    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "-fmad=false", "-Xcompiler", "-ffp-contract=off,-Wno-unknown-pragmas",
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "-fmad=false", "-Xcompiler", "-ffp-contract=off,-Wno-unknown-pragmas",
                            "-DRAST_BLOCK_Z=1", "-o", exe, os.path.join(ROOT, "tests", "blockz_rule_check.cu")])
     for seed in (1, 2):
         p = subprocess.run([exe, str(seed), "200000"], capture_output=True, text=True)
