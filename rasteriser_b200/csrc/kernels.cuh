@@ -44,23 +44,31 @@
 #include "tight_bbox.h"
 #endif
 
-// Device-only primitives used inside the RAST_HD functions, with single-lane host stand-ins for tests/emu_device_fns.cu
-// (a host "warp" is one lane at a time: a vote is the lane's own predicate, an atomic min a plain min).
 // Variant switch (off by default, not yet timed): block-level early depth rejection in the chunk rasteriser (raster_item).
 #ifndef RAST_BLOCK_Z
 #define RAST_BLOCK_Z 0
 #endif
+// Device-only primitives used inside the RAST_HD functions, with host stand-ins for tests/emu_device_fns.cu.  By default a host
+// "warp" is one lane at a time (a vote is the lane's own predicate, a warp maximum the lane's own value, an atomic min a plain
+// min); the test may define RAST_HOST_ANY / RAST_HOST_WARP_MAX_U32 before including this file to run 32 lanes in lockstep with
+// real votes and reductions.
+#ifndef RAST_HOST_ANY
+#define RAST_HOST_ANY(p) (p)
+#endif
+#ifndef RAST_HOST_WARP_MAX_U32
+#define RAST_HOST_WARP_MAX_U32(v) (v)
+#endif
 #ifdef __CUDA_ARCH__
 #define RAST_WARP_MAX_U32(v) __reduce_max_sync(0xFFFFFFFFu, (v))
 #else
-#define RAST_WARP_MAX_U32(v) (v)
+#define RAST_WARP_MAX_U32(v) RAST_HOST_WARP_MAX_U32(v)
 #endif
 #ifdef __CUDA_ARCH__
 #define RAST_ANY(p) __any_sync(0xFFFFFFFFu, (p))
 #define RAST_ATOMIC_MIN64(ptr, v) atomicMin((ptr), (v))
 #define RAST_LDCG32(ptr) __ldcg(ptr)
 #else
-#define RAST_ANY(p) (p)
+#define RAST_ANY(p) RAST_HOST_ANY(p)
 #define RAST_ATOMIC_MIN64(ptr, v) do { unsigned long long *p__ = (ptr); const unsigned long long v__ = (v); if (v__ < *p__) *p__ = v__; } while (0)
 #define RAST_LDCG32(ptr) (*(ptr))
 #endif

@@ -10,9 +10,42 @@
 // product path: nothing under rasteriser_b200/ or include/ builds, loads or calls it.
 //
 // Build (tests/test_emu_device_fns.py): nvcc -std=c++17 -O2 -Xcompiler -fPIC,-ffp-contract=off -shared -o libemu.so emu_device_fns.cu
+#include <atomic>
 #include <cstdint>
 #include <cstring>
+#include <thread>
 #include <vector>
+
+// ---- a host warp in lockstep (flag EMU_WARP): 32 threads, one per lane; votes and warp reductions are real -------------------
+// Every lane of raster_item reaches the same collectives in the same order (they sit in warp-uniform control flow), so a
+// barrier per collective is a faithful model of __any_sync / __reduce_max_sync.  Without EMU_WARP the lanes run one after the
+// other and a collective degenerates to the lane's own value (still a valid, merely different, execution).
+namespace emu_warp {
+struct Ctx {
+    std::atomic<int> arrived{0}, sense{0};
+    uint32_t vals[32];
+};
+thread_local Ctx *g_ctx = nullptr;
+thread_local uint32_t g_lane = 0;
+inline void barrier(Ctx *c, int parties) {
+    const int s = c->sense.load();
+    if (c->arrived.fetch_add(1) == parties - 1) { c->arrived.store(0); c->sense.store(s ^ 1); }
+    else while (c->sense.load() == s) std::this_thread::yield();
+}
+inline uint32_t warp_max(uint32_t v) {
+    Ctx *c = g_ctx;
+    if (!c) return v;
+    c->vals[g_lane] = v;
+    barrier(c, 32);
+    uint32_t m = 0;
+    for (int i = 0; i < 32; ++i) m = c->vals[i] > m ? c->vals[i] : m;
+    barrier(c, 32); // nobody overwrites vals before everybody has read them
+    return m;
+}
+inline bool any(bool p) { return warp_max(p ? 1u : 0u) != 0u; }
+} // namespace emu_warp
+#define RAST_HOST_ANY(p) emu_warp::any(p)
+#define RAST_HOST_WARP_MAX_U32(v) emu_warp::warp_max(v)
 
 #ifndef RAST_TIGHT_TINY
 #define RAST_TIGHT_TINY 1 // the host driver below calls rast_tight_bbox only when asked to (flag bit 0)
@@ -28,7 +61,7 @@ struct EmuMaterial { // = rast_material (include/rast.h): planar normalised texe
     const float *texels;
 };
 
-enum { EMU_TIGHT = 1, EMU_PRE_NORMALS = 2, EMU_EARLY_Z = 4, EMU_ALL_CHUNKS = 8, EMU_FLAT_FACE = 16, EMU_PREP = 32 };
+enum { EMU_TIGHT = 1, EMU_PRE_NORMALS = 2, EMU_EARLY_Z = 4, EMU_ALL_CHUNKS = 8, EMU_FLAT_FACE = 16, EMU_PREP = 32, EMU_WARP = 64 };
 
 // One frame.  lights: n x 10 floats (rast_light: direction, intensity, colour, trans_dir -- trans_dir already computed by
 // rast_transform_lights).  Outputs: rgb planar [3][rows][W], depth [rows][W], tri_ids [rows][W] for the band [y0, y1).
@@ -110,6 +143,24 @@ extern "C" int emu_draw(const float *pos, uint32_t V, const float *nrm, uint32_t
     std::vector<unsigned long long> vis(P, VIS_EMPTY);
     StagedTris *stg = new StagedTris();
     const bool early_z = (flags & EMU_EARLY_Z) != 0;
+    // EMU_WARP: 32 lane threads wait for the main thread to stage an item, rasterise it in lockstep, and report back
+    emu_warp::Ctx warp_ctx, gate; // warp_ctx: collectives among the 32 lanes; gate: main thread + 32 lanes (33 parties)
+    std::atomic<int> warp_slot{-1};
+    std::vector<std::thread> lanes;
+    if (flags & EMU_WARP) {
+        for (uint32_t lane = 0; lane < 32u; ++lane)
+            lanes.emplace_back([&, lane]() {
+                emu_warp::g_ctx = &warp_ctx;
+                emu_warp::g_lane = lane;
+                for (;;) {
+                    emu_warp::barrier(&gate, 33); // item staged (or stop)
+                    const int slot = warp_slot.load();
+                    if (slot < 0) return;
+                    raster_item<false>(*stg, (uint32_t)slot, lane, vw, vis.data(), nullptr, early_z);
+                    emu_warp::barrier(&gate, 33); // item done
+                }
+            });
+    }
     for (uint64_t t = 0; t < T; ++t) {
         const float4 v0 = rv[tris[10 * t]], v1 = rv[tris[10 * t + 1]], v2 = rv[tris[10 * t + 2]];
         const float a2 = signed_area_2d(v0, v1, v2);
@@ -133,9 +184,20 @@ extern "C" int emu_draw(const float *pos, uint32_t V, const float *nrm, uint32_t
                     const uint32_t rx1 = min(bb.x1, rx0 + CHUNK - 1u), ry1 = min(bb.y1, ry0 + CHUNK - 1u);
                     const uint32_t slot = (uint32_t)((t + cx + cy) & 31u); // any staging slot must do
                     stage_item(*stg, slot, (uint32_t)t, 0u, v0, v1, v2, rx0, ry0, rx1, ry1, rx0, ry0);
-                    for (uint32_t lane = 0; lane < 32u; ++lane) raster_item<false>(*stg, slot, lane, vw, vis.data(), nullptr, early_z);
+                    if (flags & EMU_WARP) {
+                        warp_slot.store((int)slot);
+                        emu_warp::barrier(&gate, 33);
+                        emu_warp::barrier(&gate, 33);
+                    } else {
+                        for (uint32_t lane = 0; lane < 32u; ++lane) raster_item<false>(*stg, slot, lane, vw, vis.data(), nullptr, early_z);
+                    }
                 }
         }
+    }
+    if (flags & EMU_WARP) {
+        warp_slot.store(-1);
+        emu_warp::barrier(&gate, 33);
+        for (std::thread &t : lanes) t.join();
     }
     delete stg;
 

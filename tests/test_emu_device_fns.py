@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 SRC = os.path.join(ROOT, "tests", "emu_device_fns.cu")
 CSRC = os.path.join(ROOT, "rasteriser_b200", "csrc")
-TIGHT, PRE_NORMALS, EARLY_Z, ALL_CHUNKS, FLAT_FACE, PREP = 1, 2, 4, 8, 16, 32
+TIGHT, PRE_NORMALS, EARLY_Z, ALL_CHUNKS, FLAT_FACE, PREP, WARP = 1, 2, 4, 8, 16, 32, 64
 
 
 class EmuMaterial(C.Structure):
@@ -36,7 +36,7 @@ def load_emu(name="libemu.so", defines=()):
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O2", "-fmad=false",
-                               "-Xcompiler", "-fPIC,-ffp-contract=off,-Wno-unknown-pragmas", "-shared", "-o", out, SRC] + ["-D" + d for d in defines])
+                               "-Xcompiler", "-fPIC,-ffp-contract=off,-Wno-unknown-pragmas,-pthread", "-shared", "-o", out, SRC, "-lpthread"] + ["-D" + d for d in defines])
     lib = C.CDLL(out)
     lib.emu_draw.restype = C.c_int
     lib.emu_draw.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64,
@@ -184,3 +184,28 @@ def test_block_level_depth_bound_brute_force(tmp_path):
         r = json.loads(p.stdout)
         assert r["violations"] == 0 and r["accepted_pixels"] > 1000000 and r["usable_items"] > 100000
         assert r["worst_margin_fraction"] < 0.25
+
+
+def test_lockstep_warp_emulation(emu, emu_blockz):
+    """WARP flag: the chunk rasteriser's 32 lanes run as 32 host threads in lockstep, with real votes (__any_sync) and, in the
+    RAST_BLOCK_Z build, the real warp-wide maximum of the stored depths -- the decisions a device warp takes, not the
+    one-lane-at-a-time stand-ins.  Overdraw scene (block rejection in every item), a golden scene and fuzz cases."""
+    from rasteriser_b200 import synth
+    W, H = 480, 270
+    pos, nrm, uv, tris = synth.overdraw_scene(2500, W, H, radius_px=50.0)
+    scene = orc.Scene(pos, nrm, uv, tris, [{"kd": (0.8, 0.8, 0.8), "texels": None}])
+    lights = S.lights("threepoint")
+    oa = orc.make_args(W, H)
+    want = orc.oracle_draw(scene, lights, oa, threads=4)
+    for lib in (emu, emu_blockz):
+        assert_exact(emu_draw(lib, scene, lights, oa, PRE_NORMALS | ALL_CHUNKS | EARLY_Z | WARP), want, "overdraw, lockstep warp")
+    c = [c for c in S.golden_cases() if c["name"] == "suzanne_160x120"][0]
+    scene, lights, oa = S.scene(c["scene"]), S.lights(c["lights"]), S.case_args(c)
+    for lib in (emu, emu_blockz):
+        got = emu_draw(lib, scene, lights, oa, PRE_NORMALS | ALL_CHUNKS | EARLY_Z | WARP)
+        assert orc.fnv(got[0]) == c["frame_fnv"] and orc.fnv(got[1]) == c["depth_fnv"]
+    for seed in (1001, 1005, 1012):
+        scene, lights, oa, mode, kind = _case(seed)
+        if oa.image_width * oa.image_height > 100000 or len(scene.tris) > 2000:
+            continue
+        assert_exact(emu_draw(emu_blockz, scene, lights, oa, ALL_CHUNKS | EARLY_Z | WARP), orc.oracle_draw(scene, lights, oa, threads=2), "seed %d" % seed)
