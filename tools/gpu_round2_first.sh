@@ -2,7 +2,8 @@
 # First GPU session of the next round (about 6-8 minutes): the whole suite and the benchmark on the shipped default, then the
 # prepared kernel variants -- parity files and quick A/B with output hashes -- and fresh ncu captures.
 #   here first:  python tools/build_variants.py legacy:-DRAST_TIGHT_TINY=0,-DRAST_SHADE_PREP=0 blockz:-DRAST_BLOCK_Z=1 ptrs:-DRAST_SHADE_PTRS=1 \
-#                    blockz_ptrs:-DRAST_BLOCK_Z=1,-DRAST_SHADE_PTRS=1
+#                    blockz_ptrs:-DRAST_BLOCK_Z=1,-DRAST_SHADE_PTRS=1 g12:-DRAST_SHADE_GROUPS=12 g15:-DRAST_SHADE_GROUPS=15 g20:-DRAST_SHADE_GROUPS=20 \
+#                    t256g8:-DRAST_SHADE_THREADS=256,-DRAST_SHADE_GROUPS=8
 #   there:       tools/gpu_round2_first.sh r2a
 t=${1:-r2a}
 o=gpurun_out
@@ -13,6 +14,9 @@ ab() { env RAST_LIB=${1:+build/variants/librast_b200_$1.so} $3 python tools/quic
 for v in "" legacy blockz ptrs blockz_ptrs; do
   [ -z "$v" ] || [ -f build/variants/librast_b200_$v.so ] || continue
   for w in spin1080p overdraw8k tess4k suzanne640; do ab "$v" $w; done
+done
+for v in g12 g15 g20 t256g8; do  # shade-pass geometry with the prepared records (the optimum may have moved)
+  [ -f build/variants/librast_b200_$v.so ] && ab $v spin1080p
 done
 for v in blockz ptrs blockz_ptrs; do
   [ -f build/variants/librast_b200_$v.so ] || continue
