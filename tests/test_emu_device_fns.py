@@ -192,7 +192,7 @@ def test_lockstep_warp_emulation(emu, emu_blockz):
     one-lane-at-a-time stand-ins.  Overdraw scene (block rejection in every item), a golden scene and fuzz cases."""
     from rasteriser_b200 import synth
     W, H = 480, 270
-    pos, nrm, uv, tris = synth.overdraw_scene(2500, W, H, radius_px=50.0)
+    pos, nrm, uv, tris = synth.overdraw_scene(1200, W, H, radius_px=50.0)
     scene = orc.Scene(pos, nrm, uv, tris, [{"kd": (0.8, 0.8, 0.8), "texels": None}])
     lights = S.lights("threepoint")
     oa = orc.make_args(W, H)
