@@ -276,7 +276,7 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     // the output is a band of a larger -- typically another GPU's -- image: 128-byte instead of 32-byte stores over NVLink
     // (8K overdraw frame on 8 GPUs: 1.13 -> 1.05 ms)
     const bool want_vec = ctx->shade_px == 4 || vw.out_plane != vw.band_pixels;
-    const bool vec = !ctx->flat_face && want_vec && (vw.W % 4u == 0u) && (((uintptr_t)rgb_dev & 15u) == 0u) && (((uintptr_t)depth_dev & 15u) == 0u);
+    const bool vec = !ctx->flat_face && want_vec && (vw.W % 4u == 0u) && (vw.out_plane % 4u == 0u) && (((uintptr_t)rgb_dev & 15u) == 0u) && (((uintptr_t)depth_dev & 15u) == 0u);
 #if RAST_SHADE_PREP
     bt.prep = (ctx->use_prep && bt.cn && !vec) ? ctx->d_prep[ps].as<float4>() : nullptr; // the 4-pixel shade variant gathers; no records for it
 #endif
@@ -530,14 +530,6 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
         int rc = rast_upload_materials(ctx, nullptr, 0);
         if (rc != RAST_OK) return rc;
     }
-    if (ctx->mesh_materials_dirty) {
-        // resolve material indices against the uploaded table; -1 / out of range -> sentinel (index n_materials)
-        if (ctx->scene.T) {
-            rk::k_resolve_materials<<<grid_for(ctx->scene.T, 256), 256, 0, ctx->stream>>>(ctx->d_attr.as<int4>(), ctx->scene.T, ctx->n_materials);
-            ctx->launches++;
-        }
-        ctx->mesh_materials_dirty = false;
-    }
     rk::View vw = make_view(ctx, W, H);
     if (vw.band_pixels == 0) return RAST_OK; // empty band: nothing to render or copy
     // P = pixels between output planes.  Device-pointer draws may write a band into a larger image (the full frame of a
@@ -637,6 +629,17 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
     if (!ctx->lights.empty())
         RAST_CUDA(ctx, cudaMemcpyAsync(ctx->d_lights[ctx->cs].p, ctx->h_lights.p, ctx->lights.size() * sizeof(rk::LightDev), cudaMemcpyHostToDevice, up));
     RAST_CUDA(ctx, cudaEventRecord(ctx->ev_params, up));
+    if (ctx->mesh_materials_dirty) {
+        // Resolve material indices against the uploaded table; -1 / out of range -> sentinel (index n_materials).  Launched on the
+        // stream that carries this call's front passes: k_prepare_tris (front stream) copies the resolved index into the prepared
+        // records and the shade pass waits for the front passes, so both readers are ordered behind it whatever stream the caller
+        // handed to rast_set_stream.  (Both uploads synchronise the context's stream, so no earlier shade pass still reads tri_rec.)
+        if (ctx->scene.T) {
+            rk::k_resolve_materials<<<grid_for(ctx->scene.T, 256), 256, 0, up>>>(ctx->d_attr.as<int4>(), ctx->scene.T, ctx->n_materials);
+            ctx->launches++;
+        }
+        ctx->mesh_materials_dirty = false;
+    }
 
     if (ctx->profiling) memset(ctx->pass_ms, 0, sizeof ctx->pass_ms);
 
