@@ -13,13 +13,18 @@
 // fields private: pass anything with kd / has_texture / tex_w / tex_h / texels members (host::MaterialData)
 // -- INTEGRATION.md shows the three accessor lines to add to headers/material.h.
 //
-// Semantics: the scene is uploaded on the first call (and again if the vectors change size or address),
-// the finished frame and depth overwrite the caller's buffers (the reference's callers always pass cleared
+// Semantics: the reference reads its vectors on every call.  Here the scene is uploaded on the first call and again
+// whenever it is not the same scene any more: the vectors' addresses, sizes AND contents are compared (a 64-bit hash of
+// every array per call -- a few GB/s, microseconds for a Suzanne-sized scene -- so vertices edited in place are seen).
+// A caller that redraws one huge static scene (the spin loop, renderer.cpp:105-111) can skip the hashing with
+// Session::assume_unchanged(true) -- then only addresses and sizes are compared and Session::invalidate() forces the
+// next upload.  The finished frame and depth overwrite the caller's buffers (the reference's callers always pass cleared
 // buffers: renderer.cpp:85-86,107-108), lights[i].trans_dir is written like Light::transform
 // (geometry.cpp:126).  Errors throw std::runtime_error on the C++ side of the ABI.
 #pragma once
 
 #include <cstdint>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -57,21 +62,62 @@ public:
             m[i].texels = materials[i].has_texture ? &materials[i].texels[0] : nullptr;
         }
         check(rast_upload_materials(ctx_, m.data(), (uint32_t)m.size()), "rast_upload_materials");
-        key_ = {vertices.data(), faces.data(), normals.data(), uvs.data(), materials.data(), vertices.size(), faces.size(), materials.size()};
+        key_ = make_key(vertices, faces, normals, uvs, materials, true);
         uploaded_ = true;
     }
 
+    // The caller promises that the scene arrays do not change between draws (no per-call content hash); invalidate() when they do.
+    void assume_unchanged(bool on) { assume_unchanged_ = on; }
+    void invalidate() { uploaded_ = false; }
+
     template <class Vec3s, class Faces, class Vec2s, class Materials>
     bool holds(const Vec3s &vertices, const Faces &faces, const Vec3s &normals, const Vec2s &uvs, const Materials &materials) const {
-        const Key k = {vertices.data(), faces.data(), normals.data(), uvs.data(), materials.data(), vertices.size(), faces.size(), materials.size()};
-        return uploaded_ && k.v == key_.v && k.f == key_.f && k.n == key_.n && k.u == key_.u && k.m == key_.m && k.nv == key_.nv && k.nf == key_.nf && k.nm == key_.nm;
+        if (!uploaded_) return false;
+        const Key k = make_key(vertices, faces, normals, uvs, materials, !assume_unchanged_);
+        return k.v == key_.v && k.f == key_.f && k.n == key_.n && k.u == key_.u && k.m == key_.m && k.nv == key_.nv && k.nf == key_.nf && k.nn == key_.nn &&
+               k.nu == key_.nu && k.nm == key_.nm && (assume_unchanged_ || k.hash == key_.hash);
     }
 
 private:
-    struct Key { const void *v, *f, *n, *u, *m; size_t nv, nf, nm; };
+    struct Key { const void *v, *f, *n, *u, *m; size_t nv, nf, nn, nu, nm; uint64_t hash; };
+    // 64-bit multiply-xorshift hash over 8-byte words (4 independent lanes so that it runs at memory speed)
+    static uint64_t hash_bytes(const void *p, size_t bytes, uint64_t h) {
+        const unsigned char *b = static_cast<const unsigned char *>(p);
+        uint64_t l[4] = {h ^ 0x9E3779B97F4A7C15ull, h ^ 0xC2B2AE3D27D4EB4Full, h ^ 0x165667B19E3779F9ull, h ^ 0x27D4EB2F165667C5ull};
+        size_t i = 0;
+        for (; i + 32 <= bytes; i += 32) {
+            uint64_t w[4];
+            std::memcpy(w, b + i, 32);
+            for (int k = 0; k < 4; ++k) { l[k] = (l[k] ^ w[k]) * 0x100000001B3ull; l[k] ^= l[k] >> 29; }
+        }
+        uint64_t tail[4] = {0, 0, 0, 0};
+        if (i < bytes) std::memcpy(tail, b + i, bytes - i);
+        for (int k = 0; k < 4; ++k) { l[k] = (l[k] ^ tail[k]) * 0x100000001B3ull; l[k] ^= l[k] >> 29; }
+        uint64_t out = bytes;
+        for (int k = 0; k < 4; ++k) { out = (out ^ l[k]) * 0xFF51AFD7ED558CCDull; out ^= out >> 33; }
+        return out;
+    }
+    template <class Vec3s, class Faces, class Vec2s, class Materials>
+    static Key make_key(const Vec3s &vertices, const Faces &faces, const Vec3s &normals, const Vec2s &uvs, const Materials &materials, bool with_hash) {
+        Key k = {vertices.data(), faces.data(), normals.data(), uvs.data(), materials.data(), vertices.size(), faces.size(), normals.size(), uvs.size(), materials.size(), 0};
+        if (with_hash) {
+            uint64_t h = hash_bytes(vertices.data(), vertices.size() * sizeof(typename Vec3s::value_type), 1);
+            h = hash_bytes(faces.data(), faces.size() * sizeof(typename Faces::value_type), h);
+            h = hash_bytes(normals.data(), normals.size() * sizeof(typename Vec3s::value_type), h);
+            h = hash_bytes(uvs.data(), uvs.size() * sizeof(typename Vec2s::value_type), h);
+            for (size_t i = 0; i < materials.size(); ++i) {
+                const float kd[3] = {(float)materials[i].kd[0], (float)materials[i].kd[1], (float)materials[i].kd[2]};
+                h = hash_bytes(kd, sizeof kd, h);
+                if (materials[i].has_texture)
+                    h = hash_bytes(&materials[i].texels[0], (size_t)materials[i].tex_w * (size_t)materials[i].tex_h * 3 * sizeof(float), h ^ (uint64_t)materials[i].tex_w);
+            }
+            k.hash = h;
+        }
+        return k;
+    }
     rast_ctx *ctx_ = nullptr;
     Key key_{};
-    bool uploaded_ = false;
+    bool uploaded_ = false, assume_unchanged_ = false;
 };
 
 template <class ArgsT> inline rast_args to_rast_args(const ArgsT &a) {

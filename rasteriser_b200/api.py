@@ -187,6 +187,9 @@ class Renderer:
             frame = np.empty((3, rows, a.image_width), np.uint8)
         if depth is None and want_depth:
             depth = np.empty((rows, a.image_width), np.float32)
+        _check_out("frame", frame, np.uint8, (3, rows, a.image_width))
+        if depth is not None:
+            _check_out("depth", depth, np.float32, (rows, a.image_width))
         self._check(self._lib.rast_draw_frame(self._h, C.byref(a), _ptr(frame), _ptr(depth), self._lights), "rast_draw_frame")
         return frame, depth
 
@@ -199,6 +202,9 @@ class Renderer:
             frames = np.empty((n, 3, rows, arr[0].image_width), np.uint8)
         if depths is None and want_depth:
             depths = np.empty((n, rows, arr[0].image_width), np.float32)
+        _check_out("frames", frames, np.uint8, (n, 3, rows, arr[0].image_width))
+        if depths is not None:
+            _check_out("depths", depths, np.float32, (n, rows, arr[0].image_width))
         self._check(self._lib.rast_draw_frames(self._h, arr, n, _ptr(frames), _ptr(depths), 0), "rast_draw_frames")
         return frames, depths
 
@@ -269,23 +275,77 @@ def spin_angle(ry0, k, n_frames):
 
 
 _cached = {}
+CONTENT_KEY_MAX_BYTES = 64 << 20  # scenes up to this size are fingerprinted on every call; larger ones are re-uploaded unless scene_version is given
 
 
-def draw_frame(model_vertices, faces, model_vertnormals, vertuvs, lights, materials, arguments, frame_buffer, depth_buffer, device=0):
+def _fingerprint(arrays):
+    """Content fingerprint of the scene arrays (shape, dtype and every byte): zlib.crc32 + adler32 run at GB/s, i.e.
+    microseconds on a Suzanne-sized scene."""
+    import zlib
+    out = []
+    for a in arrays:
+        b = np.ascontiguousarray(a)
+        mv = memoryview(b).cast("B") if b.size else b""
+        out.append((b.shape, b.dtype.str, zlib.crc32(mv), zlib.adler32(mv)))
+    return tuple(out)
+
+
+def _material_arrays(materials):
+    out = []
+    for m in materials:
+        kd = m.kd if isinstance(m, Material) else m["kd"]
+        tex = m.texels if isinstance(m, Material) else m.get("texels")
+        out.append(np.asarray(kd, np.float32))
+        out.append(np.zeros(0, np.float32) if tex is None else np.asarray(tex, np.float32))
+    return out
+
+
+def invalidate():
+    """Forget the scene cached by draw_frame(): the next call uploads again."""
+    for r in _cached.values():
+        r.close()
+    _cached.clear()
+
+
+def _check_out(name, a, dtype, shape):
+    if not isinstance(a, np.ndarray) or a.dtype != dtype or a.shape != shape or not a.flags.c_contiguous or not a.flags.writeable:
+        raise RastError("draw_frame: %s must be a writeable C-contiguous numpy array of dtype %s and shape %s (got %s)"
+                        % (name, np.dtype(dtype).name, shape, "%s %s" % (getattr(a, "dtype", type(a).__name__), getattr(a, "shape", ""))))
+
+
+def draw_frame(model_vertices, faces, model_vertnormals, vertuvs, lights, materials, arguments, frame_buffer, depth_buffer, device=0, scene_version=None):
     """Same argument order and meaning as the reference's draw_frame (headers/drawing.h:16-18).
 
-    frame_buffer: uint8 [3,H,W] (CImg planar), depth_buffer: float32 [H,W]; both are overwritten with
+    frame_buffer: uint8 [3,H,W] (CImg planar), depth_buffer: float32 [H,W] (or None); both are overwritten with
     the finished frame (callers of the reference always pass cleared buffers, renderer.cpp:85-86).
-    lights: float32 [L,10]; columns 7..9 (trans_dir) are written like Light::transform does."""
-    key = (device, id(model_vertices), id(faces), id(model_vertnormals), id(vertuvs), id(materials))
-    r = _cached.get(key)
+    lights: float32 [L,10]; columns 7..9 (trans_dir) are written like Light::transform does.
+
+    The reference reads its vectors on every call.  Here the scene stays on the GPU between calls as long as it is
+    the same scene: by content (a checksum of every array, for scenes up to CONTENT_KEY_MAX_BYTES -- an edit in place
+    is seen), or, for larger scenes, by the caller's `scene_version` (any hashable; bump it after changing the arrays).
+    A large scene without a version is uploaded on every call, like the reference re-reads it.  invalidate() drops
+    the cached scene."""
+    a = _as_rast_args(arguments)
+    _check_out("frame_buffer", frame_buffer, np.uint8, (3, a.image_height, a.image_width))
+    if depth_buffer is not None:
+        _check_out("depth_buffer", depth_buffer, np.float32, (a.image_height, a.image_width))
+    arrays = [np.asarray(model_vertices), np.asarray(faces), np.asarray(model_vertnormals), np.asarray(vertuvs)] + _material_arrays(materials)
+    if scene_version is not None:
+        key = (device, "version", scene_version)
+    elif sum(x.nbytes for x in arrays) <= CONTENT_KEY_MAX_BYTES:
+        key = (device, "content", _fingerprint(arrays))
+    else:
+        key = None
+    r = _cached.get(key) if key is not None else None
     if r is None:
-        _cached.clear()
+        invalidate()
         r = Renderer(device)
         r.upload_mesh(model_vertices, faces, model_vertnormals, vertuvs)
         r.upload_materials(materials)
-        _cached[key] = r
+        _cached[key if key is not None else (device, "uncached")] = r
     r.set_lights(np.asarray(lights, np.float32)[:, :7])
-    r.draw_frame(arguments, frame_buffer, depth_buffer)
+    r.draw_frame(a, frame_buffer, depth_buffer, want_depth=depth_buffer is not None)
     if isinstance(lights, np.ndarray) and lights.ndim == 2 and lights.shape[1] >= 10:
         lights[:, 7:10] = r.light_trans_dirs()
+    if key is None:
+        invalidate()

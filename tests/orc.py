@@ -203,3 +203,36 @@ def load_texture_png(path):
     t = np.ascontiguousarray(im.transpose(2, 0, 1).astype(np.float32))
     oracle().orc_normalize_texture(ptr(t), t.size)
     return t
+
+
+def build_shim_real_headers(force=False):
+    """oracle/_ref/shim_real_headers: tests/shim_real_headers_main.cpp compiled against the reference's REAL headers (and its
+    unmodified fileloader.cpp) where they lie under /root/reference, with INTEGRATION.md section 3's one-line patch applied to a
+    temporary copy of headers/material.h.  Dev container only; the binary travels to the GPU box with oracle/_ref/."""
+    import shutil
+    import tempfile
+    ref_root = os.environ.get("REFERENCE_ROOT", "/root/reference")
+    out = os.path.join(ORACLE_DIR, "_ref", "shim_real_headers")
+    src = os.path.join(ROOT, "tests", "shim_real_headers_main.cpp")
+    hdr = os.path.join(ROOT, "include", "rast_draw_frame.hpp")
+    lib = os.path.join(ROOT, "rasteriser_b200", "librast_b200.so")
+    if not os.path.isdir(ref_root):
+        return out if os.path.exists(out) else None
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(f) for f in (src, hdr)):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    tmp = tempfile.mkdtemp(prefix="shim_hdrs_")
+    try:
+        for f in os.listdir(os.path.join(ref_root, "headers")):  # quote-includes resolve next to the including file: mirror the directory
+            if f != "material.h":
+                os.symlink(os.path.join(ref_root, "headers", f), os.path.join(tmp, f))
+        text = open(os.path.join(ref_root, "headers", "material.h")).read()
+        assert "public:" in text and "RastMaterialView" not in text
+        open(os.path.join(tmp, "material.h"), "w").write(text.replace("public:", "public:\n\tfriend struct RastMaterialView;", 1))
+        flags = ["-std=c++11", "-O2", "-ffp-contract=off", "-Dcimg_display=0", "-w", "-I" + tmp, "-I" + os.path.join(ORACLE_DIR, "glm_stub"),
+                 "-I" + os.path.join(ref_root, "vendor", "cimg"), "-I" + os.path.join(ref_root, "vendor", "tinyobjloader"), "-I" + os.path.join(ROOT, "include")]
+        subprocess.check_call(["g++"] + flags + ["-o", out, src, os.path.join(ref_root, "fileloader.cpp"), "-L" + os.path.dirname(lib), "-lrast_b200",
+                                                 "-Wl,-rpath,$ORIGIN/../../rasteriser_b200", "-lpthread"])
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out

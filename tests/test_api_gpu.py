@@ -145,3 +145,33 @@ def test_sparse_host_copy_delivers_the_same_bytes(monkeypatch):
     f_empty, d_empty = sparse[0][5]
     assert not f_empty.any() and (d_empty == 1.0).all()
     assert sparse[1] < 0.9 * whole[1]  # fewer bytes crossed PCIe (two of the seven poses cover most of the frame)
+
+
+@pytest.mark.gpu
+def test_drop_in_draw_frame_sees_edits_and_new_scenes():
+    """The reference re-reads its vectors on every call (headers/drawing.h:16-18).  The drop-in keeps the scene on the GPU
+    only while its content is unchanged: an edit in place, or a different scene in recycled arrays (same id()), must be drawn."""
+    import orc
+    import scenes as S
+    from gpu_common import assert_parity
+    sc = S.scene("suzanne")
+    l7 = S.lights("threepoint")
+    a = api.Args(160, 120)
+    oa = orc.make_args(160, 120)
+
+    def draw(pos):
+        f, d = np.zeros((3, 120, 160), np.uint8), np.ones((120, 160), np.float32)
+        api.draw_frame(pos, sc.tris, sc.normals, sc.uvs, orc.lights_array(l7), sc.materials, a, f, d)
+        return f, d
+
+    pos = np.array(sc.positions)
+    f0, d0 = draw(pos)
+    want0 = orc.oracle_draw(sc, l7, oa)
+    assert np.array_equal(f0, want0[0]) and np.array_equal(d0.view(np.uint32), want0[1].view(np.uint32))
+    pos *= np.float32(0.5)  # edited in place: same object, same address
+    f1, d1 = draw(pos)
+    sc2 = orc.Scene(pos, sc.normals, sc.uvs, sc.tris, sc.materials)
+    want1 = orc.oracle_draw(sc2, l7, oa)
+    assert np.array_equal(f1, want1[0]) and np.array_equal(d1.view(np.uint32), want1[1].view(np.uint32))
+    assert not np.array_equal(f0, f1)
+    api.invalidate()

@@ -99,3 +99,26 @@ def test_product_does_not_reference_the_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                     text = open(os.path.join(dp, f), errors="ignore").read()
                     assert "liboracle" not in text and "oracle.h" not in text and "import orc" not in text, os.path.join(dp, f)
+
+
+def test_draw_frame_rejects_wrong_output_buffers():
+    """dtype / shape / contiguity of the caller's buffers are checked before anything reaches ctypes: a float64
+    or strided buffer must raise, not be overrun.  The check precedes the context, so it runs without a GPU."""
+    sc = S.scene("suzanne")
+    l = S.lights("threepoint")
+    a = api.Args(64, 48)
+    good_f, good_d = np.zeros((3, 48, 64), np.uint8), np.ones((48, 64), np.float32)
+    bad = [(np.zeros((3, 48, 64), np.float64), good_d), (np.zeros((48, 64, 3), np.uint8), good_d), (good_f, np.ones((48, 64), np.float64)),
+           (np.zeros((3, 48, 128), np.uint8)[:, :, ::2], good_d), (good_f, np.ones((64, 48), np.float32).T), (good_f[:, :40], good_d)]
+    for f, d in bad:
+        with pytest.raises(api.RastError, match="must be a writeable C-contiguous"):
+            api.draw_frame(sc.positions, sc.tris, sc.normals, sc.uvs, l, sc.materials, a, f, d)
+
+
+def test_scene_fingerprint_sees_in_place_edits():
+    sc = S.scene("suzanne")
+    arrays = [np.array(sc.positions), np.array(sc.tris), np.array(sc.normals), np.array(sc.uvs)]
+    k0 = api._fingerprint(arrays)
+    assert k0 == api._fingerprint([a.copy() for a in arrays])  # same content at other addresses: same scene
+    arrays[0][17, 1] = np.nextafter(arrays[0][17, 1], np.float32(9))
+    assert api._fingerprint(arrays) != k0
