@@ -241,10 +241,173 @@ def run_reference_arm(opts, wl):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+KERNEL_OF_PASS = {"vertex": "k_vertex", "setup": "k_setup", "raster": "k_raster_chunks", "shade": "k_resolve_shade", "clear": "k_clear"}
+# golden hashes produced by the REFERENCE's own code (tests/golden/make_golden*.py): workload -> (file, case)
+GOLDEN_OF_WORKLOAD = {"suzanne640": ("cases.json", "suzanne_640x480"), "tess4k": ("large_cases.json", "config3_tess91_4k"),
+                      "tess4k_64lights": ("large_cases.json", "config5_tess227_64lights_4k"), "overdraw8k": ("large_cases.json", "config4_overdraw_8k")}
+
+
+def golden_case(file, name):
+    d = json.load(open(os.path.join(ROOT, "tests", "golden", file)))
+    if isinstance(d, list):
+        return [c for c in d if c["name"] == name][0]
+    return d[name]
+
+
 def algorithmic_bytes(wl, visible_tris, P):
     """per frame, per pass."""
     V, Nn, T = len(wl["pos"]), len(wl["nrm"]), len(wl["tris"])
     return {"vertex": 28 * V + 24 * Nn, "setup+raster": 12 * T + 16 * V + 16 * P, "shade": 15 * P + 136 * visible_tris}
+
+
+def hbm_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        if "hbm_gbs" in peaks:
+            return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        pass
+    return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload):
+    """Per-kernel DRAM bytes / limiter counters of the committed ncu --set full captures (profiles/r*_traffic.json, written
+    by tools/ncu_traffic.py from the .ncu-rep files of the same build).  Newest round wins."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    for f in reversed(files):
+        try:
+            d = json.load(open(f))
+            if workload in d:
+                return d[workload], os.path.relpath(f, ROOT)
+        except Exception:
+            continue
+    return {}, None
+
+
+def make_renderer(api, wl, device):
+    r = api.Renderer(device)
+    r.upload_mesh(wl["pos"], wl["tris"], wl["nrm"], wl["uv"])
+    r.upload_materials(wl["materials"])
+    r.set_lights(wl["lights"])
+    return r
+
+
+def profile_passes(api, r, step, n_steps=2):
+    """Per-pass device time per step (CUDA events recorded by the library around each launch on the launching stream)."""
+    r.set_profiling(True)
+    pass_ms = {k: 0.0 for k in api.RAST_PASS_NAMES}
+    for _ in range(n_steps):
+        step()
+        r.sync()
+        for k, v in r.pass_ms().items():
+            pass_ms[k] += v / n_steps
+    r.set_profiling(False)
+    return pass_ms
+
+
+def roofline_record(wl, workload, pass_ms, n_frames, P, visible_tris, step_ms, world_frames_per_step):
+    """Roofline of the dominant kernel: algorithmic bytes per launch / its average launch duration."""
+    peak, peak_src = hbm_peak()
+    batches = (n_frames + 31) // 32
+    frames_per_launch = n_frames / batches
+    ab = algorithmic_bytes(wl, visible_tris, P)
+    dominant = max(("vertex", "setup", "raster", "shade", "clear"), key=lambda k: pass_ms[k])
+    bytes_key = {"vertex": "vertex", "setup": "setup+raster", "raster": "setup+raster", "shade": "shade", "clear": None}[dominant]
+    alg = (8 * P if dominant == "clear" else ab[bytes_key]) * frames_per_launch
+    avg_ms = pass_ms[dominant] / batches
+    achieved = alg / (avg_ms * 1e-3) / 1e9
+    tr, tr_file = ncu_traffic(workload)
+    kname = KERNEL_OF_PASS[dominant]
+    traffic, limiter = None, None
+    if kname in tr:
+        k = tr[kname]
+        traffic = k["dram_bytes_per_launch"] * frames_per_launch / k["frames_per_launch"]
+        limiter = {key: k[key] for key in ("issue_active_pct", "l1tex_throughput_pct", "warp_instructions_per_launch", "lanes_per_instruction", "top_stall") if key in k}
+        limiter["source"] = tr_file
+    rec = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+           "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms, "frames_per_launch": frames_per_launch, "pass_ms_per_step": pass_ms, "limiter": limiter,
+           # every pass of a frame against the HBM roofline, two ways: SURVEY 8(d)'s frame total B (which counts a clear and a key write-back
+           # this pipeline never performs), and the DRAM bytes ncu measured for the kernels of one batch (profiles/), both / step time
+           "whole_frame_algorithmic_bytes": sum(ab.values()),
+           "whole_frame_algorithmic_frac": sum(ab.values()) * world_frames_per_step / (step_ms * 1e-3) / 1e9 / peak}
+    if tr and all("dram_bytes_per_launch" in v for v in tr.values()):
+        per_frame = sum(v["dram_bytes_per_launch"] / v["frames_per_launch"] for v in tr.values())
+        rec["whole_frame_dram_bytes_ncu"] = per_frame
+        rec["whole_frame_dram_frac_ncu"] = per_frame * world_frames_per_step / (step_ms * 1e-3) / 1e9 / peak
+        rec["whole_frame_dram_kernels"] = sorted(tr.keys())
+    return rec
+
+
+def read_frame(r, frames_ptr, depths_ptr, index, W, H):
+    """Frame `index` of a device sequence buffer -> (rgb u8 [3,H,W], depth f32 [H,W] | None) on the host."""
+    P = W * H
+    f = np.empty((3, H, W), np.uint8)
+    r.device_read(frames_ptr + index * 3 * P, f)
+    d = None
+    if depths_ptr:
+        d = np.empty((H, W), np.float32)
+        r.device_read(depths_ptr + index * 4 * P, d)
+    return f, d
+
+
+def check_golden(api, file, case, frame, depth):
+    g = golden_case(file, case)
+    out = {"golden": "tests/golden/%s:%s (hashes of the reference's own frame)" % (file, case), "frame_fnv": api.fnv1a64(frame), "frame_ok": api.fnv1a64(frame) == g["frame_fnv"]}
+    if depth is not None:
+        out["depth_fnv"] = api.fnv1a64(depth)
+        out["depth_ok"] = out["depth_fnv"] == g["depth_fnv"]
+    out["ok"] = out["frame_ok"] and out.get("depth_ok", True)
+    return out
+
+
+def run_single_frame_workload(api, torch, name, dev, local, steps):
+    """One of BASELINE.json's single-frame configs on this GPU: device-resident frames/s, per-pass times, roofline of its
+    dominant kernel and the frame's hashes against the reference's golden ones (computed in-process, inside this run)."""
+    wl = make_workload(name)
+    r = make_renderer(api, wl, local)
+    stream = torch.cuda.current_stream(dev)
+    r.set_stream(stream.cuda_stream)
+    W, H = wl["width"], wl["height"]
+    P = W * H
+    arr = (api.RastArgs * 1)(*[a.to_rast() for a in spin_args(api, wl, 0, 1)])
+    frame_dev = torch.empty((1, 3, H, W), dtype=torch.uint8, device=dev)
+    depth_dev = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+
+    def step():
+        r.draw_frames_device(arr, frame_dev.data_ptr(), depth_dev.data_ptr())
+
+    for _ in range(3):
+        step()
+        r.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    pass_ms = profile_passes(api, r, step)
+    step()
+    r.sync()
+    st = r.stats()
+    tri_ids = r.triangle_ids(W, H)
+    visible_tris = int(len(np.unique(tri_ids[tri_ids != api.NO_TRIANGLE])))
+    frame, depth = frame_dev[0].cpu().numpy(), depth_dev[0].cpu().numpy()
+    gfile, gcase = GOLDEN_OF_WORKLOAD[name]
+    verify = check_golden(api, gfile, gcase, frame, depth)
+    g = golden_case(gfile, gcase)
+    if "tri_fnv" in g:
+        verify["tri_fnv"] = api.fnv1a64(tri_ids)
+        verify["tri_ok"] = verify["tri_fnv"] == g["tri_fnv"]
+        verify["ok"] = verify["ok"] and verify["tri_ok"]
+    rec = {"workload": wl["label"], "value": 1e3 / ms, "unit": UNIT, "ms_per_frame": ms, "steps": steps, "mtris_per_s": len(wl["tris"]) / ms / 1e3,
+           "image": [W, H], "triangles": len(wl["tris"]), "lights": len(wl["lights"]), "stats": st,
+           "roofline": roofline_record(wl, name, pass_ms, 1, P, visible_tris, ms, 1), "verify": verify}
+    del frame_dev, depth_dev
+    r.close()
+    return rec
 
 
 def main():
@@ -256,9 +419,9 @@ def main():
     ap.add_argument("--workload", default="spin1080p")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline record only: no per-config sub-records (N = 1), no gathered / band records (N > 1)")
     ap.add_argument("--frames", type=int, default=0, help="override frames per step (profiling runs)")
-    ap.add_argument("--band-gather", default="peer", choices=["peer", "nccl"], help="N>1 single frame: how the row bands reach rank 0")
-    ap.add_argument("--gather", action="store_true", help="N>1 spin: also gather the finished RGB frames to rank 0 (NCCL) inside the timed region")
+    ap.add_argument("--band-gather", default="peer", choices=["peer", "nccl"], help="--workload <single frame> at N>1: how the row bands reach rank 0")
     opts = ap.parse_args()
 
     wl = make_workload(opts.workload)
@@ -273,7 +436,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from rasteriser_b200 import api
+    from rasteriser_b200 import api, multi
 
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -282,16 +445,34 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    r = api.Renderer(local)
-    r.upload_mesh(wl["pos"], wl["tris"], wl["nrm"], wl["uv"])
-    r.upload_materials(wl["materials"])
-    r.set_lights(wl["lights"])
     stream = torch.cuda.Stream(dev)  # the kernels and the timing events share this stream
     torch.cuda.set_stream(stream)
-    r.set_stream(stream.cuda_stream)
 
-    from rasteriser_b200 import multi
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(step, steps, sync=None):
+        """K steps between two events on the launching stream, barrier + synchronize on both sides, max over ranks -> ms per step."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    r = make_renderer(api, wl, local)
+    r.set_stream(stream.cuda_stream)
     W, H, n = wl["width"], wl["height"], wl["frames"]
     # a single huge frame on N GPUs is split sort-first into row bands and gathered to rank 0 (strong scaling);
     # a frame sequence is partitioned by frame with no communication (weak scaling)
@@ -307,11 +488,6 @@ def main():
     frames_dev = torch.empty((n, 3, rows, W), dtype=torch.uint8, device=dev)
     depths_dev = torch.empty((n, rows, W), dtype=torch.float32, device=dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
     # sort-first bands: by default every rank's shade pass stores its band straight into rank 0's full-size image over
     # NVLink (peer memory, multi.PeerImage) and one tiny all-reduce orders completion; --band-gather nccl keeps the
     # staged variant (band slabs gathered with NCCL, then stitched on rank 0)
@@ -326,9 +502,6 @@ def main():
         if band_mode:  # NCCL over NVLink: band slabs to rank 0, on the same stream as the kernels
             multi.gather_bands(frames_dev[0], H)
             multi.gather_bands(depths_dev[0], H)
-        elif opts.gather and world > 1:  # optional: finished RGB frames of the sequence to rank 0
-            for c in range(0, n, 120):
-                multi.gather_frames(frames_dev[c:c + 120], min(120, n - c) * world)
 
     # ---- value: device-resident ----
     clocks = ClockSampler(local)
@@ -339,26 +512,17 @@ def main():
         r.sync()  # lets the library see the previous call's queue statistics (it grows its work queue lazily)
     barrier()
     launches0 = r.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     clocks.mark()
-    e0.record(stream)
-    for _ in range(opts.steps):
-        step_device()
-    e1.record(stream)
-    barrier()
+    ms_step = timed(step_device, opts.steps)
     clocks.mark()
-    ms = e0.elapsed_time(e1)
+    ms_total = ms_step * opts.steps
     launches = r.launch_count() - launches0
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
     clk = clocks.stop() if rank == 0 else None
     fps = (1 if band_mode else world) * n * opts.steps / (ms_total * 1e-3)
 
     # ---- e2e: host buffers through the public host entry point ----
     e2e = None
+    checksum = None
     if not opts.no_e2e:
         lib = api._lib.load()
         chunk = min(n, 120)  # frames per host call: bounds the pinned staging memory (120 x 14.5 MB at 1080p)
@@ -369,105 +533,85 @@ def main():
         depths_host = np.ctypeslib.as_array(C.cast(db, C.POINTER(C.c_float)), (chunk, rows, W))
         chunks = [(api.RastArgs * len(poses[i:i + chunk]))(*[a.to_rast() for a in poses[i:i + chunk]]) for i in range(0, n, chunk)]
 
-        def step_host():
-            for c in chunks:  # each call returns when its frames are complete in host memory
-                r.draw_frames(c, frames_host[:len(c)], depths_host[:len(c)])
-
-        step_host()
-        barrier()
-        bytes0 = r.d2h_bytes()
-        t0 = time.perf_counter()
-        for _ in range(opts.steps):
+        def host_run(with_depth):
+            def step_host():
+                for c in chunks:  # each call returns when its frames are complete in host memory
+                    r.draw_frames(c, frames_host[:len(c)], depths_host[:len(c)] if with_depth else None)
             step_host()
-        barrier()
-        wall = time.perf_counter() - t0
-        d2h_step = (r.d2h_bytes() - bytes0) // opts.steps  # what actually crossed PCIe (the library counts its copies)
-        t = torch.tensor([wall], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": (1 if band_mode else world) * n * opts.steps / float(t.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(n * 208 + len(chunks) * len(wl["lights"]) * 32), "d2h_bytes_per_step": int(d2h_step), "host_bytes_delivered_per_step": int(n * 7 * P),
+            barrier()
+            bytes0 = r.d2h_bytes()
+            t0 = time.perf_counter()
+            for _ in range(opts.steps):
+                step_host()
+            barrier()
+            wall = max_over_ranks(time.perf_counter() - t0)
+            return (1 if band_mode else world) * n * opts.steps / wall, (r.d2h_bytes() - bytes0) // opts.steps
+
+        v, d2h_step = host_run(True)
+        e2e = {"value": v, "unit": UNIT, "h2d_bytes_per_step": int(n * 208 + len(chunks) * len(wl["lights"]) * 32), "d2h_bytes_per_step": int(d2h_step),
+               "host_bytes_delivered_per_step": int(n * 7 * P),
                "note": "rast_draw_frames with pinned host outputs, %d frames per call: RGB8 + f32 depth of every frame delivered complete in host memory inside the timed region (wall clock, max over ranks); the library copies each frame's covered rectangle over PCIe (d2h_bytes_per_step, counted by the library) and writes the constant background of the host buffers itself on 4 host threads (RAST_SPARSE_COPY=0 copies whole frames)" % chunk}
         checksum = int(frames_host[len(chunks[-1]) // 2].astype(np.uint64).sum())
-        # the same with colour only (the reference's spin loop shows frames; its depth buffer is scratch)
-        def step_host_rgb():
-            for c in chunks:
-                r.draw_frames(c, frames_host[:len(c)], None)
-        step_host_rgb()
-        barrier()
-        bytes0 = r.d2h_bytes()
-        t0 = time.perf_counter()
-        for _ in range(opts.steps):
-            step_host_rgb()
-        barrier()
-        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e["frames_only"] = {"value": (1 if band_mode else world) * n * opts.steps / float(t.item()), "d2h_bytes_per_step": int((r.d2h_bytes() - bytes0) // opts.steps), "host_bytes_delivered_per_step": int(n * 3 * P),
+        v, d2h_step = host_run(False)  # colour only (the reference's spin loop shows frames; its depth buffer is scratch)
+        e2e["frames_only"] = {"value": v, "d2h_bytes_per_step": int(d2h_step), "host_bytes_delivered_per_step": int(n * 3 * P),
                               "note": "same call with depths=NULL: only the RGB8 frames cross PCIe"}
         lib.rast_host_free(fb)
         lib.rast_host_free(db)
-    else:
-        if peer is not None:  # rank 0 holds the stitched frame
-            peer.barrier()
-            got = peer.read()
-            checksum = int(got[0].astype(np.uint64).sum()) if got is not None else 0
-        else:
-            checksum = int(frames_dev[n // 2].sum().item())
 
-    # ---- per-pass kernel durations (CUDA events around each launch, same stream) ----
-    r.set_profiling(True)
-    pass_ms = {k: 0.0 for k in api.RAST_PASS_NAMES}
-    prof_steps = 2
-    for _ in range(prof_steps):
-        step_device()
-        r.sync()
-        for k, v in r.pass_ms().items():
-            pass_ms[k] += v
-    r.set_profiling(False)
+    # ---- per-pass kernel durations (CUDA events around each launch, same stream) and the roofline of the dominant kernel ----
+    pass_ms = profile_passes(api, r, step_device)
     r.draw_frames_device(arr[n - 1:n] if n > 1 else arr, frames_dev.data_ptr(), depths_dev.data_ptr())
     r.sync()
     st = r.stats()
     tri_ids = r.triangle_ids(W, rows)
     visible_tris = int(len(np.unique(tri_ids[tri_ids != api.NO_TRIANGLE])))
-    batches_per_step = (n + 31) // 32
-    launches_per_pass = prof_steps * batches_per_step
-    ab = algorithmic_bytes(wl, visible_tris, P)
-    dominant = max(("vertex", "setup", "raster", "shade", "clear"), key=lambda k: pass_ms[k])
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    frames_per_launch = n / batches_per_step
-    bytes_key = {"vertex": "vertex", "setup": "setup+raster", "raster": "setup+raster", "shade": "shade", "clear": None}[dominant]
-    alg = (8 * P if dominant == "clear" else ab[bytes_key]) * frames_per_launch
-    avg_ms = pass_ms[dominant] / launches_per_pass
-    achieved = alg / (avg_ms * 1e-3) / 1e9
-    total_alg = sum(ab.values())
-    traffic, issue = None, None
-    try:  # DRAM bytes per launch of this kernel from the committed ncu --set full capture (profiles/), scaled to this launch size
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(opts.workload, {})
-        kname = {"vertex": "k_vertex", "setup": "k_setup", "raster": "k_raster_chunks", "shade": "k_resolve_shade", "clear": "k_clear"}[dominant]
-        if kname in tr:
-            traffic = tr[kname]["dram_bytes_per_launch"] * frames_per_launch / tr[kname]["frames_per_launch"]
-            if "issue_active_pct" in tr[kname]:  # what actually limits the kernel (same capture): issue slots, not DRAM
-                issue = {"issue_active_pct": tr[kname]["issue_active_pct"], "l1tex_throughput_pct": tr[kname].get("l1tex_throughput_pct"),
-                         "warp_instructions_per_launch": tr[kname].get("warp_instructions_per_launch"),
-                         "source": "ncu --set full capture under profiles/ (smsp__issue_active.avg.pct_of_peak_sustained_active)"}
-                if "note" in tr[kname]:
-                    issue["note"] = tr[kname]["note"]
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": {"vertex": "k_vertex", "setup": "k_setup", "raster": "k_raster_chunks", "shade": "k_resolve_shade", "clear": "k_clear"}[dominant],
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms, "frames_per_launch": frames_per_launch,
-                "pass_ms_per_step": {k: v / prof_steps for k, v in pass_ms.items()},
-                "limiter": issue, "whole_frame_algorithmic_bytes": total_alg, "whole_frame_achieved_GBs": total_alg * n * world * opts.steps / (ms_total * 1e-3) / 1e9,
-                # all passes of a frame against the HBM roofline (SURVEY.md 8d frame total B / t_frame, per GPU): the passes overlap on two streams
-                "whole_frame_frac": total_alg * n * opts.steps / (ms_total * 1e-3) / 1e9 / peak}
+    roofline = roofline_record(wl, opts.workload, pass_ms, n, P, visible_tris, ms_step, n)
+
+    # ---- the frames against the reference's golden hashes (in-process) ----
+    verify = None
+    if opts.workload == "spin1080p" and n == 720:
+        r.draw_frames_device(arr, frames_dev.data_ptr(), depths_dev.data_ptr())
+        r.sync()
+        verify = {}
+        for k, case in ((0, "suzanne_1920x1080"), (90, "suzanne_1920x1080_spin90")):  # frame k of the sequence lives on rank k mod N at index k // N
+            if k % world == rank:
+                f, d = read_frame(r, frames_dev.data_ptr(), depths_dev.data_ptr(), k // world, W, H)
+                verify["frame_%d" % k] = check_golden(api, "cases.json", case, f, d)
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, verify)
+            verify = {k: v for g in gathered for k, v in g.items()}
+        verify["ok"] = all(v["ok"] for v in verify.values())
+    elif opts.workload in GOLDEN_OF_WORKLOAD and not band_mode:
+        f, d = read_frame(r, frames_dev.data_ptr(), depths_dev.data_ptr(), 0, W, H)
+        verify = check_golden(api, *GOLDEN_OF_WORKLOAD[opts.workload], f, d)
+    elif peer is not None:
+        peer.draw_band(arr)
+        peer.barrier()
+        got = peer.read()
+        if got is not None and opts.workload in GOLDEN_OF_WORKLOAD:
+            verify = check_golden(api, *GOLDEN_OF_WORKLOAD[opts.workload], got[0][0], got[1][0])
+    if checksum is None:
+        checksum = int(frames_dev[n // 2].sum().item())
+    if peer is not None:
+        peer.close()
+        peer = None
+    r.set_band(0, 0)
+
+    # ---- N > 1: the gathers north_star names, inside the same driver-run command ----
+    gathered_rec, bands_rec = None, None
+    if world > 1 and not opts.no_extras and opts.workload == "spin1080p":
+        gathered_rec = run_gathered_spin(api, multi, torch, dist, r, wl, rank, world, dev, timed, opts)
+        bands_rec = run_bands(api, multi, torch, dist, rank, world, dev, local, stream, timed, opts)
+    del frames_dev, depths_dev
+    r.close()
+
+    # ---- N = 1: the other BASELINE configs as sub-records of the same line ----
+    workloads = None
+    if world == 1 and not opts.no_extras and opts.workload == "spin1080p":
+        workloads = {}
+        for name in ("suzanne640", "tess4k", "tess4k_64lights", "overdraw8k"):
+            workloads[name] = run_single_frame_workload(api, torch, name, dev, local, 10)
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     cpu = None
@@ -487,18 +631,136 @@ def main():
         line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": opts.steps, "warmup": max(3, opts.warmup),
                 "ms_per_step": ms_total / opts.steps, "higher_is_better": True, "scaling": "strong" if band_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["label"], "frames_per_step_per_gpu": n, "image": [W, H], "triangles": len(wl["tris"]),
-                           "partition": (("sort-first row bands, each rank's shade pass stores its band into rank 0's image over NVLink peer memory (CUDA IPC), one 4-byte all-reduce per frame orders completion, all inside the timed region" if peer is not None else
+                           "partition": (("sort-first row bands, each rank's shade pass stores its band into rank 0's image over NVLink peer memory (CUDA IPC), one 4-byte all-reduce per frame orders completion, all inside the timed region" if opts.band_gather == "peer" else
                                           "sort-first row bands, band slabs gathered to rank 0 with NCCL inside the timed region") if band_mode else
-                                         "frame k of the global sequence on rank k mod N; no collective" + ("; RGB frames gathered to rank 0 with NCCL" if opts.gather and world > 1 else "")), "l2": "working set per 32-frame batch ~1 GB >> 126 MB L2 (inputs/outputs larger than L2)",
+                                         "frame k of the global sequence on rank k mod N; no collective (the gathers to rank 0 are measured in the `gathered` and `bands` records of this line)"),
+                           "l2": "working set per 32-frame batch ~1 GB >> 126 MB L2 (inputs/outputs larger than L2)",
                            "outputs": "RGB8 planes + f32 depth per frame, written to HBM"},
                 "mtris_per_s": fps * len(wl["tris"]) / 1e6, "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
-                "stats_last_frame": st, "checksum": checksum}
+                "verify": verify, "workloads": workloads, "gathered": gathered_rec, "bands": bands_rec,
+                "library": os.path.relpath(api._lib.LIB_PATH, ROOT), "stats_last_frame": st, "checksum": checksum}
         print(json.dumps(line))
-    if peer is not None:
-        peer.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_gathered_spin(api, multi, torch, dist, r, wl, rank, world, dev, timed, opts):
+    """BASELINE config 2 as written: ONE 720-frame sequence, frame k rendered on rank k mod N, every RGB frame resident in rank
+    0's memory at the end of the step (strong scaling).  Two ways: `peer` -- each rank's shade pass stores its frames straight
+    into their slots of rank 0's sequence buffer over NVLink (CUDA IPC pointer + rast_set_output_frame_stride: the gather IS
+    the kernel's store, one 4-byte all-reduce orders completion); `nccl` -- frames rendered locally, then gathered with NCCL."""
+    W, H, N = wl["width"], wl["height"], 720
+    P = W * H
+    mine = multi.frames_of_rank(N, rank, world)
+    poses = [api.Args(W, H, flat=True, tait_bryan_angles=(0.0, api.spin_angle(0.0, k, N), 0.0)) for k in mine]
+    arr = (api.RastArgs * len(poses))(*[a.to_rast() for a in poses])
+    rec = {"workload": "Suzanne 1920x1080, ONE 720-frame spin sequence, frame k on rank k mod N, RGB8 frames gathered into rank 0's [720][3][1080][1920] buffer (strong scaling)",
+           "frames_per_step": N, "unit": UNIT, "bytes_into_rank0_per_step": int((N - len(multi.frames_of_rank(N, 0, world))) * 3 * P)}
+    # -- peer memory --
+    img = multi.PeerImage(r, W, H, frames=N, with_depth=False)
+
+    def step_peer():
+        img.draw_sequence(arr, rank, world)
+        img.barrier(sync=False)
+
+    for _ in range(2):
+        step_peer()
+    r.sync()
+    ms = timed(step_peer, max(3, opts.steps // 4))
+    rec["peer"] = {"value": N / (ms * 1e-3), "ms_per_step": ms, "rank0_ingress_GBs": rec["bytes_into_rank0_per_step"] / (ms * 1e-3) / 1e9}
+    img.barrier()
+    if rank == 0:
+        ver = {}
+        for k, case in ((0, "suzanne_1920x1080"), (90, "suzanne_1920x1080_spin90")):
+            f, _ = read_frame(r, img.rgb, 0, k, W, H)
+            ver["frame_%d" % k] = check_golden(api, "cases.json", case, f, None)
+        ver["ok"] = all(v["ok"] for v in ver.values())
+        rec["peer"]["verify"] = ver
+    img.close()
+    # -- NCCL gather --
+    local = torch.empty((len(poses), 3, H, W), dtype=torch.uint8, device=dev)
+    out = {}
+
+    def step_nccl():
+        r.draw_frames_device(arr, local.data_ptr(), None)
+        out["seq"] = multi.gather_frames(local, N)
+
+    for _ in range(2):
+        step_nccl()
+    r.sync()
+    ms = timed(step_nccl, max(3, opts.steps // 4))
+    rec["nccl"] = {"value": N / (ms * 1e-3), "ms_per_step": ms, "rank0_ingress_GBs": rec["bytes_into_rank0_per_step"] / (ms * 1e-3) / 1e9}
+    if rank == 0:
+        seq = out["seq"]
+        ver = {}
+        for k, case in ((0, "suzanne_1920x1080"), (90, "suzanne_1920x1080_spin90")):
+            ver["frame_%d" % k] = check_golden(api, "cases.json", case, seq[k].cpu().numpy(), None)
+        ver["ok"] = all(v["ok"] for v in ver.values())
+        rec["nccl"]["verify"] = ver
+    best = max(("peer", "nccl"), key=lambda k: rec[k]["value"])
+    rec["value"], rec["via"] = rec[best]["value"], best
+    rec["limiter"] = "rank 0's NVLink ingress + HBM writes: (N-1)/N of the 4.48 GB sequence enters one GPU per step (NVLink 5: 900 GB/s per direction)"
+    del local, out
+    return rec
+
+
+def run_bands(api, multi, torch, dist, rank, world, dev, local, stream, timed, opts):
+    """BASELINE config 4 on N GPUs: the 8K overdraw frame split sort-first into row bands, stitched in rank 0's memory, by peer
+    stores and by an NCCL gather; the stitched frame's hashes are compared with the reference's (tests/golden/large_cases.json)."""
+    wl = make_workload("overdraw8k")
+    r = make_renderer(api, wl, local)
+    r.set_stream(stream.cuda_stream)
+    W, H = wl["width"], wl["height"]
+    y0, y1 = multi.band_of_rank(H, rank, world)
+    r.set_band(y0, y1)
+    rows = y1 - y0
+    arr = (api.RastArgs * 1)(*[a.to_rast() for a in spin_args(api, wl, 0, 1)])
+    steps = max(5, opts.steps // 2)
+    rec = {"workload": wl["label"] + ", sort-first row bands, stitched frame (RGB8 + f32 depth) resident on rank 0 (strong scaling)", "unit": UNIT,
+           "bytes_into_rank0_per_step": int((H - multi.band_of_rank(H, 0, world)[1]) * W * 7)}
+    g = GOLDEN_OF_WORKLOAD["overdraw8k"]
+    # -- peer memory --
+    img = multi.PeerImage(r, W, H)
+
+    def step_peer():
+        img.draw_band(arr)
+        img.barrier(sync=False)
+
+    for _ in range(3):
+        step_peer()
+        r.sync()
+    ms = timed(step_peer, steps)
+    rec["peer"] = {"value": 1e3 / ms, "ms_per_frame": ms}
+    pm = profile_passes(api, r, step_peer)
+    rec["peer"]["pass_ms_rank0"] = pm
+    img.barrier()
+    got = img.read()
+    if rank == 0:
+        rec["peer"]["verify"] = check_golden(api, g[0], g[1], got[0][0], got[1][0])
+    img.close()
+    # -- NCCL gather of band slabs + stitch on rank 0 --
+    fb = torch.empty((3, rows, W), dtype=torch.uint8, device=dev)
+    db = torch.empty((rows, W), dtype=torch.float32, device=dev)
+    out = {}
+
+    def step_nccl():
+        r.draw_frames_device(arr, fb.data_ptr(), db.data_ptr())
+        out["f"] = multi.gather_bands(fb, H)
+        out["d"] = multi.gather_bands(db, H)
+
+    for _ in range(3):
+        step_nccl()
+        r.sync()
+    ms = timed(step_nccl, steps)
+    rec["nccl"] = {"value": 1e3 / ms, "ms_per_frame": ms}
+    if rank == 0:
+        rec["nccl"]["verify"] = check_golden(api, g[0], g[1], out["f"].cpu().numpy(), out["d"].cpu().numpy())
+    best = max(("peer", "nccl"), key=lambda k: rec[k]["value"])
+    rec["value"], rec["via"] = rec[best]["value"], best
+    rec["gfrag_per_s"] = rec["value"] * 1.66  # 1.66 G covered fragments per frame (oracle counter, DESIGN.md section 5)
+    del fb, db, out
     r.close()
+    return rec
 
 
 if __name__ == "__main__":

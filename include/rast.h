@@ -130,6 +130,12 @@ int rast_set_band(rast_ctx *ctx, uint32_t y0, uint32_t y1);
  * are `pixels` apart instead, so a band can be written straight into its rows of a full-size image: pass
  * frames = image + y0 * W, depths = depth_image + y0 * W and pixels = W * H.  0 restores the default. */
 int rast_set_output_plane_stride(rast_ctx *ctx, uint64_t pixels);
+/* Device-pointer draws of n frames normally fill n consecutive frame slots ([n][3][H][W], [n][H][W]).  With a frame
+ * stride of `frames` the i-th frame of a call goes to slot i * frames instead: N ranks that render frame k of a sequence
+ * on rank k mod N (the spin loop, renderer.cpp:105-111, partitioned by frame) each pass sequence + rank * slot_size and
+ * a stride of N, and together fill ONE sequence buffer in order -- in rank 0's memory over NVLink when the pointer came
+ * from rast_ipc_open.  1 restores the default. */
+int rast_set_output_frame_stride(rast_ctx *ctx, uint32_t frames);
 
 /* ---- peer memory: one process per GPU, bands / frames written straight into rank 0's image over NVLink ---------
  * The reference has no counterpart (single process, single thread).  rast_device_alloc returns plain cudaMalloc
@@ -189,6 +195,10 @@ uint64_t rast_d2h_bytes(rast_ctx *ctx);
  * own div.rn.f32 fast-path sequence, csrc/exact.cuh).  This compares that against IEEE division on the GPU
  * for about n_samples pseudo-random quotients and returns how many differ in any bit (expected: 0). */
 int rast_selftest_division(rast_ctx *ctx, uint64_t n_samples, uint64_t seed, uint64_t *mismatches);
+
+/* FNV-1a-64 of a host buffer: the checksum the golden fixtures of the parity tests record for frames, depth planes and
+ * triangle-id maps (tests/golden/): lets any host verify a frame against them without the test infrastructure. */
+uint64_t rast_fnv1a64(const void *data, uint64_t bytes);
 
 /* pinned host memory for frame / depth buffers */
 void *rast_host_alloc(uint64_t bytes);

@@ -48,6 +48,8 @@ SYMBOLS = {
     "rast_spin_angle": (C.c_float, [C.c_float, C.c_uint32, C.c_uint32]),
     "rast_set_band": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "rast_set_output_plane_stride": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "rast_set_output_frame_stride": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "rast_fnv1a64": (C.c_uint64, [C.c_void_p, C.c_uint64]),
     "rast_device_alloc": (C.c_void_p, [C.c_void_p, C.c_uint64]),
     "rast_device_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rast_device_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),

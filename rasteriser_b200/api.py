@@ -142,6 +142,10 @@ class Renderer:
         """Device-pointer draws write planes `pixels` apart (0 = one band): a band rendered straight into its rows of a full-size image."""
         self._check(self._lib.rast_set_output_plane_stride(self._h, int(pixels)), "rast_set_output_plane_stride")
 
+    def set_output_frame_stride(self, frames):
+        """Device-pointer draws put the i-th frame of a call into slot i * frames (1 = dense): N ranks fill one sequence buffer round-robin."""
+        self._check(self._lib.rast_set_output_frame_stride(self._h, int(frames)), "rast_set_output_frame_stride")
+
     # ---- peer memory (one process per GPU; include/rast.h "peer memory") ----
     def device_alloc(self, nbytes):
         p = self._lib.rast_device_alloc(self._h, int(nbytes))
@@ -268,6 +272,12 @@ def frame_matrices(args):
     out = [np.zeros(16, np.float32) for _ in range(4)]
     _lib.load().rast_frame_matrices(C.byref(a), *[_ptr(o) for o in out])
     return tuple(out)
+
+
+def fnv1a64(a):
+    """FNV-1a-64 of a numpy array's bytes as 16 hex digits -- the checksum format of tests/golden/*.json."""
+    a = np.ascontiguousarray(a)
+    return "%016x" % _lib.load().rast_fnv1a64(a.ctypes.data, a.nbytes)
 
 
 def spin_angle(ry0, k, n_frames):

@@ -37,16 +37,16 @@
 #ifndef RAST_SHADE_PREP
 #define RAST_SHADE_PREP 1
 #endif
-#ifndef RAST_SHADE_PTRS
-#define RAST_SHADE_PTRS 0
-#endif
 #if RAST_TIGHT_TINY
 #include "tight_bbox.h"
 #endif
 
-// Variant switch (off by default, not yet timed): block-level early depth rejection in the chunk rasteriser (raster_item).
+// Block-level early depth rejection in the chunk rasteriser (raster_item<.., BLOCKZ = true>), taken by k_raster_chunks for
+// batches with high overdraw (the early_z condition): on a B200 the 8K overdraw frame's raster pass 5.69 -> 5.04 ms with
+// identical frames; the low-overdraw instantiation is the plain loop (the variant's extra registers and tests cost the 1080p
+// spin batch 4 % when it was compiled into the one loop).  -DRAST_BLOCK_Z=0 builds without it.
 #ifndef RAST_BLOCK_Z
-#define RAST_BLOCK_Z 0
+#define RAST_BLOCK_Z 1
 #endif
 // Device-only primitives used inside the RAST_HD functions, with host stand-ins for tests/emu_device_fns.cu.  By default a host
 // "warp" is one lane at a time (a vote is the lane's own predicate, a warp maximum the lane's own value, an atomic min a plain
@@ -129,6 +129,8 @@ struct View {
     uint32_t band_pixels;     // W * (y1 - y0)
     uint32_t out_plane;       // pixels between the R, G and B planes (and between frames' depth planes) of the OUTPUT: band_pixels, or the
                               // whole frame's W * H when a band is written straight into a full-size image (rast_set_output_plane_stride)
+    uint32_t out_frame_stride;// frame slots between consecutive frames of a call in the OUTPUT (1 = dense; N = every N-th slot of a sequence
+                              // buffer that N ranks fill round-robin, rast_set_output_frame_stride)
 };
 
 struct Batch {
@@ -142,6 +144,7 @@ struct Batch {
     uint32_t queue_cap;
     uint32_t tiny_max_pixels; // bboxes up to this many pixels are rasterised by the setup thread itself
     unsigned long long *counters; // [0] queue count (may exceed queue_cap), [1] queue cursor, [2] overflow flag
+    uint8_t *tile_flags;      // [n_frames][tiles_y][tiles_x]: 1 = some pass may have written a key into that 32 x 16 pixel tile (k_resolve_shade)
     uint32_t *bbox;           // [n_frames][4] or nullptr: covered rectangle of each frame, written by the shade pass as
                               // atomicMin of (x, y, W-1-x, rows-1-y) over the covered pixels (all 0xFFFFFFFF = nothing covered);
                               // the host copies only that rectangle back and fills the rest itself
@@ -322,6 +325,28 @@ __global__ void __launch_bounds__(256) k_vertex(Scene sc, View vw, Batch bt) {
     }
 }
 
+// ---- tile flags ------------------------------------------------------------------------------
+// Tile flags: one byte per SHADE_TILE_W x SHADE_TILE_H (32 x 16) pixel tile of each frame of the batch, set by every pass
+// that may write a key into the tile (k_setup for the triangles it rasterises itself, the raster kernels for every work item
+// they stage -- conservatively: the item's rectangle, not its coverage).  A tile whose flag is 0 holds VIS_EMPTY keys only,
+// so the shade pass neither reads nor resets them: it writes the cleared frame (0, 0, 0 / 1.0f: renderer.cpp:85-86) with a
+// handful of 16-byte stores.  On a Suzanne frame two thirds of the tiles are like that; before, the background cost 35 % of
+// the pass's instructions (40 per group of 32 pixels, ncu source counters) and all of its key reads.
+constexpr uint32_t SHADE_TILE_W = 32, SHADE_TILE_H = 16, SHADE_WARPS = 4;
+
+RAST_HD uint32_t flag_tiles_x(const View &vw) { return (vw.W + SHADE_TILE_W - 1u) / SHADE_TILE_W; }
+RAST_HD uint32_t flag_tiles_y(const View &vw) { return (vw.y1 - vw.y0 + SHADE_TILE_H - 1u) / SHADE_TILE_H; }
+
+// mark the tiles of frame f that the pixel rectangle [x0,x1] x [y0,y1] (image rows, inside the band) overlaps
+__device__ __forceinline__ void mark_tiles(uint8_t *__restrict__ flags, uint32_t f, const View &vw, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1) {
+    const uint32_t tx_n = flag_tiles_x(vw);
+    uint8_t *fl = flags + (size_t)f * tx_n * flag_tiles_y(vw);
+    const uint32_t tx0 = x0 / SHADE_TILE_W, tx1 = x1 / SHADE_TILE_W, ty0 = (y0 - vw.y0) / SHADE_TILE_H, ty1 = (y1 - vw.y0) / SHADE_TILE_H;
+    for (uint32_t ty = ty0; ty <= ty1; ++ty)
+        for (uint32_t tx = tx0; tx <= tx1; ++tx) fl[ty * tx_n + tx] = 1;
+}
+
+
 // ---- K2: triangle setup, cull, classification -----------------------------------------------
 // draw_triangle up to the pixel loops (drawing.cpp:165-188).  Tiny bboxes are rasterised here;
 // larger ones are cut into CHUNK x CHUNK work items for k_raster_chunks.
@@ -406,6 +431,7 @@ __device__ RAST_SETUP_INLINE void setup_triangle(uint32_t t, uint32_t f, float4 
 #if RAST_PROBE_NO_WALK
         if (wx0 != 0xFFFFFFFFu) return; // timing probe only: the per-triangle cost without any pixel test
 #endif
+        mark_tiles(bt.tile_flags, f, vw, wx0, wy0, wx1, wy1); // keys may appear in these tiles (k_resolve_shade skips the others)
         for (uint32_t y = wy0; y <= wy1; ++y)
             for (uint32_t x = wx0; x <= wx1; ++x) test_and_commit(s, x, y, t, vis, vw);
     }
@@ -562,7 +588,7 @@ RAST_HD void stage_item(StagedTris &stg, uint32_t lane, uint32_t tri, uint32_t f
 // Rasterise staged item `it` with the whole warp.  TILE_MODE = false: keys go to the visibility buffer `vis`
 // (global atomicMin; early-z reads it through L2 when `early_z`).  TILE_MODE = true: keys go to the CTA's
 // shared-memory tile `tile_keys` (TILE x TILE, anchored at the item's block origin); early-z always on.
-template <bool TILE_MODE>
+template <bool TILE_MODE, bool BLOCKZ = (RAST_BLOCK_Z != 0)>
 RAST_HD void raster_item(const StagedTris &stg, uint32_t it, uint32_t lane, const View &vw, unsigned long long *vis_all,
                                             unsigned long long *tile_keys, bool early_z) {
     using namespace exact;
@@ -610,7 +636,7 @@ RAST_HD void raster_item(const StagedTris &stg, uint32_t it, uint32_t lane, cons
             // conservative), every fragment of the block would lose its atomicMin: the edge evaluation is skipped for all 128 pixels.
             uint32_t bz_hi[4] = {0u, 0u, 0u, 0u};
             bool bz_loaded = false;
-            if (!TILE_MODE && early_z) {
+            if (BLOCKZ && !TILE_MODE && early_z) {
                 const uint32_t in4 = ymask & (((x >= rx0 && x <= rx1) ? 5u : 0u) | ((x + 1u >= rx0 && x + 1u <= rx1) ? 10u : 0u));
                 const unsigned long long *q0 = vis + (size_t)(y - vw.y0) * vw.W + x;
                 uint32_t mine = 0u;
@@ -727,9 +753,14 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_chunks(Scene sc, V
                 }
             }
             stage_item(stg, lane, tri, f, v0, v1, v2, rx0, ry0, rx1, ry1, rx0, ry0);
+            if (tri != INVALID_TRI && stg.w[23][lane] != 0u) mark_tiles(bt.tile_flags, f, vw, rx0, ry0, rx1, ry1); // some block of the item may hold a candidate
         }
         __syncwarp();
-        for (uint32_t it = 0; it < n_items; ++it) raster_item<false>(stg, it, lane, vw, bt.vis, nullptr, early_z);
+        if (RAST_BLOCK_Z != 0 && early_z) {
+            for (uint32_t it = 0; it < n_items; ++it) raster_item<false, true>(stg, it, lane, vw, bt.vis, nullptr, true);
+        } else {
+            for (uint32_t it = 0; it < n_items; ++it) raster_item<false, false>(stg, it, lane, vw, bt.vis, nullptr, early_z);
+        }
         __syncwarp();
     }
 }
@@ -823,7 +854,10 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_tiles(Scene sc, Vi
     for (uint32_t i = threadIdx.x; i < TILE * TILE; i += blockDim.x) {
         const unsigned long long key = tile_keys[i];
         const uint32_t x = ox + (i % TILE), y = oy + (i / TILE);
-        if (key != VIS_EMPTY && x < vw.W && y < vw.y1) atomicMin(vis + (size_t)(y - vw.y0) * vw.W + x, key);
+        if (key != VIS_EMPTY && x < vw.W && y < vw.y1) {
+            atomicMin(vis + (size_t)(y - vw.y0) * vw.W + x, key);
+            mark_tiles(bt.tile_flags, f, vw, x, y, x, y);
+        }
     }
 }
 
@@ -1106,97 +1140,124 @@ RAST_HD Shaded shade_pixel_prep(uint32_t tri, uint32_t x, uint32_t y, const Scen
 }
 #endif // RAST_SHADE_PREP
 
-// Grid: x = segments of SHADE_THREADS * PX * SHADE_GROUPS pixels along a row, y = row of the band,
-// z = frame of the batch -- no thread divides to find its pixel.  A thread owns SHADE_GROUPS groups of PX
-// adjacent pixels, the groups SHADE_THREADS * PX pixels apart.  Phase 1 issues the key loads of ALL its
-// groups and keeps one coverage bit per pixel: with most of a frame background, a warp that fetched only
-// 256 B of keys and then waited for DRAM left the memory system idle (measured: long-scoreboard bound at
-// 40 warps/SM).  Phase 2 walks the groups; a covered group re-reads its keys (L1 hits) and shades.
-// PX = 4 (W % 4 == 0, 16-byte aligned outputs): keys in as 2 x 16 B, colour out as one uchar4 per plane,
-// depth as one float4 (CImg planar layout, CImg.h:11715-11721).  PX = 1: scalar loads/stores, any W.
-#ifndef RAST_SHADE_THREADS
-#define RAST_SHADE_THREADS 128
-#endif
-#ifndef RAST_SHADE_GROUPS
-#define RAST_SHADE_GROUPS 16
-#endif
-constexpr int SHADE_THREADS = RAST_SHADE_THREADS;
-constexpr int SHADE_GROUPS = RAST_SHADE_GROUPS; // measured (1080p spin step, shade ms): 2 -> 10.3, 4 -> 8.94, 8 -> 8.60, 15 -> 8.11, 16 -> 8.20, 24 -> 8.60, 32 -> 8.64
-__host__ __device__ constexpr int shade_groups(int px) { return px * SHADE_GROUPS <= 32 ? SHADE_GROUPS : 32 / px; } // one coverage bit per pixel in a 32-bit mask
+// Grid: x = 128-pixel columns (one 32-pixel tile column per warp), y = 16-row tile rows of the band, z = frame of the batch
+// -- no thread divides to find its pixel.  A warp owns one 32 x 16 tile: lane = column, 16 rows.  Untouched tile: constant
+// stores, done.  Touched tile: phase 1 issues the key loads of all 16 rows (256 contiguous bytes per row and warp) and keeps
+// one coverage bit per row; phase 2 walks the rows, a covered pixel is shaded from the prepared record / gathered
+// attributes, and the results go to the warp's slice of shared memory; the tile then leaves in 16-byte stores (WIDE: W % 16
+// == 0 and 16-byte aligned planes; otherwise scalar stores from the loop, any W).  Planar output, CImg layout
+// (CImg.h:11715-11721).
+// Output addresses of a tile, computed from the block indices alone.  The touched path calls this AFTER its row loop with
+// freshly (opaquely) re-read indices, so that no output pointer stays live across the shading code (72 -> 64 registers).
+struct TileOut { uint8_t *rgb; float *depth; uint32_t nrows, x0; };
+__device__ __forceinline__ TileOut tile_out(const View &vw, uint8_t *rgb, float *depth, uint32_t bx, uint32_t by, uint32_t bz, uint32_t warp) {
+    TileOut t;
+    t.x0 = (bx * SHADE_WARPS + warp) * SHADE_TILE_W;
+    const uint32_t r0 = by * SHADE_TILE_H;
+    t.nrows = min(SHADE_TILE_H, vw.y1 - vw.y0 - r0);
+    const size_t tile0 = (size_t)r0 * vw.W + t.x0, P = vw.out_plane;
+    t.rgb = rgb + (size_t)bz * 3 * P * vw.out_frame_stride + tile0;
+    t.depth = depth ? depth + (size_t)bz * P * vw.out_frame_stride + tile0 : nullptr;
+    return t;
+}
 
-template <int PX>
-__device__ __forceinline__ void load_keys(const unsigned long long *p, unsigned long long (&keys)[PX]) {
-    if (PX == 4) {
-        const ulonglong2 k01 = *reinterpret_cast<const ulonglong2 *>(p), k23 = *reinterpret_cast<const ulonglong2 *>(p + 2);
-        keys[0] = k01.x; keys[PX > 1 ? 1 : 0] = k01.y; keys[PX > 2 ? 2 : 0] = k23.x; keys[PX > 3 ? 3 : 0] = k23.y;
-    } else {
-        keys[0] = *p;
+// One tile leaves in 16-byte stores: colour planes 16 rows x 32 B = one store per lane and plane, depth 16 rows x 128 B =
+// four stores per lane.  src_* = the warp's shared-memory slices, or nullptr for the cleared frame (0 / 1.0f).
+__device__ __forceinline__ void store_tile_wide(const TileOut &t, const View &vw, uint32_t lane, const uint8_t *src_rgb, const float *src_d) {
+    const uint32_t W = vw.W, cr = lane >> 1, cx = (lane & 1u) * 16u;
+    const size_t P = vw.out_plane;
+    if (cr < t.nrows && t.x0 + cx < W) {
+        uint8_t *p = t.rgb + (size_t)cr * W + cx;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        constexpr uint32_t PL = SHADE_TILE_W * SHADE_TILE_H;
+        *reinterpret_cast<uint4 *>(p) = src_rgb ? reinterpret_cast<const uint4 *>(src_rgb)[lane] : z;
+        *reinterpret_cast<uint4 *>(p + P) = src_rgb ? reinterpret_cast<const uint4 *>(src_rgb + PL)[lane] : z;
+        *reinterpret_cast<uint4 *>(p + 2 * P) = src_rgb ? reinterpret_cast<const uint4 *>(src_rgb + 2 * PL)[lane] : z;
+    }
+    if (t.depth) {
+        const uint32_t dx = (lane & 7u) * 4u;
+        const float4 one = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+#pragma unroll
+        for (uint32_t j = 0; j < 4u; ++j) {
+            const uint32_t dr = j * 4u + (lane >> 3);
+            if (dr < t.nrows && t.x0 + dx < W) *reinterpret_cast<float4 *>(t.depth + (size_t)dr * W + dx) = src_d ? reinterpret_cast<const float4 *>(src_d)[j * 32u + lane] : one;
+        }
     }
 }
 
-// (forcing 10 or 12 CTAs per SM -- 48 / 40 registers -- measured 7-10 % slower than the 56 registers the compiler picks)
-#if RAST_SHADE_PREP
-template <int PX, bool PRE_NORMALS, bool FLAT, bool PREP = false>
-#else
-template <int PX, bool PRE_NORMALS, bool FLAT>
+#ifndef RAST_SHADE_MIN_BLOCKS
+#define RAST_SHADE_MIN_BLOCKS 0
 #endif
-__global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View vw, Batch bt, const __grid_constant__ LightTable lt,
-                                                                 const LightDev *__restrict__ lights, uint8_t *__restrict__ rgb, float *__restrict__ depth,
-                                                                 uint32_t keep_frame) {
-    constexpr uint32_t STRIDE = SHADE_THREADS * PX;
-    constexpr int GROUPS = shade_groups(PX);
-    const uint32_t xb = blockIdx.x * (STRIDE * GROUPS) + threadIdx.x * PX;
-    const uint32_t row = blockIdx.y, f = blockIdx.z;
-    const uint32_t P = vw.out_plane;
-    // One per-thread index serves the keys and both outputs: the frame's offset into each output (which differs from the
-    // offset into the keys: 3 planes per frame, and planes that may be larger than the band) is folded into block-uniform
-    // base pointers.  (A second per-thread 64-bit index cost 4 registers = one resident CTA per SM = 3.6 % of the pass.)
-    const size_t i0 = (size_t)f * vw.band_pixels + (size_t)row * vw.W + xb;
-    rgb += (size_t)f * (3 * (size_t)P - vw.band_pixels);      // rgb[i0] = R plane of frame f, this thread's first pixel
-    if (depth) depth += (size_t)f * ((size_t)P - vw.band_pixels);
-    unsigned long long *vis = bt.vis + i0;
+template <bool WIDE, bool PRE_NORMALS, bool FLAT, bool PREP>
+#if RAST_SHADE_MIN_BLOCKS > 0
+__global__ void __launch_bounds__(SHADE_WARPS * 32, RAST_SHADE_MIN_BLOCKS) k_resolve_shade(
+#else
+__global__ void __launch_bounds__(SHADE_WARPS * 32) k_resolve_shade(
+#endif
+    Scene sc, View vw, Batch bt, const __grid_constant__ LightTable lt, const LightDev *__restrict__ lights, uint8_t *__restrict__ rgb, float *__restrict__ depth, uint32_t keep_frame) {
+    __shared__ __align__(16) uint8_t s_rgb[SHADE_WARPS][3][SHADE_TILE_W * SHADE_TILE_H];
+    __shared__ __align__(16) float s_depth[SHADE_WARPS][SHADE_TILE_W * SHADE_TILE_H];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t x0 = (blockIdx.x * SHADE_WARPS + warp) * SHADE_TILE_W; // warp-uniform
+    if (x0 >= vw.W) return;
+    const uint32_t ty = blockIdx.y, f = blockIdx.z;
+    const uint32_t W = vw.W, rows = vw.y1 - vw.y0, r0 = ty * SHADE_TILE_H;
+    const uint32_t nrows = min(SHADE_TILE_H, rows - r0);
+    const uint32_t x = x0 + lane;
+    const bool in_x = x < W;
+    unsigned long long *vis = bt.vis + (size_t)f * vw.band_pixels + (size_t)r0 * W + x; // this lane's column of keys
+    uint8_t *flag = bt.tile_flags + ((size_t)f * flag_tiles_y(vw) + ty) * flag_tiles_x(vw) + x0 / SHADE_TILE_W;
     const bool reset = f != keep_frame; // hand the keys back as VIS_EMPTY (the next batch then needs no clear pass)
 
-    // phase 1: all key loads in flight at once; one coverage bit per pixel
-    uint32_t covered = 0;
+    bool touched = *flag != 0;
+    uint32_t covered = 0; // bit r: this lane's pixel of row r has a winning triangle
+    if (touched) {
+        // phase 1: all key loads in flight at once.  The low word is the triangle index, 0xFFFFFFFF only in VIS_EMPTY
+        // (rast_upload_mesh caps the triangle count below it).
 #pragma unroll
-    for (int g = 0; g < GROUPS; ++g) {
-        if (xb + g * STRIDE < vw.W) {
-            unsigned long long keys[PX];
-            load_keys<PX>(vis + g * STRIDE, keys);
-#pragma unroll
-            for (int k = 0; k < PX; ++k) covered |= (keys[k] != VIS_EMPTY ? 1u : 0u) << (g * PX + k);
-            // (prefetch.global.L1 of the winning triangle's record from here, while the key is in a register, measured
-            //  33 % SLOWER: 8.20 -> 10.92 ms per 720 frames -- the records are L1 / L2 hits anyway and the prefetches only load the LSU)
+        for (uint32_t r = 0; r < SHADE_TILE_H; ++r)
+            if (r < nrows && in_x) covered |= (*reinterpret_cast<const uint32_t *>(vis + (size_t)r * W) != INVALID_TRI ? 1u : 0u) << r;
+        touched = __any_sync(0xFFFFFFFFu, covered != 0u);
+        if (reset && lane == 0u) *flag = 0;
+    }
+
+    if (!touched) { // nothing drawn here: the cleared frame (renderer.cpp:85-86)
+        const TileOut t = tile_out(vw, rgb, depth, blockIdx.x, ty, f, warp);
+        if (WIDE) {
+            store_tile_wide(t, vw, lane, nullptr, nullptr);
+        } else if (in_x) {
+            const size_t P = vw.out_plane;
+            for (uint32_t r = 0; r < nrows; ++r) {
+                const size_t o = (size_t)r * W + lane;
+                t.rgb[o] = 0; t.rgb[o + P] = 0; t.rgb[o + 2 * P] = 0;
+                if (t.depth) t.depth[o] = 1.0f;
+            }
         }
+        return;
     }
 
     // Covered rectangle of the frame (for the sparse device-to-host copy): one warp-wide min per bound, and an atomic
     // only when the warp would move that bound (the plain read may be stale -- then the atomic is merely redundant).
-    if (bt.bbox != nullptr && __any_sync(0xFFFFFFFFu, covered != 0u)) {
-        uint32_t lo = 0xFFFFFFFFu, hic = 0xFFFFFFFFu;
+    if (bt.bbox != nullptr) {
+        uint32_t lo = 0xFFFFFFFFu, hic = 0xFFFFFFFFu, ylo = 0xFFFFFFFFu, yhic = 0xFFFFFFFFu;
         if (covered) {
-            const uint32_t b0 = (uint32_t)__ffs((int)covered) - 1u, b1 = 31u - (uint32_t)__clz((int)covered); // bit = group * PX + pixel
-            lo = xb + (b0 / PX) * STRIDE + (b0 % PX);
-            hic = vw.W - 1u - (xb + (b1 / PX) * STRIDE + (b1 % PX));
+            lo = x;
+            hic = W - 1u - x;
+            ylo = r0 + (uint32_t)__ffs((int)covered) - 1u;
+            yhic = rows - 1u - (r0 + 31u - (uint32_t)__clz((int)covered));
         }
         lo = __reduce_min_sync(0xFFFFFFFFu, lo);
         hic = __reduce_min_sync(0xFFFFFFFFu, hic);
-        if ((threadIdx.x & 31u) == 0u) {
+        ylo = __reduce_min_sync(0xFFFFFFFFu, ylo);
+        yhic = __reduce_min_sync(0xFFFFFFFFu, yhic);
+        if (lane == 0u) {
             uint32_t *bb = bt.bbox + 4u * f;
-            const uint32_t rows = vw.y1 - vw.y0;
             if (lo < bb[0]) atomicMin(bb + 0, lo);
-            if (row < bb[1]) atomicMin(bb + 1, row);
+            if (ylo < bb[1]) atomicMin(bb + 1, ylo);
             if (hic < bb[2]) atomicMin(bb + 2, hic);
-            if (rows - 1u - row < bb[3]) atomicMin(bb + 3, rows - 1u - row);
+            if (yhic < bb[3]) atomicMin(bb + 3, yhic);
         }
     }
-
-    // (The background is a quarter of this kernel's instructions -- 35 per group of 32 pixels, mostly address arithmetic --
-    //  but writing it in bursts is slower than walking the loop: a straight-line exit for all-background warps measured
-    //  8.29 -> 9.49 ms per 720 frames, and writing every uncovered group up front at immediate offsets, then looping over the
-    //  covered groups only, 8.35 -> 9.15 ms, both at 56 registers and with fewer instructions executed.  Bursts of byte stores
-    //  queue in front of the other warps' gathers; the loop spaces them out.)
 
     // phase 2.  The per-frame base pointers are made opaque so that a gather is "base + index * 16" (one
     // IMAD.WIDE) instead of a 64-bit add of the frame offset to every index followed by the address computation.
@@ -1206,64 +1267,47 @@ __global__ void __launch_bounds__(SHADE_THREADS) k_resolve_shade(Scene sc, View 
     const float4 *rv = reinterpret_cast<const float4 *>(rv_base);
     const float4 *cn = reinterpret_cast<const float4 *>(cn_base);
     const FrameParams *fp = bt.frames + f;
-#if RAST_SHADE_PTRS
-    uint8_t *out_r = rgb + i0;
-    float *out_d = depth + i0; // only dereferenced when depth != nullptr
-#endif
 #if RAST_SHADE_PREP
     unsigned long long prep_base = (unsigned long long)(PREP ? bt.prep + (size_t)f * sc.T * PREP_QUADS : nullptr);
     asm volatile("" : "+l"(prep_base));
     const float4 *prep = reinterpret_cast<const float4 *>(prep_base);
 #endif
+    const bool cw = __ldg(&fp->wind_clockwise) != 0u;
+    uint8_t *sr = &s_rgb[warp][0][lane];
+    float *sd = &s_depth[warp][lane];
+    TileOut tn{}; // non-WIDE: scalar stores from the loop
+    if (!WIDE) tn = tile_out(vw, rgb, depth, blockIdx.x, ty, f, warp);
 #pragma unroll 1
-    for (uint32_t g = 0; g < GROUPS; ++g) {
-        const uint32_t x0 = xb + g * STRIDE;
-        if (x0 >= vw.W) break;
-        Shaded px[PX];
-#pragma unroll
-        for (int k = 0; k < PX; ++k) { px[k].r = px[k].g = px[k].b = 0u; px[k].depth = 1.0f; } // renderer.cpp:85-86
-        const uint32_t cov = (covered >> (g * PX)) & ((1u << PX) - 1u);
-        if (cov) {
-            unsigned long long keys[PX];
-            load_keys<PX>(vis + g * STRIDE, keys);
-            const bool cw = __ldg(&fp->wind_clockwise) != 0u;
-#pragma unroll
-            for (int k = 0; k < PX; ++k)
-                if (cov & (1u << k)) {
+    for (uint32_t r = 0; r < nrows; ++r) {
+        Shaded px;
+        px.r = px.g = px.b = 0u; px.depth = 1.0f; // renderer.cpp:85-86
+        if ((covered >> r) & 1u) {
+            unsigned long long *key = vis + (size_t)r * W;
+            const uint32_t tri = *reinterpret_cast<const uint32_t *>(key); // L1 / L2 hit: phase 1 fetched the line
 #if RAST_SHADE_PREP
-                    if (PREP) px[k] = shade_pixel_prep((uint32_t)keys[k], x0 + k, vw.y0 + row, sc, prep, cw, lt, lights);
-                    else
+            if (PREP) px = shade_pixel_prep(tri, x, vw.y0 + r0 + r, sc, prep, cw, lt, lights);
+            else
 #endif
-                    px[k] = shade_pixel<PRE_NORMALS, FLAT>((uint32_t)keys[k], x0 + k, vw.y0 + row, sc, rv, cn, FLAT ? fp->modelview : fp->normal_m, cw, lt, lights);
-                }
-            if (reset) {
-                if (PX == 4) {
-                    *reinterpret_cast<ulonglong2 *>(vis + g * STRIDE) = make_ulonglong2(VIS_EMPTY, VIS_EMPTY);
-                    *reinterpret_cast<ulonglong2 *>(vis + g * STRIDE + 2) = make_ulonglong2(VIS_EMPTY, VIS_EMPTY);
-                } else {
-                    vis[g * STRIDE] = VIS_EMPTY;
-                }
-            }
+            px = shade_pixel<PRE_NORMALS, FLAT>(tri, x, vw.y0 + r0 + r, sc, rv, cn, FLAT ? fp->modelview : fp->normal_m, cw, lt, lights);
+            if (reset) *key = VIS_EMPTY;
         }
-#if RAST_SHADE_PTRS
-        // variant (not yet timed): two running per-thread pointers instead of one index re-based on three planes every group
-        if (PX == 1) {
-            out_r[0] = (uint8_t)px[0].r; out_r[P] = (uint8_t)px[0].g; out_r[2 * (size_t)P] = (uint8_t)px[0].b;
-            if (depth) *out_d = px[0].depth;
-            out_r += STRIDE; out_d += STRIDE;
-            continue;
+        if (WIDE) {
+            sr[r * SHADE_TILE_W] = (uint8_t)px.r;
+            sr[r * SHADE_TILE_W + SHADE_TILE_W * SHADE_TILE_H] = (uint8_t)px.g;
+            sr[r * SHADE_TILE_W + 2 * SHADE_TILE_W * SHADE_TILE_H] = (uint8_t)px.b;
+            sd[r * SHADE_TILE_W] = px.depth;
+        } else if (in_x) {
+            const size_t o = (size_t)r * W + lane, P = vw.out_plane;
+            tn.rgb[o] = (uint8_t)px.r; tn.rgb[o + P] = (uint8_t)px.g; tn.rgb[o + 2 * P] = (uint8_t)px.b;
+            if (tn.depth) tn.depth[o] = px.depth;
         }
-#endif
-        const size_t o = i0 + g * STRIDE, i = o;
-        if (PX == 4) {
-            *reinterpret_cast<uchar4 *>(rgb + o) = make_uchar4(px[0].r, px[PX > 1 ? 1 : 0].r, px[PX > 2 ? 2 : 0].r, px[PX > 3 ? 3 : 0].r);
-            *reinterpret_cast<uchar4 *>(rgb + o + P) = make_uchar4(px[0].g, px[PX > 1 ? 1 : 0].g, px[PX > 2 ? 2 : 0].g, px[PX > 3 ? 3 : 0].g);
-            *reinterpret_cast<uchar4 *>(rgb + o + 2 * (size_t)P) = make_uchar4(px[0].b, px[PX > 1 ? 1 : 0].b, px[PX > 2 ? 2 : 0].b, px[PX > 3 ? 3 : 0].b);
-            if (depth) *reinterpret_cast<float4 *>(depth + i) = make_float4(px[0].depth, px[PX > 1 ? 1 : 0].depth, px[PX > 2 ? 2 : 0].depth, px[PX > 3 ? 3 : 0].depth);
-        } else {
-            rgb[o] = (uint8_t)px[0].r; rgb[o + P] = (uint8_t)px[0].g; rgb[o + 2 * (size_t)P] = (uint8_t)px[0].b;
-            if (depth) depth[i] = px[0].depth;
-        }
+    }
+    if (WIDE) {
+        __syncwarp();
+        uint32_t bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z, wp = threadIdx.x >> 5;
+        asm volatile("" : "+r"(bx), "+r"(by), "+r"(bz), "+r"(wp)); // opaque: recomputed here, not carried through the loop
+        const TileOut t = tile_out(vw, rgb, depth, bx, by, bz, wp);
+        store_tile_wide(t, vw, threadIdx.x & 31u, &s_rgb[wp][0][0], &s_depth[wp][0]);
     }
 }
 

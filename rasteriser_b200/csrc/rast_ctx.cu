@@ -138,8 +138,8 @@ struct rast_ctx {
     uint32_t n_materials = 0;
     bool pre_normals = false;
     uint64_t out_plane_stride = 0; // rast_set_output_plane_stride (0 = the band's own pixel count)
+    uint32_t out_frame_stride = 1; // rast_set_output_frame_stride (device-pointer draws: frame slots between consecutive frames)
     bool flat_face = false; // extension mode of the current call (rast_args.flat == RAST_FLAT_FACE)
-    int shade_px = 1; // adjacent pixels per group in the shade pass: 1 measured faster than 4 (uchar4/float4 stores) on B200
     rk::LightTable light_table{}; // first PARAM_LIGHTS lights, passed to the shade kernel by value
     std::vector<rast_light> lights;
 
@@ -158,7 +158,7 @@ struct rast_ctx {
     // batch parity): the front passes of the next batch run on a high-priority stream of their own while the shade pass of
     // this batch runs on the context's stream -- both are issue-bound at 66-76 % and fill each other's gaps (two contexts
     // on one GPU measured +13 %; RAST_OVERLAP=0 serialises).
-    DeviceBuffer d_rv[2], d_cn[2], d_vis[2];
+    DeviceBuffer d_rv[2], d_cn[2], d_vis[2], d_flags[2]; // d_flags: one byte per 32 x 16 pixel tile and frame (kernels.cuh, tile flags), cleared with the keys
 #if RAST_SHADE_PREP
     DeviceBuffer d_prep[2];   // prepared shading records of a batch (kernels.cuh, k_prepare_tris), by pipeline slot like rv / cn
     bool use_prep = false;    // this call: records fit (decided in draw_frames_impl)
@@ -186,7 +186,7 @@ struct rast_ctx {
     uint32_t list_cap = 1u << 22, items_cap = 1u << 25;
     // visibility-buffer bookkeeping: slots [0, vis_clean_slots) of band size vis_clean_pixels hold VIS_EMPTY,
     // except vis_dirty_slot (the last frame of the previous call, kept for inspection)
-    uint32_t vis_clean_slots[2] = {0, 0}, vis_clean_pixels[2] = {0, 0};
+    uint32_t vis_clean_slots[2] = {0, 0}, vis_clean_pixels[2] = {0, 0}, vis_clean_w[2] = {0, 0};
     int vis_dirty_slot[2] = {-1, -1};
 
     // most recent frame (for rast_read_triangle_ids / rast_depth_to_u8 / stats)
@@ -234,6 +234,7 @@ rk::View make_view(const rast_ctx *ctx, uint32_t W, uint32_t H) {
     }
     v.band_pixels = W * (v.y1 - v.y0);
     v.out_plane = v.band_pixels;
+    v.out_frame_stride = 1;
     return v;
 }
 
@@ -272,13 +273,12 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     bt.rv = ctx->d_rv[ps].as<float4>();
     bt.cn = ctx->pre_normals ? ctx->d_cn[ps].as<float4>() : nullptr;
     bt.vis = ctx->d_vis[ps].as<unsigned long long>();
-    // 4 adjacent pixels per lane (uchar4 / float4 stores) is slower into local memory but faster when
-    // the output is a band of a larger -- typically another GPU's -- image: 128-byte instead of 32-byte stores over NVLink
-    // (8K overdraw frame on 8 GPUs: 1.13 -> 1.05 ms)
-    const bool want_vec = ctx->shade_px == 4 || vw.out_plane != vw.band_pixels;
-    const bool vec = !ctx->flat_face && want_vec && (vw.W % 4u == 0u) && (vw.out_plane % 4u == 0u) && (((uintptr_t)rgb_dev & 15u) == 0u) && (((uintptr_t)depth_dev & 15u) == 0u);
+    bt.tile_flags = ctx->d_flags[ps].as<uint8_t>();
+    const size_t flags_per_frame = (size_t)rk::flag_tiles_x(vw) * rk::flag_tiles_y(vw);
+    // the tile leaves the shade pass in 16-byte stores when every plane row segment is 16-byte aligned
+    const bool wide = (vw.W % 16u == 0u) && (vw.out_plane % 16u == 0u) && (((uintptr_t)rgb_dev & 15u) == 0u) && (((uintptr_t)depth_dev & 15u) == 0u);
 #if RAST_SHADE_PREP
-    bt.prep = (ctx->use_prep && bt.cn && !vec) ? ctx->d_prep[ps].as<float4>() : nullptr; // the 4-pixel shade variant gathers; no records for it
+    bt.prep = (ctx->use_prep && bt.cn) ? ctx->d_prep[ps].as<float4>() : nullptr;
 #endif
     bt.queue = ctx->d_queue.as<uint2>();
     bt.queue_cap = ctx->queue_cap;
@@ -296,20 +296,23 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     if (prof) cudaEventRecord(ctx->ev_pass[0], st);
     // Visibility slots known to be empty (handed back by the previous shade pass) are not cleared again.
     uint32_t n_clear_launches = 0;
-    if (ctx->vis_clean_pixels[ps] != vw.band_pixels) { ctx->vis_clean_slots[ps] = 0; ctx->vis_dirty_slot[ps] = -1; }
+    if (ctx->vis_clean_pixels[ps] != vw.band_pixels || ctx->vis_clean_w[ps] != vw.W) { ctx->vis_clean_slots[ps] = 0; ctx->vis_dirty_slot[ps] = -1; } // (the tile-flag layout follows W)
     if (ctx->vis_dirty_slot[ps] >= 0 && (uint32_t)ctx->vis_dirty_slot[ps] < ctx->vis_clean_slots[ps]) { // only one dirty slot is tracked: settle it now
         rk::k_clear<<<grid_for(((size_t)vw.band_pixels + 1) / 2, 256), 256, 0, st>>>(bt.vis + (size_t)ctx->vis_dirty_slot[ps] * vw.band_pixels, vw.band_pixels);
+        RAST_CUDA(ctx, cudaMemsetAsync(bt.tile_flags + (size_t)ctx->vis_dirty_slot[ps] * flags_per_frame, 0, flags_per_frame, st));
         ctx->vis_dirty_slot[ps] = -1;
         n_clear_launches++;
     }
     if (count > ctx->vis_clean_slots[ps]) {
         const size_t from = (size_t)ctx->vis_clean_slots[ps] * vw.band_pixels;
         rk::k_clear<<<grid_for((n_vis - from + 1) / 2, 256), 256, 0, st>>>(bt.vis + from, n_vis - from);
+        RAST_CUDA(ctx, cudaMemsetAsync(bt.tile_flags + (size_t)ctx->vis_clean_slots[ps] * flags_per_frame, 0, (count - ctx->vis_clean_slots[ps]) * flags_per_frame, st));
         if (ctx->vis_dirty_slot[ps] >= (int)ctx->vis_clean_slots[ps]) ctx->vis_dirty_slot[ps] = -1;
         ctx->vis_clean_slots[ps] = count;
         n_clear_launches++;
     }
     ctx->vis_clean_pixels[ps] = vw.band_pixels;
+    ctx->vis_clean_w[ps] = vw.W;
     if (prof) cudaEventRecord(ctx->ev_pass[1], st);
     if (sc.V) rk::k_vertex<<<dim3(grid_for((size_t)sc.V + (bt.cn ? sc.Nn : 0u), 256), count), 256, 0, st>>>(sc, vw, bt);
 #if RAST_SHADE_PREP
@@ -368,21 +371,21 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     if (vw.band_pixels) {
         const rk::LightDev *lights = ctx->d_lights[ctx->cs].as<rk::LightDev>();
         const uint32_t rows = vw.y1 - vw.y0;
-        const dim3 grid(grid_for(vw.W, rk::SHADE_THREADS * rk::shade_groups(vec ? 4 : 1) * (vec ? 4 : 1)), rows, count);
+        const dim3 grid(grid_for(vw.W, rk::SHADE_TILE_W * rk::SHADE_WARPS), grid_for(rows, rk::SHADE_TILE_H), count);
+        const unsigned threads = rk::SHADE_WARPS * 32;
         const rk::LightTable &lt = ctx->light_table;
-        if (ctx->flat_face) { // extension: face normals (never taken for reference-compatible arguments)
-            rk::k_resolve_shade<1, false, true><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
-        } else if (vec) {
-            if (bt.cn) rk::k_resolve_shade<4, true, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
-            else rk::k_resolve_shade<4, false, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
-        } else {
+#define RAST_SHADE_LAUNCH(PRE, FLAT, PREP)                                                                                                        \
+        do {                                                                                                                                      \
+            if (wide) rk::k_resolve_shade<true, PRE, FLAT, PREP><<<grid, threads, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame); \
+            else rk::k_resolve_shade<false, PRE, FLAT, PREP><<<grid, threads, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);     \
+        } while (0)
+        if (ctx->flat_face) RAST_SHADE_LAUNCH(false, true, false); // extension: face normals (never taken for reference-compatible arguments)
 #if RAST_SHADE_PREP
-            if (bt.cn && bt.prep) rk::k_resolve_shade<1, true, false, true><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
-            else
+        else if (bt.cn && bt.prep) RAST_SHADE_LAUNCH(true, false, true);
 #endif
-            if (bt.cn) rk::k_resolve_shade<1, true, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
-            else rk::k_resolve_shade<1, false, false><<<grid, rk::SHADE_THREADS, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);
-        }
+        else if (bt.cn) RAST_SHADE_LAUNCH(true, false, false);
+        else RAST_SHADE_LAUNCH(false, false, false);
+#undef RAST_SHADE_LAUNCH
     }
     if (prof) cudaEventRecord(ctx->ev_pass[5], st);
     ctx->launches += n_tile_launches + n_clear_launches + (sc.V ? 1 : 0) + ((sc.T && vw.band_pixels) ? 2 : 0) + (vw.band_pixels ? 1 : 0);
@@ -538,6 +541,8 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
         if (ctx->out_plane_stride < vw.band_pixels) return fail(ctx, RAST_EINVAL, "rast_draw_frames: output plane stride smaller than the band");
         vw.out_plane = (uint32_t)ctx->out_plane_stride;
     }
+    if (device_ptrs) vw.out_frame_stride = ctx->out_frame_stride;
+    const size_t S = vw.out_frame_stride;
     const size_t P = vw.out_plane;
     const uint32_t B = batch_capacity(ctx, vw);
     const uint32_t nb = n < B ? n : B;
@@ -582,8 +587,10 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
                         (n > nb || (size_t)nb * P >= ((size_t)16 << 20));
         if (ctx->use_prep) RAST_CUDA(ctx, ctx->d_prep[ps].reserve((size_t)nb * ctx->scene.T * rk::PREP_QUADS * sizeof(float4)));
 #endif
-        if ((size_t)nb * P * 8 > ctx->d_vis[ps].bytes) { ctx->vis_clean_slots[ps] = 0; ctx->vis_dirty_slot[ps] = -1; }
+        const size_t flag_bytes = (size_t)nb * rk::flag_tiles_x(vw) * rk::flag_tiles_y(vw);
+        if ((size_t)nb * P * 8 > ctx->d_vis[ps].bytes || flag_bytes > ctx->d_flags[ps].bytes) { ctx->vis_clean_slots[ps] = 0; ctx->vis_dirty_slot[ps] = -1; }
         RAST_CUDA(ctx, ctx->d_vis[ps].reserve((size_t)nb * P * 8));
+        RAST_CUDA(ctx, ctx->d_flags[ps].reserve(flag_bytes));
     }
     // camera-space normals are precomputed per frame when there are few of them relative to the image;
     // for huge meshes the shade pass transforms only the normals of winning triangles instead
@@ -651,13 +658,13 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
         uint8_t *rgb_dst;
         float *depth_dst = nullptr;
         if (device_ptrs && frames) {
-            rgb_dst = frames + (size_t)first * 3 * P;
+            rgb_dst = frames + (size_t)first * S * 3 * P;
         } else {
             RAST_CUDA(ctx, ctx->d_rgb[slot].reserve((size_t)nb * 3 * P));
             rgb_dst = ctx->d_rgb[slot].as<uint8_t>();
         }
         if (device_ptrs && depths) {
-            depth_dst = depths + (size_t)first * P;
+            depth_dst = depths + (size_t)first * S * P;
         } else if (depths || n == 1) { // a single frame always keeps its depth (rast_depth_to_u8); a sequence only on request
             RAST_CUDA(ctx, ctx->d_depth[slot].reserve((size_t)nb * P * 4));
             depth_dst = ctx->d_depth[slot].as<float>();
@@ -682,7 +689,7 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
         ctx->last_batch_pixels = (unsigned long long)count * vw.band_pixels;
         ctx->last_slot_frame = count - 1;
         ctx->last_frames_offset = first + count - 1;
-        ctx->last_depth_dev = depth_dst ? depth_dst + (size_t)(count - 1) * P : nullptr;
+        ctx->last_depth_dev = depth_dst ? depth_dst + (size_t)(count - 1) * S * P : nullptr;
         ctx->have_frame = true;
 
         if (!device_ptrs) {
@@ -759,7 +766,6 @@ int rast_create(int device, rast_ctx **out) {
         return RAST_ECUDA;
     }
     ctx->stream = ctx->own_stream;
-    if (const char *e = getenv("RAST_SHADE_PX")) ctx->shade_px = atoi(e) == 4 ? 4 : 1;
     if (const char *e = getenv("RAST_SPARSE_COPY")) ctx->sparse_copy = atoi(e) != 0;
     if (const char *e = getenv("RAST_OVERLAP")) ctx->overlap = atoi(e) != 0;
 #if RAST_SHADE_PREP
@@ -783,7 +789,7 @@ void rast_destroy(rast_ctx *ctx) {
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->front_stream) cudaStreamSynchronize(ctx->front_stream);
     DeviceBuffer *dev[] = {&ctx->d_pos, &ctx->d_nrm, &ctx->d_uv, &ctx->d_vidx, &ctx->d_attr, &ctx->d_mats, &ctx->d_texels, &ctx->d_frames[0], &ctx->d_frames[1], &ctx->d_lights[0], &ctx->d_lights[1],
-                           &ctx->d_rv[0], &ctx->d_rv[1], &ctx->d_cn[0], &ctx->d_cn[1], &ctx->d_tiles, &ctx->d_list, &ctx->d_items, &ctx->d_vis[0], &ctx->d_vis[1], &ctx->d_bbox[0], &ctx->d_bbox[1], &ctx->d_queue, &ctx->d_counters, &ctx->d_aux, &ctx->d_rgb[0], &ctx->d_rgb[1], &ctx->d_depth[0], &ctx->d_depth[1]};
+                           &ctx->d_rv[0], &ctx->d_rv[1], &ctx->d_cn[0], &ctx->d_cn[1], &ctx->d_tiles, &ctx->d_list, &ctx->d_items, &ctx->d_vis[0], &ctx->d_vis[1], &ctx->d_flags[0], &ctx->d_flags[1], &ctx->d_bbox[0], &ctx->d_bbox[1], &ctx->d_queue, &ctx->d_counters, &ctx->d_aux, &ctx->d_rgb[0], &ctx->d_rgb[1], &ctx->d_depth[0], &ctx->d_depth[1]};
     for (DeviceBuffer *b : dev) b->release();
 #if RAST_SHADE_PREP
     ctx->d_prep[0].release();
@@ -972,6 +978,20 @@ int rast_set_output_plane_stride(rast_ctx *ctx, uint64_t pixels) {
     if (pixels > 0xFFFFFFFFull) return fail(ctx, RAST_EINVAL, "rast_set_output_plane_stride: more than 2^32 pixels");
     ctx->out_plane_stride = pixels;
     return RAST_OK;
+}
+
+int rast_set_output_frame_stride(rast_ctx *ctx, uint32_t frames) {
+    if (!ctx) return RAST_EINVAL;
+    if (frames == 0) return fail(ctx, RAST_EINVAL, "rast_set_output_frame_stride: stride must be at least 1");
+    ctx->out_frame_stride = frames;
+    return RAST_OK;
+}
+
+uint64_t rast_fnv1a64(const void *data, uint64_t bytes) {
+    uint64_t h = 1469598103934665603ull;
+    const unsigned char *b = static_cast<const unsigned char *>(data);
+    for (uint64_t i = 0; i < bytes; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
 }
 
 // ---- device memory shared between the processes of one node (one process per GPU) -----------------------------

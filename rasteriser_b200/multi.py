@@ -76,26 +76,31 @@ class PeerImage:
 
         img = PeerImage(renderer, W, H)                  # collective: every rank calls it
         img.draw_band(args)                              # this rank's rows of one frame, into rank dst's image
-        img.draw_frames(args_list, first_index, stride)  # frames first_index, +stride, ... of a sequence
+        img.draw_sequence(args_list, first_index, stride)  # frames first_index, +stride, ... of a sequence, batched
         img.barrier(); rgb, depth = img.read()           # rank dst: numpy copies (other ranks: None)
     """
 
-    def __init__(self, renderer, width, height, frames=1, dst=0, group=None):
+    def __init__(self, renderer, width, height, frames=1, dst=0, group=None, with_depth=True):
         self.r, self.W, self.H, self.frames, self.dst, self.group = renderer, int(width), int(height), int(frames), dst, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         P = self.W * self.H
-        self.rgb_bytes, self.depth_bytes = self.frames * 3 * P, self.frames * 4 * P
+        self.rgb_bytes, self.depth_bytes = self.frames * 3 * P, (self.frames * 4 * P if with_depth else 0)
         self._owned = self.rank == dst
         self._flag = None
+        self.depth = 0  # with_depth=False: colour only (the spin sequence gathers RGB frames)
         handles = [None, None]
         if self._owned:
-            self.rgb, self.depth = renderer.device_alloc(self.rgb_bytes), renderer.device_alloc(self.depth_bytes)
-            handles = [renderer.ipc_export(self.rgb), renderer.ipc_export(self.depth)]
+            self.rgb = renderer.device_alloc(self.rgb_bytes)
+            if with_depth:
+                self.depth = renderer.device_alloc(self.depth_bytes)
+            handles = [renderer.ipc_export(self.rgb), renderer.ipc_export(self.depth) if with_depth else None]
         if self.world > 1:
             dist.broadcast_object_list(handles, src=dst, group=group)
             if not self._owned:
-                self.rgb, self.depth = renderer.ipc_open(handles[0]), renderer.ipc_open(handles[1])
+                self.rgb = renderer.ipc_open(handles[0])
+                if with_depth:
+                    self.depth = renderer.ipc_open(handles[1])
 
     def draw_band(self, args, frame=0):
         """Render this rank's row band of one frame (rast_set_band must hold band_of_rank) into the shared image.
@@ -106,16 +111,20 @@ class PeerImage:
         one = args if isinstance(args, (list, tuple, ctypes.Array)) else [args]
         self.r.set_output_plane_stride(P)
         try:
-            self.r.draw_frames_device(one, self.rgb + frame * 3 * P + y0 * self.W, self.depth + (frame * P + y0 * self.W) * 4)
+            self.r.draw_frames_device(one, self.rgb + frame * 3 * P + y0 * self.W, (self.depth + (frame * P + y0 * self.W) * 4) if self.depth else None)
         finally:
             self.r.set_output_plane_stride(0)
 
-    def draw_frames(self, args_list, first_index, stride):
-        """Render frames first_index, first_index + stride, ... of the sequence into their slots of the shared image."""
+    def draw_sequence(self, args_list, first_index, stride):
+        """Render frames first_index, first_index + stride, ... of the sequence into their slots of the shared image, batched
+        through the kernels like any multi-frame call: rast_set_output_frame_stride puts the i-th frame of the call into slot
+        first_index + i * stride, so N ranks (first_index = rank, stride = N) fill one sequence buffer in order."""
         P = self.W * self.H
-        for i, a in enumerate(args_list):  # slots are `stride` frames apart: one call per frame keeps the ABI's dense layout
-            k = first_index + i * stride
-            self.r.draw_frames_device([a], self.rgb + k * 3 * P, self.depth + k * P * 4)
+        self.r.set_output_frame_stride(stride)
+        try:
+            self.r.draw_frames_device(args_list, self.rgb + first_index * 3 * P, (self.depth + first_index * P * 4) if self.depth else None)
+        finally:
+            self.r.set_output_frame_stride(1)
 
     def barrier(self, sync=True):
         """After it returns on rank dst (and the current stream has passed it), every rank's band is in the image.
@@ -138,10 +147,11 @@ class PeerImage:
             return None
         import numpy as np
         rgb = np.empty((self.frames, 3, self.H, self.W), np.uint8)
-        depth = np.empty((self.frames, self.H, self.W), np.float32)
+        depth = np.empty((self.frames, self.H, self.W), np.float32) if self.depth else None
         self.r.sync()
         self.r.device_read(self.rgb, rgb)
-        self.r.device_read(self.depth, depth)
+        if self.depth:
+            self.r.device_read(self.depth, depth)
         return rgb, depth
 
     def close(self):
@@ -150,9 +160,11 @@ class PeerImage:
             dist.barrier(group=self.group)  # nobody unmaps while a peer may still write
         if not self._owned:
             self.r.ipc_close(self.rgb)
-            self.r.ipc_close(self.depth)
+            if self.depth:
+                self.r.ipc_close(self.depth)
         if self.world > 1:
             dist.barrier(group=self.group)
         if self._owned:
             self.r.device_free(self.rgb)
-            self.r.device_free(self.depth)
+            if self.depth:
+                self.r.device_free(self.depth)

@@ -46,6 +46,19 @@ if rank == 0:
 else:
     assert got is None
 img.close()
+# a frame sequence partitioned by frame (frame k on rank k mod N), every rank's shade pass storing its frames into their slots
+# of rank 0's sequence buffer (rast_set_output_frame_stride), colour only
+N = 7
+seq_poses = [api.Args(320, 240, tait_bryan_angles=(0.0, api.spin_angle(0.1, k, N), 0.0)) for k in range(N)]
+want_seq, _ = r.draw_frames(seq_poses)
+seq = multi.PeerImage(r, 320, 240, frames=N, with_depth=False)
+seq.draw_sequence(seq_poses[rank::world], rank, world)
+seq.barrier()
+got_seq = seq.read()
+if rank == 0:
+    assert got_seq[1] is None and np.array_equal(got_seq[0], want_seq), "sequence differs"
+    print("SEQ_OK")
+seq.close()
 dist.destroy_process_group()
 r.close()
 '''
@@ -61,4 +74,4 @@ def test_bands_written_into_rank0_image_over_peer_memory(tmp_path):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
-    assert "PEER_OK" in out.stdout
+    assert "PEER_OK" in out.stdout and "SEQ_OK" in out.stdout
