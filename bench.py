@@ -389,6 +389,7 @@ def run_single_frame_workload(api, torch, name, dev, local, steps):
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / steps
     pass_ms = profile_passes(api, r, step)
+    r.set_keep_visibility(True)  # after the timed region: the last frame keeps its keys for the statistics and the id hash
     step()
     r.sync()
     st = r.stats()
@@ -560,10 +561,12 @@ def main():
 
     # ---- per-pass kernel durations (CUDA events around each launch, same stream) and the roofline of the dominant kernel ----
     pass_ms = profile_passes(api, r, step_device)
+    r.set_keep_visibility(True)  # after the timed regions: the last frame keeps its keys for the statistics
     r.draw_frames_device(arr[n - 1:n] if n > 1 else arr, frames_dev.data_ptr(), depths_dev.data_ptr())
     r.sync()
     st = r.stats()
     tri_ids = r.triangle_ids(W, rows)
+    r.set_keep_visibility(False)
     visible_tris = int(len(np.unique(tri_ids[tri_ids != api.NO_TRIANGLE])))
     roofline = roofline_record(wl, opts.workload, pass_ms, n, P, visible_tris, ms_step, n)
 

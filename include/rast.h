@@ -177,6 +177,11 @@ int rast_sync(rast_ctx *ctx);
  * [H][W] u32, host pointer.  This is the visibility buffer's low word; parity tests compare it
  * bit-exactly with the oracle. */
 int rast_read_triangle_ids(rast_ctx *ctx, uint32_t *tri_ids);
+/* The shade pass normally hands every visibility key back as "empty" while it consumes it, so that the next call needs no
+ * clear pass.  With keep_visibility the LAST frame of each call keeps its keys for rast_read_triangle_ids / rast_get_stats
+ * (the two return RAST_ESTATE otherwise), at the price of one clear of that frame's keys in the next call (8 bytes per
+ * pixel).  Off by default: the reference has no such output. */
+int rast_set_keep_visibility(rast_ctx *ctx, int enabled);
 /* depth_buffer.normalize(0,255) + uchar truncation (renderer.cpp:93; CImg.h:26786-26794,52410) of
  * the most recent frame's depth, computed on the device; out = host [H][W] u8. */
 int rast_depth_to_u8(rast_ctx *ctx, uint8_t *out);

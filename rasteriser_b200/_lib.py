@@ -60,6 +60,7 @@ SYMBOLS = {
     "rast_draw_frame_device": (C.c_int, [C.c_void_p, C.POINTER(RastArgs), C.c_void_p, C.c_void_p]),
     "rast_draw_frames": (C.c_int, [C.c_void_p, C.POINTER(RastArgs), C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]),
     "rast_sync": (C.c_int, [C.c_void_p]),
+    "rast_set_keep_visibility": (C.c_int, [C.c_void_p, C.c_int]),
     "rast_read_triangle_ids": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rast_depth_to_u8": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rast_get_stats": (C.c_int, [C.c_void_p, C.POINTER(RastStats)]),

@@ -230,6 +230,10 @@ class Renderer:
         return self._band[1] - self._band[0] if getattr(self, "_band", None) else height
 
     # ---- auxiliary ----
+    def set_keep_visibility(self, on):
+        """Keep the last frame's visibility keys of every call (triangle_ids / stats need it; costs a clear in the next call)."""
+        self._check(self._lib.rast_set_keep_visibility(self._h, int(bool(on))), "rast_set_keep_visibility")
+
     def triangle_ids(self, width, height):
         out = np.empty((height, width), np.uint32)
         self._check(self._lib.rast_read_triangle_ids(self._h, _ptr(out)), "rast_read_triangle_ids")

@@ -159,7 +159,7 @@ struct TileBins {
     uint32_t *start;       // [n_frames * tiles] exclusive prefix of count (k_plan)
     uint32_t *fill;        // [n_frames * tiles] running cursor (k_fill)
     uint2 *list;           // queued triangles (triangle, frame) (k_setup)
-    uint32_t *items;       // triangle ids grouped by tile (k_fill)
+    uint2 *items;          // (triangle id, depth key of its nearest vertex) grouped by tile (k_fill)
     uint32_t list_cap, items_cap;
     uint32_t tiles_x, tiles_y; // tiles of one frame (band)
 };
@@ -590,7 +590,7 @@ RAST_HD void stage_item(StagedTris &stg, uint32_t lane, uint32_t tri, uint32_t f
 // shared-memory tile `tile_keys` (TILE x TILE, anchored at the item's block origin); early-z always on.
 template <bool TILE_MODE, bool BLOCKZ = (RAST_BLOCK_Z != 0)>
 RAST_HD void raster_item(const StagedTris &stg, uint32_t it, uint32_t lane, const View &vw, unsigned long long *vis_all,
-                                            unsigned long long *tile_keys, bool early_z) {
+                                            unsigned long long *tile_keys, bool early_z, const volatile uint32_t *block_far = nullptr) {
     using namespace exact;
     const uint32_t tri = stg.w[19][it];
     const uint32_t live = stg.w[23][it];
@@ -636,6 +636,19 @@ RAST_HD void raster_item(const StagedTris &stg, uint32_t it, uint32_t lane, cons
             // conservative), every fragment of the block would lose its atomicMin: the edge evaluation is skipped for all 128 pixels.
             uint32_t bz_hi[4] = {0u, 0u, 0u, 0u};
             bool bz_loaded = false;
+            if (BLOCKZ && TILE_MODE && block_far != nullptr) {
+                // tile schedule: the farthest depth stored in this block of the CTA's shared-memory tile, refreshed by the CTA's warps as
+                // they go (k_raster_tiles); a stale value is a larger one, i.e. conservative
+                const uint32_t kmax = block_far[strip * 2u + column];
+                if (kmax != 0xFFFFFFFFu) {
+                    const uint32_t bxa = max(ox + column * 16u, rx0), bxb = min(ox + column * 16u + 15u, rx1);
+                    const uint32_t bya = max(oy + strip * 8u, ry0), byb = min(oy + strip * 8u + 7u, ry1);
+                    const float dxa = (float)(bxa - rx0), dxb = (float)(bxb - rx0), dya = (float)(bya - ry0), dyb = (float)(byb - ry0);
+                    const float lb = bz_o + fminf(bz_gx * dxa, bz_gx * dxb) + fminf(bz_gy * dya, bz_gy * dyb) - bz_m;
+                    const uint32_t far_bits = (kmax & 0x80000000u) ? (kmax ^ 0x80000000u) : ~kmax; // inverse of depth_key
+                    if (lb > exact::u2f(far_bits)) continue;
+                }
+            }
             if (BLOCKZ && !TILE_MODE && early_z) {
                 const uint32_t in4 = ymask & (((x >= rx0 && x <= rx1) ? 5u : 0u) | ((x + 1u >= rx0 && x + 1u <= rx1) ? 10u : 0u));
                 const unsigned long long *q0 = vis + (size_t)(y - vw.y0) * vw.W + x;
@@ -768,7 +781,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_chunks(Scene sc, V
 // ---- screen-tile binning ----------------------------------------------------------------------
 // Single CTA: decides whether this batch takes the binned schedule and, if so, turns the per-tile counts into
 // run offsets.  Falls back to the chunk schedule when the list or the item array would overflow.
-__global__ void __launch_bounds__(1024) k_plan_tiles(Batch bt, TileBins tb) {
+__global__ void __launch_bounds__(1024) k_plan_tiles(Batch bt, TileBins tb, unsigned long long min_bbox_area) {
     __shared__ uint32_t partial[1024];
     const uint32_t n = bt.n_frames * tb.tiles_x * tb.tiles_y;
     const uint32_t per = (n + 1023u) / 1024u;
@@ -784,13 +797,15 @@ __global__ void __launch_bounds__(1024) k_plan_tiles(Batch bt, TileBins tb) {
         __syncthreads();
     }
     const unsigned long long total = partial[1023];
-    const bool ok = bt.counters[CNT_LIST] <= tb.list_cap && total <= tb.items_cap;
+    // (min_bbox_area: the host asked for bins because the PREVIOUS call showed high overdraw; a batch that turns out not to have it
+    //  keeps the chunk queue, which k_setup filled as well)
+    const bool ok = bt.counters[CNT_LIST] <= tb.list_cap && total <= tb.items_cap && bt.counters[CNT_BBOX_AREA] >= min_bbox_area;
     uint32_t run = threadIdx.x ? partial[threadIdx.x - 1] : 0u;
     for (uint32_t i = lo; i < hi; ++i) { tb.start[i] = run; run += tb.count[i]; }
     if (threadIdx.x == 0) {
         bt.counters[CNT_TILE_ITEMS] = total;
         bt.counters[CNT_TILE_MODE] = ok ? 1ull : 0ull;
-        if (!ok) bt.counters[CNT_TILE_OVERFLOW] = 1ull;
+        if (bt.counters[CNT_LIST] > tb.list_cap || total > tb.items_cap) bt.counters[CNT_TILE_OVERFLOW] = 1ull;
     }
 }
 
@@ -802,20 +817,40 @@ __global__ void __launch_bounds__(256) k_fill_tiles(Scene sc, View vw, Batch bt,
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         const uint2 ent = tb.list[e];
         const float4 *rv = bt.rv + (size_t)ent.y * sc.V;
-        const BBox bb = bounding_box(rv[sc.vidx0[ent.x]], rv[sc.vidx1[ent.x]], rv[sc.vidx2[ent.x]], vw);
+        const float4 v0 = rv[sc.vidx0[ent.x]], v1 = rv[sc.vidx1[ent.x]], v2 = rv[sc.vidx2[ent.x]];
+        const BBox bb = bounding_box(v0, v1, v2, vw);
+        const uint32_t zkey = depth_key(fminf(fminf(v0.z, v1.z), v2.z)); // nearest vertex: the tile's CTA processes its bin near to far (order only)
         const uint32_t tx0 = bb.x0 / TILE, tx1 = bb.x1 / TILE, ty0 = (bb.y0 - vw.y0) / TILE, ty1 = (bb.y1 - vw.y0) / TILE;
         for (uint32_t ty = ty0; ty <= ty1; ++ty)
             for (uint32_t tx = tx0; tx <= tx1; ++tx) {
                 const uint32_t g = ent.y * tiles + ty * tb.tiles_x + tx;
-                tb.items[tb.start[g] + atomicAdd(&tb.fill[g], 1u)] = ent.x;
+                tb.items[tb.start[g] + atomicAdd(&tb.fill[g], 1u)] = make_uint2(ent.x, zkey);
             }
     }
 }
 
-// One CTA per (tile, frame): the tile's keys live in shared memory until every triangle of the bin is done.
-__global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_tiles(Scene sc, View vw, Batch bt, TileBins tb) {
-    __shared__ StagedTris stage_all[RASTER_WARPS];
+// One CTA per (tile, frame): the tile's 1024 keys live in shared memory until every triangle of the bin is done, so the depth
+// test, the early rejections and the atomics never leave the SM (the chunk queue re-read 10.8 GB of keys from DRAM on the 8K
+// overdraw frame: 265 MB of keys, 2 x the L2, visited in random order).  What makes the schedule pay at depth complexity 50:
+//   * the bin is processed NEAR TO FAR: a counting sort of its entries by the depth key of the triangle's nearest vertex (64
+//     buckets between the bin's own minimum and maximum, in shared memory; bins above TILE_SORT_MAX entries stay unsorted --
+//     the order only decides how much work is skipped, never the result);
+//   * every warp keeps refreshing the FARTHEST stored depth of "its" two 16 x 8 blocks (block_far); an item whose depth plane,
+//     less the proven margin of stage_item, lies behind it on a block skips that block without evaluating an edge function,
+//     and an item that loses on all its blocks is dropped when it is staged.  After the first few layers almost everything is;
+//   * 128 items are staged at a time by the whole CTA (lane = item) and then dealt to the four warps round-robin, so the near
+//     items -- the ones that do real work -- are spread over all warps.
+constexpr uint32_t TILE_WARPS = 4, TILE_SORT_MAX = 2048, TILE_SORT_BUCKETS = 64;
+
+__device__ __forceinline__ float key_to_depth(uint32_t k) { return exact::u2f((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k); } // inverse of depth_key
+
+__global__ void __launch_bounds__(TILE_WARPS * 32) k_raster_tiles(Scene sc, View vw, Batch bt, TileBins tb) {
+    __shared__ StagedTris stage_all[TILE_WARPS];
     __shared__ unsigned long long tile_keys[TILE * TILE];
+    __shared__ uint32_t order[TILE_SORT_MAX];
+    __shared__ uint32_t hist[TILE_SORT_BUCKETS];
+    __shared__ uint32_t block_far[8];
+    __shared__ uint32_t zrange[2];
     if (bt.counters[CNT_TILE_MODE] == 0ull) return;
     const uint32_t f = blockIdx.y, tile = blockIdx.x;
     const uint32_t g = f * tb.tiles_x * tb.tiles_y + tile;
@@ -823,19 +858,62 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_tiles(Scene sc, Vi
     if (n == 0u) return;
     const uint32_t first = tb.start[g];
     const uint32_t ox = (tile % tb.tiles_x) * TILE, oy = vw.y0 + (tile / tb.tiles_x) * TILE;
-    for (uint32_t i = threadIdx.x; i < TILE * TILE; i += blockDim.x) tile_keys[i] = VIS_EMPTY;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    // pixels of the tile that lie outside the image can never be written: key 0 (nearer than anything) keeps them out of the far bounds
+    for (uint32_t i = tid; i < TILE * TILE; i += TILE_WARPS * 32) tile_keys[i] = (ox + (i % TILE) < vw.W && oy + (i / TILE) < vw.y1) ? VIS_EMPTY : 0ull;
+    if (tid < 8u) block_far[tid] = 0xFFFFFFFFu;
+    if (tid < TILE_SORT_BUCKETS) hist[tid] = 0u;
+    if (tid == 0u) { zrange[0] = 0xFFFFFFFFu; zrange[1] = 0u; }
     __syncthreads();
 
-    StagedTris &stg = stage_all[threadIdx.x >> 5];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    // ---- near-to-far order of the bin (counting sort on the nearest-vertex depth key) ----
+    const uint2 *bin = tb.items + first;
+    const bool sorted = n <= TILE_SORT_MAX;
+    if (sorted) {
+        uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+        for (uint32_t i = tid; i < n; i += TILE_WARPS * 32) { const uint32_t z = bin[i].y; lo = min(lo, z); hi = max(hi, z); }
+        lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+        hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+        if (lane == 0u) { atomicMin(&zrange[0], lo); atomicMax(&zrange[1], hi); }
+        __syncthreads();
+        const uint32_t zlo = zrange[0];
+        const float scale = (float)(TILE_SORT_BUCKETS - 1u) / fmaxf((float)(zrange[1] - zlo), 1.0f); // monotone in the key: equal keys share a bucket
+        for (uint32_t i = tid; i < n; i += TILE_WARPS * 32) atomicAdd(&hist[min((uint32_t)((float)(bin[i].y - zlo) * scale), TILE_SORT_BUCKETS - 1u)], 1u);
+        __syncthreads();
+        if (warp == 0u) { // exclusive scan of the 64 bucket counts: two per lane
+            const uint32_t a = hist[2u * lane], b = hist[2u * lane + 1u];
+            uint32_t incl = a + b;
+#pragma unroll
+            for (uint32_t d = 1; d < 32u; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += v; }
+            hist[2u * lane] = incl - a - b;
+            hist[2u * lane + 1u] = incl - b;
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < n; i += TILE_WARPS * 32) {
+            const uint2 e = bin[i];
+            order[atomicAdd(&hist[min((uint32_t)((float)(e.y - zlo) * scale), TILE_SORT_BUCKETS - 1u)], 1u)] = e.x;
+        }
+        __syncthreads();
+    }
+
     const float4 *rv = bt.rv + (size_t)f * sc.V;
-    for (uint32_t base = warp * 32u; base < n; base += RASTER_WARPS * 32u) {
-        const uint32_t n_items = min(32u, n - base);
-        {   // ---- stage: lane = item ----
+    // the farthest stored depth of block b of the tile (strip b >> 1, column b & 1): lane -> row lane >> 2, four adjacent pixels
+    auto refresh_far = [&](uint32_t b) {
+        const volatile unsigned long long *p = tile_keys + ((b >> 1) * 8u + (lane >> 2)) * TILE + (b & 1u) * 16u + (lane & 3u) * 4u;
+        uint32_t m = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m = max(m, (uint32_t)(p[k] >> 32));
+        m = __reduce_max_sync(0xFFFFFFFFu, m);
+        if (lane == 0u) *reinterpret_cast<volatile uint32_t *>(&block_far[b]) = m;
+    };
+    for (uint32_t base = 0; base < n; base += TILE_WARPS * 32) {
+        const uint32_t m_items = min(TILE_WARPS * 32u, n - base);
+        {   // ---- stage: thread = item ----
+            StagedTris &stg = stage_all[warp];
             uint32_t tri = INVALID_TRI, rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;
             float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;
-            if (lane < n_items) {
-                tri = tb.items[first + base + lane];
+            if (tid < m_items) {
+                tri = sorted ? order[base + tid] : bin[base + tid].x;
                 v0 = rv[sc.vidx0[tri]]; v1 = rv[sc.vidx1[tri]]; v2 = rv[sc.vidx2[tri]];
                 const BBox bb = bounding_box(v0, v1, v2, vw);
                 rx0 = max(bb.x0, ox); ry0 = max(bb.y0, oy);
@@ -843,22 +921,47 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_tiles(Scene sc, Vi
                 if (rx0 > rx1 || ry0 > ry1) tri = INVALID_TRI;
             }
             stage_item(stg, lane, tri, f, v0, v1, v2, rx0, ry0, rx1, ry1, ox, oy);
+#if RAST_BLOCK_Z
+            if (tri != INVALID_TRI && stg.w[23][lane] != 0u) {
+                // the whole item against the farthest depth stored anywhere in the tile: lower bound of its depth plane over its rectangle
+                uint32_t kmax = 0u;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) kmax = max(kmax, *reinterpret_cast<volatile uint32_t *>(&block_far[b]));
+                if (kmax != 0xFFFFFFFFu) {
+                    const float gx = exact::u2f(stg.w[28][lane]), gy = exact::u2f(stg.w[29][lane]);
+                    const float lb = exact::u2f(stg.w[27][lane]) + fminf(0.f, gx * (float)(rx1 - rx0)) + fminf(0.f, gy * (float)(ry1 - ry0)) - exact::u2f(stg.w[30][lane]);
+                    if (lb > key_to_depth(kmax)) stg.w[23][lane] = 0u; // behind everything already in the tile: no live block
+                }
+            }
+#endif
         }
-        __syncwarp();
-        for (uint32_t it = 0; it < n_items; ++it) raster_item<true>(stg, it, lane, vw, nullptr, tile_keys, true);
-        __syncwarp();
+        __syncthreads();
+        // ---- rasterise: item j of the round goes to warp j % 4 (the nearest items first, one per warp) ----
+        uint32_t since = 0;
+        for (uint32_t j = warp; j < m_items; j += TILE_WARPS, ++since) {
+            if ((since & 3u) == 0u) { refresh_far(2u * warp); refresh_far(2u * warp + 1u); }
+#if RAST_BLOCK_Z
+            raster_item<true, true>(stage_all[j >> 5], j & 31u, lane, vw, nullptr, tile_keys, true, block_far);
+#else
+            raster_item<true, false>(stage_all[j >> 5], j & 31u, lane, vw, nullptr, tile_keys, true);
+#endif
+        }
+        refresh_far(2u * warp); refresh_far(2u * warp + 1u);
+        __syncthreads();
     }
-    __syncthreads();
     // merge the tile into the visibility buffer (tiny triangles were written there directly by k_setup)
     unsigned long long *vis = bt.vis + (size_t)f * vw.band_pixels;
-    for (uint32_t i = threadIdx.x; i < TILE * TILE; i += blockDim.x) {
+    bool any = false;
+    for (uint32_t i = tid; i < TILE * TILE; i += TILE_WARPS * 32) {
         const unsigned long long key = tile_keys[i];
         const uint32_t x = ox + (i % TILE), y = oy + (i / TILE);
         if (key != VIS_EMPTY && x < vw.W && y < vw.y1) {
             atomicMin(vis + (size_t)(y - vw.y0) * vw.W + x, key);
-            mark_tiles(bt.tile_flags, f, vw, x, y, x, y);
+            any = true;
         }
     }
+    // thread tid covers columns tid % 32 of rows tid / 32 + 4k: warp w = rows w, w + 4, ...: both tile-flag rows (16 pixel rows each)
+    if (__any_sync(0xFFFFFFFFu, any) && lane == 0u) mark_tiles(bt.tile_flags, f, vw, ox, oy, min(ox + TILE - 1u, vw.W - 1u), min(oy + TILE - 1u, vw.y1 - 1u));
 }
 
 // ---- K4: resolve + deferred shading ---------------------------------------------------------
@@ -1140,49 +1243,42 @@ RAST_HD Shaded shade_pixel_prep(uint32_t tri, uint32_t x, uint32_t y, const Scen
 }
 #endif // RAST_SHADE_PREP
 
-// Grid: x = 128-pixel columns (one 32-pixel tile column per warp), y = 16-row tile rows of the band, z = frame of the batch
-// -- no thread divides to find its pixel.  A warp owns one 32 x 16 tile: lane = column, 16 rows.  Untouched tile: constant
-// stores, done.  Touched tile: phase 1 issues the key loads of all 16 rows (256 contiguous bytes per row and warp) and keeps
-// one coverage bit per row; phase 2 walks the rows, a covered pixel is shaded from the prepared record / gathered
-// attributes, and the results go to the warp's slice of shared memory; the tile then leaves in 16-byte stores (WIDE: W % 16
-// == 0 and 16-byte aligned planes; otherwise scalar stores from the loop, any W).  Planar output, CImg layout
-// (CImg.h:11715-11721).
-// Output addresses of a tile, computed from the block indices alone.  The touched path calls this AFTER its row loop with
-// freshly (opaquely) re-read indices, so that no output pointer stays live across the shading code (72 -> 64 registers).
+// Grid: x = 32-pixel tile columns, y = 16-row tile rows of the band, z = frame of the batch -- no thread divides to find its
+// pixel.  A CTA owns one 32 x 16 tile (= one tile flag), each of its four warps four rows of it: lane = column.  (One warp per
+// whole tile measured badly: a covered tile is 16 rows x ~330 instructions of serial work for one warp while its CTA's
+// siblings over background have long exited and their slots idle -- a 640x480 frame's shade pass 15.6 -> 28.5 us, the 1080p
+// spin batch only 4 % better than the row-segment kernel it replaced.)  Untouched tile: constant stores, done.  Touched tile:
+// phase 1 issues the warp's four key loads (256 contiguous bytes per row) and keeps one coverage bit per row; phase 2 walks
+// the rows, a covered pixel is shaded from the prepared record / gathered attributes, the results go to the warp's slice of
+// shared memory and leave in two 16-byte store instructions (WIDE: W % 16 == 0 and 16-byte aligned planes; otherwise scalar
+// stores from the loop, any W).  Planar output, CImg layout (CImg.h:11715-11721).
+constexpr uint32_t SHADE_ROWS = SHADE_TILE_H / SHADE_WARPS; // rows per warp
+
+// Output addresses of a warp's rows, computed from the block indices alone.  The touched path calls this AFTER its row loop
+// with freshly (opaquely) re-read indices, so that no output pointer stays live across the shading code.
 struct TileOut { uint8_t *rgb; float *depth; uint32_t nrows, x0; };
 __device__ __forceinline__ TileOut tile_out(const View &vw, uint8_t *rgb, float *depth, uint32_t bx, uint32_t by, uint32_t bz, uint32_t warp) {
     TileOut t;
-    t.x0 = (bx * SHADE_WARPS + warp) * SHADE_TILE_W;
-    const uint32_t r0 = by * SHADE_TILE_H;
-    t.nrows = min(SHADE_TILE_H, vw.y1 - vw.y0 - r0);
-    const size_t tile0 = (size_t)r0 * vw.W + t.x0, P = vw.out_plane;
-    t.rgb = rgb + (size_t)bz * 3 * P * vw.out_frame_stride + tile0;
-    t.depth = depth ? depth + (size_t)bz * P * vw.out_frame_stride + tile0 : nullptr;
+    t.x0 = bx * SHADE_TILE_W;
+    const uint32_t r0 = by * SHADE_TILE_H + warp * SHADE_ROWS, rows = vw.y1 - vw.y0;
+    t.nrows = r0 < rows ? min(SHADE_ROWS, rows - r0) : 0u;
+    const size_t first = (size_t)r0 * vw.W + t.x0, P = vw.out_plane;
+    t.rgb = rgb + (size_t)bz * 3 * P * vw.out_frame_stride + first;
+    t.depth = depth ? depth + (size_t)bz * P * vw.out_frame_stride + first : nullptr;
     return t;
 }
 
-// One tile leaves in 16-byte stores: colour planes 16 rows x 32 B = one store per lane and plane, depth 16 rows x 128 B =
-// four stores per lane.  src_* = the warp's shared-memory slices, or nullptr for the cleared frame (0 / 1.0f).
-__device__ __forceinline__ void store_tile_wide(const TileOut &t, const View &vw, uint32_t lane, const uint8_t *src_rgb, const float *src_d) {
-    const uint32_t W = vw.W, cr = lane >> 1, cx = (lane & 1u) * 16u;
-    const size_t P = vw.out_plane;
-    if (cr < t.nrows && t.x0 + cx < W) {
-        uint8_t *p = t.rgb + (size_t)cr * W + cx;
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        constexpr uint32_t PL = SHADE_TILE_W * SHADE_TILE_H;
-        *reinterpret_cast<uint4 *>(p) = src_rgb ? reinterpret_cast<const uint4 *>(src_rgb)[lane] : z;
-        *reinterpret_cast<uint4 *>(p + P) = src_rgb ? reinterpret_cast<const uint4 *>(src_rgb + PL)[lane] : z;
-        *reinterpret_cast<uint4 *>(p + 2 * P) = src_rgb ? reinterpret_cast<const uint4 *>(src_rgb + 2 * PL)[lane] : z;
-    }
-    if (t.depth) {
-        const uint32_t dx = (lane & 7u) * 4u;
-        const float4 one = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-#pragma unroll
-        for (uint32_t j = 0; j < 4u; ++j) {
-            const uint32_t dr = j * 4u + (lane >> 3);
-            if (dr < t.nrows && t.x0 + dx < W) *reinterpret_cast<float4 *>(t.depth + (size_t)dr * W + dx) = src_d ? reinterpret_cast<const float4 *>(src_d)[j * 32u + lane] : one;
-        }
-    }
+// A warp's four rows leave in 16-byte stores: colour 3 planes x 4 rows x 32 B = one store by 24 lanes, depth 4 rows x 128 B =
+// one store by all lanes.  src_* = the warp's shared-memory slices ([3][4][32] bytes, [4][32] floats), or nullptr for the
+// cleared frame (0 / 1.0f).
+__device__ __forceinline__ void store_rows_wide(const TileOut &t, const View &vw, uint32_t lane, const uint8_t *src_rgb, const float *src_d) {
+    const uint32_t W = vw.W;
+    const uint32_t plane = lane >> 3, cr = (lane >> 1) & 3u, cx = (lane & 1u) * 16u;
+    if (plane < 3u && cr < t.nrows && t.x0 + cx < W)
+        *reinterpret_cast<uint4 *>(t.rgb + (size_t)plane * vw.out_plane + (size_t)cr * W + cx) = src_rgb ? reinterpret_cast<const uint4 *>(src_rgb)[lane] : make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t dr = lane >> 3, dx = (lane & 7u) * 4u;
+    if (t.depth && dr < t.nrows && t.x0 + dx < W)
+        *reinterpret_cast<float4 *>(t.depth + (size_t)dr * W + dx) = src_d ? reinterpret_cast<const float4 *>(src_d)[lane] : make_float4(1.0f, 1.0f, 1.0f, 1.0f);
 }
 
 #ifndef RAST_SHADE_MIN_BLOCKS
@@ -1195,36 +1291,37 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, RAST_SHADE_MIN_BLOCKS) k_res
 __global__ void __launch_bounds__(SHADE_WARPS * 32) k_resolve_shade(
 #endif
     Scene sc, View vw, Batch bt, const __grid_constant__ LightTable lt, const LightDev *__restrict__ lights, uint8_t *__restrict__ rgb, float *__restrict__ depth, uint32_t keep_frame) {
-    __shared__ __align__(16) uint8_t s_rgb[SHADE_WARPS][3][SHADE_TILE_W * SHADE_TILE_H];
-    __shared__ __align__(16) float s_depth[SHADE_WARPS][SHADE_TILE_W * SHADE_TILE_H];
+    __shared__ __align__(16) uint8_t s_rgb[SHADE_WARPS][3][SHADE_ROWS * SHADE_TILE_W];
+    __shared__ __align__(16) float s_depth[SHADE_WARPS][SHADE_ROWS * SHADE_TILE_W];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t x0 = (blockIdx.x * SHADE_WARPS + warp) * SHADE_TILE_W; // warp-uniform
-    if (x0 >= vw.W) return;
-    const uint32_t ty = blockIdx.y, f = blockIdx.z;
-    const uint32_t W = vw.W, rows = vw.y1 - vw.y0, r0 = ty * SHADE_TILE_H;
-    const uint32_t nrows = min(SHADE_TILE_H, rows - r0);
+    const uint32_t x0 = blockIdx.x * SHADE_TILE_W, ty = blockIdx.y, f = blockIdx.z;
+    const uint32_t W = vw.W, rows = vw.y1 - vw.y0, r0 = ty * SHADE_TILE_H + warp * SHADE_ROWS; // this warp's first row (band-relative)
+    const uint32_t nrows = r0 < rows ? min(SHADE_ROWS, rows - r0) : 0u; // (a warp below the band's last row idles through: the CTA meets at a barrier)
     const uint32_t x = x0 + lane;
     const bool in_x = x < W;
     unsigned long long *vis = bt.vis + (size_t)f * vw.band_pixels + (size_t)r0 * W + x; // this lane's column of keys
-    uint8_t *flag = bt.tile_flags + ((size_t)f * flag_tiles_y(vw) + ty) * flag_tiles_x(vw) + x0 / SHADE_TILE_W;
+    uint8_t *flag = bt.tile_flags + ((size_t)f * flag_tiles_y(vw) + ty) * flag_tiles_x(vw) + blockIdx.x;
     const bool reset = f != keep_frame; // hand the keys back as VIS_EMPTY (the next batch then needs no clear pass)
 
     bool touched = *flag != 0;
     uint32_t covered = 0; // bit r: this lane's pixel of row r has a winning triangle
     if (touched) {
-        // phase 1: all key loads in flight at once.  The low word is the triangle index, 0xFFFFFFFF only in VIS_EMPTY
-        // (rast_upload_mesh caps the triangle count below it).
+        // phase 1: the key loads of the warp's rows in flight together.  The low word is the triangle index, 0xFFFFFFFF only in
+        // VIS_EMPTY (rast_upload_mesh caps the triangle count below it).
 #pragma unroll
-        for (uint32_t r = 0; r < SHADE_TILE_H; ++r)
+        for (uint32_t r = 0; r < SHADE_ROWS; ++r)
             if (r < nrows && in_x) covered |= (*reinterpret_cast<const uint32_t *>(vis + (size_t)r * W) != INVALID_TRI ? 1u : 0u) << r;
         touched = __any_sync(0xFFFFFFFFu, covered != 0u);
-        if (reset && lane == 0u) *flag = 0;
+    }
+    if (reset) { // the flag goes back to 0 once every warp of the tile has read it
+        __syncthreads();
+        if (threadIdx.x == 0u) *flag = 0;
     }
 
-    if (!touched) { // nothing drawn here: the cleared frame (renderer.cpp:85-86)
+    if (!touched) { // nothing drawn in these rows: the cleared frame (renderer.cpp:85-86)
         const TileOut t = tile_out(vw, rgb, depth, blockIdx.x, ty, f, warp);
         if (WIDE) {
-            store_tile_wide(t, vw, lane, nullptr, nullptr);
+            store_rows_wide(t, vw, lane, nullptr, nullptr);
         } else if (in_x) {
             const size_t P = vw.out_plane;
             for (uint32_t r = 0; r < nrows; ++r) {
@@ -1293,8 +1390,8 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32) k_resolve_shade(
         }
         if (WIDE) {
             sr[r * SHADE_TILE_W] = (uint8_t)px.r;
-            sr[r * SHADE_TILE_W + SHADE_TILE_W * SHADE_TILE_H] = (uint8_t)px.g;
-            sr[r * SHADE_TILE_W + 2 * SHADE_TILE_W * SHADE_TILE_H] = (uint8_t)px.b;
+            sr[r * SHADE_TILE_W + SHADE_ROWS * SHADE_TILE_W] = (uint8_t)px.g;
+            sr[r * SHADE_TILE_W + 2 * SHADE_ROWS * SHADE_TILE_W] = (uint8_t)px.b;
             sd[r * SHADE_TILE_W] = px.depth;
         } else if (in_x) {
             const size_t o = (size_t)r * W + lane, P = vw.out_plane;
@@ -1307,8 +1404,208 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32) k_resolve_shade(
         uint32_t bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z, wp = threadIdx.x >> 5;
         asm volatile("" : "+r"(bx), "+r"(by), "+r"(bz), "+r"(wp)); // opaque: recomputed here, not carried through the loop
         const TileOut t = tile_out(vw, rgb, depth, bx, by, bz, wp);
-        store_tile_wide(t, vw, threadIdx.x & 31u, &s_rgb[wp][0][0], &s_depth[wp][0]);
+        store_rows_wide(t, vw, threadIdx.x & 31u, &s_rgb[wp][0][0], &s_depth[wp][0]);
     }
+}
+
+// ---- the same pass with one warp per whole tile (big batches) -------------------------------------------------------------
+// k_resolve_shade above gives every warp 4 rows: the most parallel slices, right for a single small frame (a 640x480 frame is
+// 600 tiles).  A big batch (32 frames of 1080p = 130 k tiles) has parallelism to spare and is better served by amortising a
+// tile's latency chain (flag -> keys -> records) over 16 rows: one warp per 32 x 16 tile.  Warps must then not share a CTA's
+// fate: a covered tile is ~5 k instructions, a background one ~40, and a CTA holds its slots until its slowest warp is done.
+// RAST_SHADE_CTA_WARPS = warps per CTA (side by side in x); RAST_SHADE_PERSIST = 1: a persistent grid whose warps fetch tiles
+// from a counter (RAST_SHADE_GRAB consecutive tiles per fetch) instead of one CTA per RAST_SHADE_CTA_WARPS tiles.
+#ifndef RAST_SHADE_CTA_WARPS
+#define RAST_SHADE_CTA_WARPS 1
+#endif
+#ifndef RAST_SHADE_PERSIST
+#define RAST_SHADE_PERSIST 0
+#endif
+#ifndef RAST_SHADE_GRAB
+#define RAST_SHADE_GRAB 4
+#endif
+constexpr uint32_t SHADE_WT_WARPS = RAST_SHADE_CTA_WARPS;
+
+struct WarpTile { uint32_t f, ty, tx; };
+__device__ __forceinline__ WarpTile decode_tile(const View &vw, uint32_t t) { // t = (f * tiles_y + ty) * tiles_x + tx
+    const uint32_t tx_n = flag_tiles_x(vw), ty_n = flag_tiles_y(vw);
+    WarpTile w;
+    w.tx = t % tx_n;
+    const uint32_t q = t / tx_n;
+    w.ty = q % ty_n;
+    w.f = q / ty_n;
+    return w;
+}
+
+__device__ __forceinline__ void store_tile_wide(const View &vw, uint8_t *rgb, float *depth, const WarpTile &w, uint32_t lane, const uint8_t *src_rgb, const float *src_d) {
+    const uint32_t W = vw.W, x0 = w.tx * SHADE_TILE_W, r0 = w.ty * SHADE_TILE_H, nrows = min(SHADE_TILE_H, vw.y1 - vw.y0 - r0);
+    const size_t first = (size_t)r0 * W + x0, P = vw.out_plane;
+    uint8_t *o_rgb = rgb + (size_t)w.f * 3 * P * vw.out_frame_stride + first;
+    const uint32_t cr = lane >> 1, cx = (lane & 1u) * 16u; // colour planes: 16 rows x 32 B = one 16-byte store per lane and plane
+    if (cr < nrows && x0 + cx < W) {
+        uint8_t *p = o_rgb + (size_t)cr * W + cx;
+        constexpr uint32_t PL = SHADE_TILE_W * SHADE_TILE_H;
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(p) = src_rgb ? reinterpret_cast<const uint4 *>(src_rgb)[lane] : z;
+        *reinterpret_cast<uint4 *>(p + P) = src_rgb ? reinterpret_cast<const uint4 *>(src_rgb + PL)[lane] : z;
+        *reinterpret_cast<uint4 *>(p + 2 * P) = src_rgb ? reinterpret_cast<const uint4 *>(src_rgb + 2 * PL)[lane] : z;
+    }
+    if (depth) { // 16 rows x 128 B = four 16-byte stores per lane
+        float *o_d = depth + (size_t)w.f * P * vw.out_frame_stride + first;
+        const uint32_t dx = (lane & 7u) * 4u;
+        const float4 one = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+#pragma unroll
+        for (uint32_t j = 0; j < 4u; ++j) {
+            const uint32_t dr = j * 4u + (lane >> 3);
+            if (dr < nrows && x0 + dx < W) *reinterpret_cast<float4 *>(o_d + (size_t)dr * W + dx) = src_d ? reinterpret_cast<const float4 *>(src_d)[j * 32u + lane] : one;
+        }
+    }
+}
+
+template <bool WIDE, bool PRE_NORMALS, bool FLAT, bool PREP>
+__device__ __forceinline__ void shade_warp_tile(uint32_t t, uint32_t lane, uint8_t *s_rgb, float *s_depth, const Scene &sc, const View &vw, const Batch &bt,
+                                                const LightTable &lt, const LightDev *__restrict__ lights, uint8_t *__restrict__ rgb, float *__restrict__ depth, uint32_t keep_frame) {
+    const WarpTile w = decode_tile(vw, t);
+    const uint32_t f = w.f;
+    const uint32_t W = vw.W, rows = vw.y1 - vw.y0, x0 = w.tx * SHADE_TILE_W, r0 = w.ty * SHADE_TILE_H;
+    const uint32_t nrows = min(SHADE_TILE_H, rows - r0);
+    const uint32_t x = x0 + lane;
+    const bool in_x = x < W;
+    unsigned long long *vis = bt.vis + (size_t)f * vw.band_pixels + (size_t)r0 * W + x; // this lane's column of keys
+    uint8_t *flag = bt.tile_flags + t;
+    const bool reset = f != keep_frame; // hand the keys back as VIS_EMPTY (the next batch then needs no clear pass)
+
+    bool touched = *flag != 0;
+    uint32_t covered = 0; // bit r: this lane's pixel of row r has a winning triangle
+    if (touched) {
+        // phase 1: all key loads in flight at once.  The low word is the triangle index, 0xFFFFFFFF only in VIS_EMPTY
+        // (rast_upload_mesh caps the triangle count below it).
+#pragma unroll
+        for (uint32_t r = 0; r < SHADE_TILE_H; ++r)
+            if (r < nrows && in_x) covered |= (*reinterpret_cast<const uint32_t *>(vis + (size_t)r * W) != INVALID_TRI ? 1u : 0u) << r;
+        touched = __any_sync(0xFFFFFFFFu, covered != 0u);
+        if (reset && lane == 0u) *flag = 0;
+    }
+
+    if (!touched) { // nothing drawn here: the cleared frame (renderer.cpp:85-86)
+        if (WIDE) {
+            store_tile_wide(vw, rgb, depth, w, lane, nullptr, nullptr);
+        } else if (in_x) {
+            const size_t P = vw.out_plane, first = (size_t)r0 * W + x0;
+            uint8_t *o_rgb = rgb + (size_t)f * 3 * P * vw.out_frame_stride + first;
+            float *o_d = depth ? depth + (size_t)f * P * vw.out_frame_stride + first : nullptr;
+            for (uint32_t r = 0; r < nrows; ++r) {
+                const size_t o = (size_t)r * W + lane;
+                o_rgb[o] = 0; o_rgb[o + P] = 0; o_rgb[o + 2 * P] = 0;
+                if (o_d) o_d[o] = 1.0f;
+            }
+        }
+        return;
+    }
+
+    if (bt.bbox != nullptr) { // covered rectangle of the frame (sparse device-to-host copy), as in k_resolve_shade
+        uint32_t lo = 0xFFFFFFFFu, hic = 0xFFFFFFFFu, ylo = 0xFFFFFFFFu, yhic = 0xFFFFFFFFu;
+        if (covered) {
+            lo = x;
+            hic = W - 1u - x;
+            ylo = r0 + (uint32_t)__ffs((int)covered) - 1u;
+            yhic = rows - 1u - (r0 + 31u - (uint32_t)__clz((int)covered));
+        }
+        lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+        hic = __reduce_min_sync(0xFFFFFFFFu, hic);
+        ylo = __reduce_min_sync(0xFFFFFFFFu, ylo);
+        yhic = __reduce_min_sync(0xFFFFFFFFu, yhic);
+        if (lane == 0u) {
+            uint32_t *bb = bt.bbox + 4u * f;
+            if (lo < bb[0]) atomicMin(bb + 0, lo);
+            if (ylo < bb[1]) atomicMin(bb + 1, ylo);
+            if (hic < bb[2]) atomicMin(bb + 2, hic);
+            if (yhic < bb[3]) atomicMin(bb + 3, yhic);
+        }
+    }
+
+    unsigned long long rv_base = (unsigned long long)(bt.rv + (size_t)f * sc.V);
+    unsigned long long cn_base = (unsigned long long)(PRE_NORMALS ? bt.cn + (size_t)f * sc.Nn : nullptr);
+    asm volatile("" : "+l"(rv_base), "+l"(cn_base));
+    const float4 *rv = reinterpret_cast<const float4 *>(rv_base);
+    const float4 *cn = reinterpret_cast<const float4 *>(cn_base);
+    const FrameParams *fp = bt.frames + f;
+#if RAST_SHADE_PREP
+    unsigned long long prep_base = (unsigned long long)(PREP ? bt.prep + (size_t)f * sc.T * PREP_QUADS : nullptr);
+    asm volatile("" : "+l"(prep_base));
+    const float4 *prep = reinterpret_cast<const float4 *>(prep_base);
+#endif
+    const bool cw = __ldg(&fp->wind_clockwise) != 0u;
+    uint8_t *sr = s_rgb + lane;
+    float *sd = s_depth + lane;
+    uint8_t *n_rgb = nullptr; // non-WIDE: scalar stores from the loop
+    float *n_d = nullptr;
+    if (!WIDE) {
+        const size_t P = vw.out_plane, first = (size_t)r0 * W + x0;
+        n_rgb = rgb + (size_t)f * 3 * P * vw.out_frame_stride + first;
+        n_d = depth ? depth + (size_t)f * P * vw.out_frame_stride + first : nullptr;
+    }
+#pragma unroll 1
+    for (uint32_t r = 0; r < nrows; ++r) {
+        Shaded px;
+        px.r = px.g = px.b = 0u; px.depth = 1.0f; // renderer.cpp:85-86
+        if ((covered >> r) & 1u) {
+            unsigned long long *key = vis + (size_t)r * W;
+            const uint32_t tri = *reinterpret_cast<const uint32_t *>(key); // L1 / L2 hit: phase 1 fetched the line
+#if RAST_SHADE_PREP
+            if (PREP) px = shade_pixel_prep(tri, x, vw.y0 + r0 + r, sc, prep, cw, lt, lights);
+            else
+#endif
+            px = shade_pixel<PRE_NORMALS, FLAT>(tri, x, vw.y0 + r0 + r, sc, rv, cn, FLAT ? fp->modelview : fp->normal_m, cw, lt, lights);
+            if (reset) *key = VIS_EMPTY;
+        }
+        if (WIDE) {
+            sr[r * SHADE_TILE_W] = (uint8_t)px.r;
+            sr[r * SHADE_TILE_W + SHADE_TILE_W * SHADE_TILE_H] = (uint8_t)px.g;
+            sr[r * SHADE_TILE_W + 2 * SHADE_TILE_W * SHADE_TILE_H] = (uint8_t)px.b;
+            sd[r * SHADE_TILE_W] = px.depth;
+        } else if (in_x) {
+            const size_t o = (size_t)r * W + lane, P = vw.out_plane;
+            n_rgb[o] = (uint8_t)px.r; n_rgb[o + P] = (uint8_t)px.g; n_rgb[o + 2 * P] = (uint8_t)px.b;
+            if (n_d) n_d[o] = px.depth;
+        }
+    }
+    if (WIDE) {
+        __syncwarp();
+        uint32_t t2 = t;
+        asm volatile("" : "+r"(t2)); // opaque: the output addresses are recomputed here, not carried through the loop
+        store_tile_wide(vw, rgb, depth, decode_tile(vw, t2), lane, s_rgb, s_depth);
+        __syncwarp();
+    }
+}
+
+#ifndef RAST_SHADE_WT_MIN_BLOCKS
+#define RAST_SHADE_WT_MIN_BLOCKS 0
+#endif
+template <bool WIDE, bool PRE_NORMALS, bool FLAT, bool PREP>
+#if RAST_SHADE_WT_MIN_BLOCKS > 0
+__global__ void __launch_bounds__(SHADE_WT_WARPS * 32, RAST_SHADE_WT_MIN_BLOCKS) k_resolve_shade_wt(
+#else
+__global__ void __launch_bounds__(SHADE_WT_WARPS * 32) k_resolve_shade_wt(
+#endif
+    Scene sc, View vw, Batch bt, const __grid_constant__ LightTable lt, const LightDev *__restrict__ lights, uint8_t *__restrict__ rgb, float *__restrict__ depth,
+    uint32_t keep_frame, uint32_t n_tiles, unsigned int *cursor) {
+    __shared__ __align__(16) uint8_t s_rgb[SHADE_WT_WARPS][3 * SHADE_TILE_W * SHADE_TILE_H];
+    __shared__ __align__(16) float s_depth[SHADE_WT_WARPS][SHADE_TILE_W * SHADE_TILE_H];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#if RAST_SHADE_PERSIST
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0u) base = atomicAdd(cursor, (unsigned int)RAST_SHADE_GRAB);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n_tiles) break;
+        const uint32_t end = min(base + (uint32_t)RAST_SHADE_GRAB, n_tiles);
+        for (uint32_t t = base; t < end; ++t) shade_warp_tile<WIDE, PRE_NORMALS, FLAT, PREP>(t, lane, s_rgb[warp], s_depth[warp], sc, vw, bt, lt, lights, rgb, depth, keep_frame);
+    }
+#else
+    const uint32_t t = blockIdx.x * SHADE_WT_WARPS + warp;
+    if (t < n_tiles) shade_warp_tile<WIDE, PRE_NORMALS, FLAT, PREP>(t, lane, s_rgb[warp], s_depth[warp], sc, vw, bt, lt, lights, rgb, depth, keep_frame);
+#endif
 }
 
 // ---- auxiliary kernels ----------------------------------------------------------------------

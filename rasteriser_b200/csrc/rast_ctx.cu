@@ -168,6 +168,10 @@ struct rast_ctx {
     cudaEvent_t ev_raster[2] = {nullptr, nullptr}, ev_shade[2] = {nullptr, nullptr};
     bool shade_pending[2] = {false, false};
     bool overlap = true;
+    uint32_t shade_wt_min_tiles = 16384; // batches with at least this many 32 x 16 tiles take the one-warp-per-tile shade kernel (RAST_SHADE_WT_MIN_TILES)
+    unsigned shade_wt_grid = 148;         // persistent flavour of it (RAST_SHADE_PERSIST): SMs x resident CTAs per SM
+    DeviceBuffer d_shade_cursor;
+    bool keep_visibility = false; // rast_set_keep_visibility: the last frame of a call keeps its keys (rast_read_triangle_ids / rast_get_stats)
     int last_ps = 0; // pipeline slot of the most recent batch (rast_read_triangle_ids / rast_get_stats)
     DeviceBuffer d_rgb[2], d_depth[2];
     PinnedBuffer h_frames, h_lights, h_status, h_bbox[2];
@@ -194,8 +198,9 @@ struct rast_ctx {
     uint32_t last_slot_frame = 0; // index of the last frame inside d_vis / d_rv
     const float *last_depth_dev = nullptr;
     size_t last_frames_offset = 0; // index into d_frames of the last frame's params
-    bool have_frame = false;
+    bool have_frame = false, have_visibility = false;
     uint64_t last_queue_count = 0;
+    size_t call_frames = 0; // frames of the call being launched
     unsigned long long last_batch_pixels = 0; // pixels (all frames) of the last batch launched
 
     // profiling
@@ -319,11 +324,12 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     if (bt.prep && sc.T) { rk::k_prepare_tris<<<dim3(grid_for(sc.T, 128), count), 128, 0, st>>>(sc, bt); ctx->launches++; }
 #endif
     if (prof) cudaEventRecord(ctx->ev_pass[2], st);
-    // Raster schedule of this batch.  The screen-tile binned schedule is implemented and parity-tested but measured
-    // slower than the bbox-anchored chunk queue on B200 at both ends (1080p Suzanne batch: 28.9 vs 4.3 ms per 720 frames;
-    // 8K overdraw-50 frame: 6.8 vs 5.9 ms -- screen-aligned 32x32 tiles create ~40 % more partially covered blocks and leave
-    // most warps of a tile's CTA idle when bins are short), so it only runs when asked for (RAST_RASTER_MODE=tile).
-    const bool tile_mode = sc.T && ctx->raster_mode_forced == 1;
+    // Raster schedule of this batch: the bbox-anchored chunk queue (k_raster_chunks, any order, global atomicMin) for frames where few
+    // fragments compete per pixel, screen-tile bins (k_raster_tiles: the tile's keys in shared memory, bin processed near to far, block
+    // and item level depth rejection) at high overdraw.  RAST_RASTER_MODE=chunk|tile forces one.
+    // "auto" bins the batch when the previous call's queued bbox area showed high overdraw (TILE_MODE_OVERDRAW); k_plan_tiles confirms it
+    // for this batch on the device and otherwise leaves the batch to the chunk queue, which k_setup fills in either case
+    const bool tile_mode = sc.T && (ctx->raster_mode_forced == 1 || (ctx->raster_mode_forced == -1 && ctx->tile_mode_next));
     rk::TileBins tb{};
     uint32_t n_tile_launches = 0;
     if (tile_mode) {
@@ -332,12 +338,12 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
         const size_t n_tiles = (size_t)count * tb.tiles_x * tb.tiles_y;
         RAST_CUDA(ctx, ctx->d_tiles.reserve(3 * n_tiles * 4));
         RAST_CUDA(ctx, ctx->d_list.reserve((size_t)ctx->list_cap * sizeof(uint2)));
-        RAST_CUDA(ctx, ctx->d_items.reserve((size_t)ctx->items_cap * 4));
+        RAST_CUDA(ctx, ctx->d_items.reserve((size_t)ctx->items_cap * sizeof(uint2)));
         tb.count = ctx->d_tiles.as<uint32_t>();
         tb.start = tb.count + n_tiles;
         tb.fill = tb.start + n_tiles;
         tb.list = ctx->d_list.as<uint2>();
-        tb.items = ctx->d_items.as<uint32_t>();
+        tb.items = ctx->d_items.as<uint2>();
         tb.list_cap = ctx->list_cap;
         tb.items_cap = ctx->items_cap;
         RAST_CUDA(ctx, cudaMemsetAsync(tb.count, 0, n_tiles * 4, st));
@@ -349,18 +355,19 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     }
     if (prof) cudaEventRecord(ctx->ev_pass[3], st);
     if (tile_mode && vw.band_pixels) {
-        rk::k_plan_tiles<<<1, 1024, 0, st>>>(bt, tb);
+        const unsigned long long min_area = ctx->raster_mode_forced == 1 ? 0ull : (unsigned long long)(TILE_MODE_OVERDRAW / 2) * vw.band_pixels * count;
+        rk::k_plan_tiles<<<1, 1024, 0, st>>>(bt, tb, min_area);
         rk::k_fill_tiles<<<ctx->raster_grid, 256, 0, st>>>(sc, vw, bt, tb);
         n_tile_launches += 2;
     }
     if (sc.T && vw.band_pixels) rk::k_raster_chunks<<<ctx->raster_grid, rk::RASTER_WARPS * 32, 0, st>>>(sc, vw, bt); // returns at once when the bins are used
     if (tile_mode && vw.band_pixels) {
-        rk::k_raster_tiles<<<dim3(tb.tiles_x * tb.tiles_y, count), rk::RASTER_WARPS * 32, 0, st>>>(sc, vw, bt, tb);
+        rk::k_raster_tiles<<<dim3(tb.tiles_x * tb.tiles_y, count), rk::TILE_WARPS * 32, 0, st>>>(sc, vw, bt, tb);
         n_tile_launches += 1;
     }
     // queue statistics of the call's last batch travel back from here (overflow => the queue grows before the next call): the
     // next call's front passes reset the counters and may start before this call's shade pass has finished
-    if (keep_frame < count) RAST_CUDA(ctx, cudaMemcpyAsync(ctx->h_status.p, ctx->d_counters.p, 64, cudaMemcpyDeviceToHost, st));
+    if (first + count == ctx->call_frames) RAST_CUDA(ctx, cudaMemcpyAsync(ctx->h_status.p, ctx->d_counters.p, 64, cudaMemcpyDeviceToHost, st));
     if (prof) cudaEventRecord(ctx->ev_pass[4], st);
     if (two_streams) { // the shade pass runs on the context's stream, after this batch's raster pass
         RAST_CUDA(ctx, cudaEventRecord(ctx->ev_raster[ps], st));
@@ -371,12 +378,27 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     if (vw.band_pixels) {
         const rk::LightDev *lights = ctx->d_lights[ctx->cs].as<rk::LightDev>();
         const uint32_t rows = vw.y1 - vw.y0;
-        const dim3 grid(grid_for(vw.W, rk::SHADE_TILE_W * rk::SHADE_WARPS), grid_for(rows, rk::SHADE_TILE_H), count);
+        const dim3 grid(grid_for(vw.W, rk::SHADE_TILE_W), grid_for(rows, rk::SHADE_TILE_H), count);
         const unsigned threads = rk::SHADE_WARPS * 32;
         const rk::LightTable &lt = ctx->light_table;
+        // one warp per whole tile for big batches, four warps per tile (4 rows each) when the batch has few tiles (kernels.cuh)
+        const uint32_t n_tiles = (uint32_t)(flags_per_frame * count);
+        const bool warp_tiles = n_tiles >= ctx->shade_wt_min_tiles;
+        unsigned int *cursor = nullptr;
+        unsigned wt_grid = grid_for(n_tiles, rk::SHADE_WT_WARPS);
+#if RAST_SHADE_PERSIST
+        if (warp_tiles) {
+            cursor = ctx->d_shade_cursor.as<unsigned int>() + ps;
+            RAST_CUDA(ctx, cudaMemsetAsync(cursor, 0, 4, st));
+            wt_grid = ctx->shade_wt_grid;
+        }
+#endif
 #define RAST_SHADE_LAUNCH(PRE, FLAT, PREP)                                                                                                        \
         do {                                                                                                                                      \
-            if (wide) rk::k_resolve_shade<true, PRE, FLAT, PREP><<<grid, threads, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame); \
+            if (warp_tiles) {                                                                                                                     \
+                if (wide) rk::k_resolve_shade_wt<true, PRE, FLAT, PREP><<<wt_grid, rk::SHADE_WT_WARPS * 32, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame, n_tiles, cursor); \
+                else rk::k_resolve_shade_wt<false, PRE, FLAT, PREP><<<wt_grid, rk::SHADE_WT_WARPS * 32, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame, n_tiles, cursor);     \
+            } else if (wide) rk::k_resolve_shade<true, PRE, FLAT, PREP><<<grid, threads, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame); \
             else rk::k_resolve_shade<false, PRE, FLAT, PREP><<<grid, threads, 0, st>>>(sc, vw, bt, lt, lights, rgb_dev, depth_dev, keep_frame);     \
         } while (0)
         if (ctx->flat_face) RAST_SHADE_LAUNCH(false, true, false); // extension: face normals (never taken for reference-compatible arguments)
@@ -559,7 +581,7 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
 
     {   // overdraw estimate of the previous call's last batch: queued bbox area / pixels rendered
         const unsigned long long *hs = ctx->h_status.as<unsigned long long>();
-        if (ctx->last_batch_pixels) ctx->tile_mode_next = hs[3] > (unsigned long long)TILE_MODE_OVERDRAW * ctx->last_batch_pixels; // recorded; not acted on (see launch_batch)
+        if (ctx->last_batch_pixels) ctx->tile_mode_next = hs[3] > (unsigned long long)TILE_MODE_OVERDRAW * ctx->last_batch_pixels;
         if (hs[7] != 0ull) { // the bins overflowed (that batch fell back to the chunk queue): grow them
             RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             if (ctx->list_cap < (1u << 27)) ctx->list_cap *= 2;
@@ -649,6 +671,7 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
     }
 
     if (ctx->profiling) memset(ctx->pass_ms, 0, sizeof ctx->pass_ms);
+    ctx->call_frames = n;
 
     int slot = 0, ps = ctx->next_ps;
     PendingBatch pending;
@@ -674,7 +697,7 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
             ctx->copied_pending[slot] = false;
         }
         // the last frame of the call keeps its visibility keys for rast_read_triangle_ids / rast_get_stats
-        const uint32_t keep_frame = (first + count == n) ? count - 1 : 0xFFFFFFFFu;
+        const uint32_t keep_frame = (ctx->keep_visibility && first + count == n) ? count - 1 : 0xFFFFFFFFu;
         uint32_t *bbox_dev = nullptr;
         if (!device_ptrs && ctx->sparse_copy) {
             RAST_CUDA(ctx, ctx->d_bbox[slot].reserve((size_t)nb * 16));
@@ -691,6 +714,7 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
         ctx->last_frames_offset = first + count - 1;
         ctx->last_depth_dev = depth_dst ? depth_dst + (size_t)(count - 1) * S * P : nullptr;
         ctx->have_frame = true;
+        ctx->have_visibility = keep_frame < count;
 
         if (!device_ptrs) {
             if (bbox_dev) RAST_CUDA(ctx, cudaMemcpyAsync(ctx->h_bbox[slot].p, bbox_dev, (size_t)count * 16, cudaMemcpyDeviceToHost, done_stream));
@@ -759,6 +783,10 @@ int rast_create(int device, rast_ctx **out) {
         ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rk::k_raster_chunks, rk::RASTER_WARPS * 32, 0) == cudaSuccess;
         if (const char *e = getenv("RAST_RASTER_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
         ctx->raster_grid = (unsigned)(sms > 0 ? sms : 148) * (unsigned)(per_sm > 0 ? per_sm : 1);
+        int wt_per_sm = 0;
+        ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wt_per_sm, rk::k_resolve_shade_wt<true, true, false, RAST_SHADE_PREP != 0>, rk::SHADE_WT_WARPS * 32, 0) == cudaSuccess;
+        ctx->shade_wt_grid = (unsigned)(sms > 0 ? sms : 148) * (unsigned)(wt_per_sm > 0 ? wt_per_sm : 1);
+        ok = ok && ctx->d_shade_cursor.reserve(64) == cudaSuccess;
     }
     if (!ok) {
         g_create_error = std::string("rast_create: CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -767,6 +795,7 @@ int rast_create(int device, rast_ctx **out) {
     }
     ctx->stream = ctx->own_stream;
     if (const char *e = getenv("RAST_SPARSE_COPY")) ctx->sparse_copy = atoi(e) != 0;
+    if (const char *e = getenv("RAST_SHADE_WT_MIN_TILES")) ctx->shade_wt_min_tiles = (uint32_t)atoll(e);
     if (const char *e = getenv("RAST_OVERLAP")) ctx->overlap = atoi(e) != 0;
 #if RAST_SHADE_PREP
     if (const char *e = getenv("RAST_SHADE_PREP_RUNTIME")) ctx->prep_enabled = atoi(e) != 0;
@@ -789,7 +818,7 @@ void rast_destroy(rast_ctx *ctx) {
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->front_stream) cudaStreamSynchronize(ctx->front_stream);
     DeviceBuffer *dev[] = {&ctx->d_pos, &ctx->d_nrm, &ctx->d_uv, &ctx->d_vidx, &ctx->d_attr, &ctx->d_mats, &ctx->d_texels, &ctx->d_frames[0], &ctx->d_frames[1], &ctx->d_lights[0], &ctx->d_lights[1],
-                           &ctx->d_rv[0], &ctx->d_rv[1], &ctx->d_cn[0], &ctx->d_cn[1], &ctx->d_tiles, &ctx->d_list, &ctx->d_items, &ctx->d_vis[0], &ctx->d_vis[1], &ctx->d_flags[0], &ctx->d_flags[1], &ctx->d_bbox[0], &ctx->d_bbox[1], &ctx->d_queue, &ctx->d_counters, &ctx->d_aux, &ctx->d_rgb[0], &ctx->d_rgb[1], &ctx->d_depth[0], &ctx->d_depth[1]};
+                           &ctx->d_rv[0], &ctx->d_rv[1], &ctx->d_cn[0], &ctx->d_cn[1], &ctx->d_tiles, &ctx->d_list, &ctx->d_items, &ctx->d_vis[0], &ctx->d_vis[1], &ctx->d_flags[0], &ctx->d_flags[1], &ctx->d_bbox[0], &ctx->d_bbox[1], &ctx->d_queue, &ctx->d_counters, &ctx->d_shade_cursor, &ctx->d_aux, &ctx->d_rgb[0], &ctx->d_rgb[1], &ctx->d_depth[0], &ctx->d_depth[1]};
     for (DeviceBuffer *b : dev) b->release();
 #if RAST_SHADE_PREP
     ctx->d_prep[0].release();
@@ -988,7 +1017,7 @@ int rast_set_output_frame_stride(rast_ctx *ctx, uint32_t frames) {
 }
 
 uint64_t rast_fnv1a64(const void *data, uint64_t bytes) {
-    uint64_t h = 1469598103934665603ull;
+    uint64_t h = 14695981039346656037ull;
     const unsigned char *b = static_cast<const unsigned char *>(data);
     for (uint64_t i = 0; i < bytes; ++i) { h ^= b[i]; h *= 1099511628211ull; }
     return h;
@@ -1082,6 +1111,7 @@ int rast_sync(rast_ctx *ctx) {
 int rast_read_triangle_ids(rast_ctx *ctx, uint32_t *tri_ids) {
     if (!ctx || !tri_ids) return RAST_EINVAL;
     if (!ctx->have_frame) return fail(ctx, RAST_ESTATE, "rast_read_triangle_ids: no frame has been drawn");
+    if (!ctx->have_visibility) return fail(ctx, RAST_ESTATE, "rast_read_triangle_ids: the last frame's visibility buffer was not kept (rast_set_keep_visibility)");
     RAST_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint32_t P = ctx->last_view.band_pixels;
     RAST_CUDA(ctx, ctx->d_aux.reserve((size_t)P * 4 + 64));
@@ -1114,6 +1144,7 @@ int rast_depth_to_u8(rast_ctx *ctx, uint8_t *out) {
 int rast_get_stats(rast_ctx *ctx, rast_stats *out) {
     if (!ctx || !out) return RAST_EINVAL;
     if (!ctx->have_frame) return fail(ctx, RAST_ESTATE, "rast_get_stats: no frame has been drawn");
+    if (!ctx->have_visibility) return fail(ctx, RAST_ESTATE, "rast_get_stats: the last frame's visibility buffer was not kept (rast_set_keep_visibility)");
     RAST_CUDA(ctx, cudaSetDevice(ctx->device));
     RAST_CUDA(ctx, ctx->d_aux.reserve(64));
     unsigned long long *cnt = ctx->d_aux.as<unsigned long long>();
@@ -1132,6 +1163,12 @@ int rast_get_stats(rast_ctx *ctx, rast_stats *out) {
     out->front_facing = host[1];
     out->visible_pixels = host[0];
     out->queued_chunks = ctx->h_status.as<unsigned long long>()[0];
+    return RAST_OK;
+}
+
+int rast_set_keep_visibility(rast_ctx *ctx, int enabled) {
+    if (!ctx) return RAST_EINVAL;
+    ctx->keep_visibility = enabled != 0;
     return RAST_OK;
 }
 

@@ -15,6 +15,7 @@ def make_renderer(scene, lights7, device=0):
     r.upload_mesh(scene.positions, scene.tris, scene.normals, scene.uvs)
     r.upload_materials(scene.materials)
     r.set_lights(lights7)
+    r.set_keep_visibility(True)  # the parity tests compare the winning triangle of every pixel
     return r
 
 

@@ -37,7 +37,7 @@ Args::Args(int, char **)
       displacement(0.f), tait_bryan_angles(0.f) {}
 
 static uint64_t fnv(const void *p, size_t n) {
-    uint64_t h = 1469598103934665603ull;
+    uint64_t h = 14695981039346656037ull;
     const unsigned char *b = static_cast<const unsigned char *>(p);
     for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
     return h;

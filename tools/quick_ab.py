@@ -65,6 +65,7 @@ def main():
         for k, v in r.pass_ms().items():
             passes[k] = passes.get(k, 0.0) + v / opts.calls
     r.set_profiling(False)
+    r.set_keep_visibility(True)
     call()
     r.sync()
     k = min(n, 4)
