@@ -241,7 +241,9 @@ def run_reference_arm(opts, wl):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-KERNEL_OF_PASS = {"vertex": "k_vertex", "setup": "k_setup", "raster": "k_raster_chunks", "shade": "k_resolve_shade", "clear": "k_clear"}
+# pass -> kernels that implement it (the library picks per batch: chunk queue or screen-tile bins, 4-rows-per-warp or warp-per-tile shading);
+# the captured one (profiles/r*_traffic.json, same workload) names the record
+KERNEL_OF_PASS = {"vertex": ("k_vertex",), "setup": ("k_setup",), "raster": ("k_raster_tiles", "k_raster_chunks"), "shade": ("k_resolve_shade_wt", "k_resolve_shade"), "clear": ("k_clear",)}
 # golden hashes produced by the REFERENCE's own code (tests/golden/make_golden*.py): workload -> (file, case)
 GOLDEN_OF_WORKLOAD = {"suzanne640": ("cases.json", "suzanne_640x480"), "tess4k": ("large_cases.json", "config3_tess91_4k"),
                       "tess4k_64lights": ("large_cases.json", "config5_tess227_64lights_4k"), "overdraw8k": ("large_cases.json", "config4_overdraw_8k")}
@@ -318,7 +320,7 @@ def roofline_record(wl, workload, pass_ms, n_frames, P, visible_tris, step_ms, w
     avg_ms = pass_ms[dominant] / batches
     achieved = alg / (avg_ms * 1e-3) / 1e9
     tr, tr_file = ncu_traffic(workload)
-    kname = KERNEL_OF_PASS[dominant]
+    kname = ([k for k in KERNEL_OF_PASS[dominant] if k in tr] or [KERNEL_OF_PASS[dominant][-1]])[0]
     traffic, limiter = None, None
     if kname in tr:
         k = tr[kname]

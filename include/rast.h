@@ -55,10 +55,12 @@ typedef struct {
  * has_texture == 0.  Copied to the device by rast_upload_materials. */
 typedef struct {
     float kd[3];
-    int32_t has_texture;
+    int32_t has_texture; /* 0: Kd is the albedo; 1: the texture is (the reference: material.cpp:19-21 ignores Kd of a textured material);
+                          * 1 | RAST_TEXTURE_MODULATE_KD: extension, texel x Kd per channel */
     int32_t tex_w, tex_h;
     const float *texels;
 } rast_material;
+#define RAST_TEXTURE_MODULATE_KD 2
 
 /* The fields of Args that draw_frame consumes -- headers/arguments.h:7-21; drawing.cpp:222
  * (scale, displacement, tait_bryan_angles), :229 (aspect_ratio), :247,255 (image size),

@@ -57,7 +57,7 @@ public:
         std::vector<rast_material> m(materials.size());
         for (size_t i = 0; i < materials.size(); ++i) {
             m[i].kd[0] = materials[i].kd[0]; m[i].kd[1] = materials[i].kd[1]; m[i].kd[2] = materials[i].kd[2];
-            m[i].has_texture = materials[i].has_texture ? 1 : 0;
+            m[i].has_texture = materials[i].has_texture ? (1 | texture_bits_) : 0;
             m[i].tex_w = materials[i].tex_w; m[i].tex_h = materials[i].tex_h;
             m[i].texels = materials[i].has_texture ? &materials[i].texels[0] : nullptr;
         }
@@ -65,6 +65,10 @@ public:
         key_ = make_key(vertices, faces, normals, uvs, materials, true);
         uploaded_ = true;
     }
+
+    // Extension (default off, the reference ignores Kd of a textured material: material.cpp:19-21): RAST_TEXTURE_MODULATE_KD makes the
+    // texel modulate Kd.  Takes effect at the next upload.
+    void set_texture_bits(int bits) { if (bits != texture_bits_) { texture_bits_ = bits; uploaded_ = false; } }
 
     // The caller promises that the scene arrays do not change between draws (no per-call content hash); invalidate() when they do.
     void assume_unchanged(bool on) { assume_unchanged_ = on; }
@@ -118,6 +122,7 @@ private:
     rast_ctx *ctx_ = nullptr;
     Key key_{};
     bool uploaded_ = false, assume_unchanged_ = false;
+    int texture_bits_ = 0;
 };
 
 template <class ArgsT> inline rast_args to_rast_args(const ArgsT &a) {

@@ -313,6 +313,9 @@ void orc_material_sample(const orc_material *m, const float uv[2], float out[3])
         out[0] = linear_at_xy(m->texels, m->tex_w, m->tex_h, u, v);
         out[1] = linear_at_xy(m->texels + plane, m->tex_w, m->tex_h, u, v);
         out[2] = linear_at_xy(m->texels + 2 * plane, m->tex_w, m->tex_h, u, v);
+        /* EXTENSION (not in the reference, which drops Kd of a textured material: fileloader.cpp:47-58 / material.cpp:19-21):
+         * has_texture bit 1 = the texel modulates the material's Kd, one rounded product per channel */
+        if (m->has_texture & 2) { out[0] = m->kd[0] * out[0]; out[1] = m->kd[1] * out[1]; out[2] = m->kd[2] * out[2]; }
     } else {
         out[0] = m->kd[0]; out[1] = m->kd[1]; out[2] = m->kd[2];
     }

@@ -60,6 +60,7 @@ class Material:
     texels: float32 [3, h, w], already normalised to [0,1] as the reference's constructor does."""
     kd: tuple = (1.0, 1.0, 1.0)
     texels: np.ndarray = field(default=None, repr=False)
+    modulate_kd: bool = False  # extension (RAST_TEXTURE_MODULATE_KD): albedo = texel x Kd; the reference ignores Kd of a textured material
 
 
 def _ptr(a):
@@ -115,11 +116,12 @@ class Renderer:
         for i, m in enumerate(materials):
             kd = m.kd if isinstance(m, Material) else m["kd"]
             tex = m.texels if isinstance(m, Material) else m.get("texels")
+            mod = m.modulate_kd if isinstance(m, Material) else m.get("modulate_kd", False)
             arr[i].kd = (C.c_float * 3)(*[float(x) for x in kd])
             if tex is not None:
                 t = np.ascontiguousarray(tex, np.float32)
                 keep.append(t)
-                arr[i].has_texture, arr[i].tex_h, arr[i].tex_w, arr[i].texels = 1, t.shape[1], t.shape[2], t.ctypes.data
+                arr[i].has_texture, arr[i].tex_h, arr[i].tex_w, arr[i].texels = (3 if mod else 1), t.shape[1], t.shape[2], t.ctypes.data
         self._check(self._lib.rast_upload_materials(self._h, arr, len(materials)), "rast_upload_materials")
 
     def set_lights(self, lights):

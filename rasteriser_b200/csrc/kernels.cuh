@@ -102,7 +102,7 @@ struct LightDev {             // pre-combined per light: -trans_dir and intensit
 
 struct MaterialDev {          // material.h:11-25
     float kd[3];
-    int has_texture;
+    int has_texture;          // 0 = Kd, 1 = texture (the reference), 1 | 2 = texture x Kd (extension RAST_TEXTURE_MODULATE_KD)
     int tex_w, tex_h;
     long long texel_offset;   // into Scene::texels, in texels
 };
@@ -468,6 +468,40 @@ const __grid_constant__ Scene sc, const __grid_constant__ View vw, const __grid_
     for (int k = 0; k < TRIS; ++k) {
         const uint64_t t = t0 + (uint64_t)k * 256;
         if (t < sc.T) setup_triangle<BINS>((uint32_t)t, f, v0[k], v1[k], v2[k], cw, vw, bt, tb);
+    }
+}
+
+// The same pass as a software pipeline, for meshes far larger than the L2.  k_setup above is bound by the latency of its two dependent
+// load stages (ncu, 8.0 M triangles: 35 % of the stall samples sit on the index loads and on the vertex gathers, issue slots 69 % used):
+// every warp loads, waits, gathers, waits, computes.  Here a persistent CTA walks chunks of 256 consecutive triangles (chunk c, c + grid,
+// ...) and every thread keeps two loads ahead of its arithmetic: while triangle i is set up, the vertices of triangle i + 1 and the
+// indices of triangle i + 2 are in flight.  Same per-triangle code, same results.  Measured on a B200 against k_setup<.., 2>: 49.9 M
+// triangles (1.0 GB of indices and vertices, DRAM latency) 0.615 -> 0.563 ms; 8.0 M triangles (160 MB, mostly L2 hits after k_vertex)
+// 0.133 -> 0.169 ms (one wave per SM) / 0.222 ms -- the host takes it from SETUP_PIPE_MIN_TRIANGLES triangles on.
+constexpr uint64_t SETUP_PIPE_MIN_TRIANGLES = 1ull << 25;
+template <bool BINS>
+__global__ void __launch_bounds__(256) k_setup_pipe(const __grid_constant__ Scene sc, const __grid_constant__ View vw, const __grid_constant__ Batch bt,
+                                                    const __grid_constant__ TileBins tb) {
+    const uint32_t f = blockIdx.y;
+    const float4 *rv = bt.rv + (size_t)f * sc.V;
+    const bool cw = bt.frames[f].wind_clockwise != 0u;
+    const uint64_t stride = (uint64_t)gridDim.x * 256u;
+    uint64_t t = (uint64_t)blockIdx.x * 256u + threadIdx.x;
+    // prologue: indices of the first two triangles, vertices of the first
+    int a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
+    if (t < sc.T) { a0 = sc.vidx0[t]; a1 = sc.vidx1[t]; a2 = sc.vidx2[t]; }
+    if (t + stride < sc.T) { b0 = sc.vidx0[t + stride]; b1 = sc.vidx1[t + stride]; b2 = sc.vidx2[t + stride]; }
+    float4 v0 = rv[a0], v1 = rv[a1], v2 = rv[a2];
+#pragma unroll 1
+    for (; t < sc.T; t += stride) {
+        // vertices of the next triangle (its indices arrived during the previous iteration), indices of the one after
+        const float4 n0 = rv[b0], n1 = rv[b1], n2 = rv[b2];
+        int c0 = 0, c1 = 0, c2 = 0;
+        const uint64_t t2 = t + 2 * stride;
+        if (t2 < sc.T) { c0 = sc.vidx0[t2]; c1 = sc.vidx1[t2]; c2 = sc.vidx2[t2]; }
+        setup_triangle<BINS>((uint32_t)t, f, v0, v1, v2, cw, vw, bt, tb);
+        v0 = n0; v1 = n1; v2 = n2;
+        b0 = c0; b1 = c1; b2 = c2;
     }
 }
 
@@ -1070,6 +1104,7 @@ RAST_HD Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t y, const Scene &sc
         unsigned long long tex_base = (unsigned long long)(sc.texels + toff);
         asm volatile("" : "+l"(tex_base)); // opaque base: each corner becomes one IMAD.WIDE instead of a 64-bit add + LEA pair
         sample_texture(reinterpret_cast<const float4 *>(tex_base), mt.x, mt.y, mul(u, (float)mt.x), mul(sub(1.f, v), (float)mt.y), ar, ag, ab);
+        if (exact::f2u(mk.w) & 2u) { ar = mul(mk.x, ar); ag = mul(mk.y, ag); ab = mul(mk.z, ab); } // extension RAST_TEXTURE_MODULATE_KD: texel x Kd
     }
 
     // perspective_interpolate + normalize (drawing.cpp:64-75,131-132)
@@ -1160,18 +1195,40 @@ __global__ void __launch_bounds__(128) k_prepare_tris(Scene sc, Batch bt) {
     prepare_triangle((uint32_t)t, sc, bt.rv + (size_t)f * sc.V, bt.cn + (size_t)f * sc.Nn, bt.prep + ((size_t)f * sc.T + t) * PREP_QUADS);
 }
 
+// A prepared record and its material in registers, loaded per covered pixel.  (Keeping it per lane across the rows of a tile and
+// reloading only when the lane's winning triangle changes was measured on a B200 -- a lane walks down a pixel column and a Suzanne
+// triangle is ~50 pixels tall, so ten of the twelve 16-byte loads per pixel disappear: L1 data-pipe utilisation 73 % -> 45 %, but 80
+// instead of 64 registers, 31 % instead of 40 % of the warp slots occupied, and the 32-frame 1080p launch went from 339 to 387 us.
+// The pass is co-limited by issue slots and the L1 data pipe; trading one for occupancy does not pay.)
+struct PrepRec {
+    float4 q0, q1, q2, q3, q4, q5, q6, q7, q8;
+    float n2z;
+    float4 mk;               // material: kd.rgb, has_texture bits
+    int tex_w, tex_h;
+    unsigned long long tex_base;
+};
+
+RAST_HD void load_prep_record(PrepRec &r, uint32_t tri, const Scene &sc, const float4 *__restrict__ prep) {
+    using namespace exact;
+    const float4 *q = prep + (size_t)tri * PREP_QUADS;
+    r.q0 = ldg(q); r.q1 = ldg(q + 1); r.q2 = ldg(q + 2); r.q3 = ldg(q + 3); r.q4 = ldg(q + 4); r.q5 = ldg(q + 5);
+    r.q6 = ldg(q + 6); r.q7 = ldg(q + 7); r.q8 = ldg(q + 8);
+    r.n2z = ldg(reinterpret_cast<const float *>(q + 9));
+    const MaterialDev *mp = sc.mats + f2u(r.q3.w);
+    r.mk = ldg(reinterpret_cast<const float4 *>(mp));                   // kd.rgb, has_texture
+    const int4 mt = ldg(reinterpret_cast<const int4 *>(mp) + 1);        // tex_w, tex_h, texel_offset (lo, hi)
+    r.tex_w = mt.x; r.tex_h = mt.y;
+    const long long toff = ((long long)(uint32_t)mt.z) | ((long long)mt.w << 32);
+    r.tex_base = (unsigned long long)(sc.texels + toff);
+}
+
 // shade_pixel for a prepared triangle: the same operations on the same values, in the same order, from the record
-RAST_HD Shaded shade_pixel_prep(uint32_t tri, uint32_t x, uint32_t y, const Scene &sc, const float4 *__restrict__ prep, bool wind_clockwise,
-                                const LightTable &lt, const LightDev *__restrict__ lights) {
+RAST_HD Shaded shade_prepared(const PrepRec &p, uint32_t x, uint32_t y, bool wind_clockwise, const LightTable &lt, const LightDev *__restrict__ lights) {
     using namespace exact;
     Shaded out;
-    const float4 *q = prep + (size_t)tri * PREP_QUADS;
-    const float4 q0 = ldg(q), q1 = ldg(q + 1), q2 = ldg(q + 2), q3 = ldg(q + 3), q4 = ldg(q + 4), q5 = ldg(q + 5);
-    const float4 q7 = ldg(q + 7), q8 = ldg(q + 8);
-    const float n2z = ldg(reinterpret_cast<const float *>(q + 9));
-    const MaterialDev *mp = sc.mats + f2u(q3.w);
-    const float4 mk = ldg(reinterpret_cast<const float4 *>(mp));      // kd.rgb, has_texture
-    const int4 mt = ldg(reinterpret_cast<const int4 *>(mp) + 1);      // tex_w, tex_h, texel_offset (lo, hi)
+    const float4 q0 = p.q0, q1 = p.q1, q2 = p.q2, q3 = p.q3, q4 = p.q4, q5 = p.q5, q7 = p.q7, q8 = p.q8;
+    const float n2z = p.n2z;
+    const float4 mk = p.mk;
 
     // barycentric + depth (drawing.cpp:41-49,115-116): e_k from the prepared differences
     const float px = (float)x, py = (float)y;
@@ -1187,13 +1244,11 @@ RAST_HD Shaded shade_pixel_prep(uint32_t tri, uint32_t x, uint32_t y, const Scen
 
     float ar = mk.x, ag = mk.y, ab = mk.z;
     if (f2u(mk.w) != 0u) {
-        const float4 q6 = ldg(q + 6);
+        const float4 q6 = p.q6;
         const float u = mul(d, add(add(mul(i0, q5.z), mul(i1, q6.x)), mul(i2, q6.z))); // drawing.cpp:135
         const float v = mul(d, add(add(mul(i0, q5.w), mul(i1, q6.y)), mul(i2, q6.w)));
-        const long long toff = ((long long)(uint32_t)mt.z) | ((long long)mt.w << 32);
-        unsigned long long tex_base = (unsigned long long)(sc.texels + toff);
-        asm volatile("" : "+l"(tex_base));
-        sample_texture(reinterpret_cast<const float4 *>(tex_base), mt.x, mt.y, mul(u, (float)mt.x), mul(sub(1.f, v), (float)mt.y), ar, ag, ab);
+        sample_texture(reinterpret_cast<const float4 *>(p.tex_base), p.tex_w, p.tex_h, mul(u, (float)p.tex_w), mul(sub(1.f, v), (float)p.tex_h), ar, ag, ab);
+        if (exact::f2u(mk.w) & 2u) { ar = mul(mk.x, ar); ag = mul(mk.y, ag); ab = mul(mk.z, ab); } // extension RAST_TEXTURE_MODULATE_KD: texel x Kd
     }
 
     const float mx = mul(d, add(add(mul(i0, q7.x), mul(i1, q7.w)), mul(i2, q8.z)));
@@ -1240,6 +1295,14 @@ RAST_HD Shaded shade_pixel_prep(uint32_t tri, uint32_t x, uint32_t y, const Scen
     out.g = to_uint(glm_min(sg, 255.f)) & 0xFFu;
     out.b = to_uint(glm_min(sb, 255.f)) & 0xFFu;
     return out;
+}
+
+// one pixel, record loaded on the spot (host emulation, tests)
+RAST_HD Shaded shade_pixel_prep(uint32_t tri, uint32_t x, uint32_t y, const Scene &sc, const float4 *__restrict__ prep, bool wind_clockwise,
+                                const LightTable &lt, const LightDev *__restrict__ lights) {
+    PrepRec r;
+    load_prep_record(r, tri, sc, prep);
+    return shade_prepared(r, x, y, wind_clockwise, lt, lights);
 }
 #endif // RAST_SHADE_PREP
 
@@ -1370,6 +1433,9 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32) k_resolve_shade(
     const float4 *prep = reinterpret_cast<const float4 *>(prep_base);
 #endif
     const bool cw = __ldg(&fp->wind_clockwise) != 0u;
+#if RAST_SHADE_PREP
+    PrepRec rec;
+#endif
     uint8_t *sr = &s_rgb[warp][0][lane];
     float *sd = &s_depth[warp][lane];
     TileOut tn{}; // non-WIDE: scalar stores from the loop
@@ -1382,8 +1448,10 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32) k_resolve_shade(
             unsigned long long *key = vis + (size_t)r * W;
             const uint32_t tri = *reinterpret_cast<const uint32_t *>(key); // L1 / L2 hit: phase 1 fetched the line
 #if RAST_SHADE_PREP
-            if (PREP) px = shade_pixel_prep(tri, x, vw.y0 + r0 + r, sc, prep, cw, lt, lights);
-            else
+            if (PREP) {
+                load_prep_record(rec, tri, sc, prep);
+                px = shade_prepared(rec, x, vw.y0 + r0 + r, cw, lt, lights);
+            } else
 #endif
             px = shade_pixel<PRE_NORMALS, FLAT>(tri, x, vw.y0 + r0 + r, sc, rv, cn, FLAT ? fp->modelview : fp->normal_m, cw, lt, lights);
             if (reset) *key = VIS_EMPTY;
@@ -1536,6 +1604,9 @@ __device__ __forceinline__ void shade_warp_tile(uint32_t t, uint32_t lane, uint8
     const float4 *prep = reinterpret_cast<const float4 *>(prep_base);
 #endif
     const bool cw = __ldg(&fp->wind_clockwise) != 0u;
+#if RAST_SHADE_PREP
+    PrepRec rec;
+#endif
     uint8_t *sr = s_rgb + lane;
     float *sd = s_depth + lane;
     uint8_t *n_rgb = nullptr; // non-WIDE: scalar stores from the loop
@@ -1553,8 +1624,10 @@ __device__ __forceinline__ void shade_warp_tile(uint32_t t, uint32_t lane, uint8
             unsigned long long *key = vis + (size_t)r * W;
             const uint32_t tri = *reinterpret_cast<const uint32_t *>(key); // L1 / L2 hit: phase 1 fetched the line
 #if RAST_SHADE_PREP
-            if (PREP) px = shade_pixel_prep(tri, x, vw.y0 + r0 + r, sc, prep, cw, lt, lights);
-            else
+            if (PREP) {
+                load_prep_record(rec, tri, sc, prep);
+                px = shade_prepared(rec, x, vw.y0 + r0 + r, cw, lt, lights);
+            } else
 #endif
             px = shade_pixel<PRE_NORMALS, FLAT>(tri, x, vw.y0 + r0 + r, sc, rv, cn, FLAT ? fp->modelview : fp->normal_m, cw, lt, lights);
             if (reset) *key = VIS_EMPTY;

@@ -168,6 +168,8 @@ struct rast_ctx {
     cudaEvent_t ev_raster[2] = {nullptr, nullptr}, ev_shade[2] = {nullptr, nullptr};
     bool shade_pending[2] = {false, false};
     bool overlap = true;
+    bool setup_pipe = true;               // meshes of >= SETUP_PIPE_MIN_TRIANGLES triangles take the software-pipelined setup kernel (RAST_SETUP_PIPE=0: never)
+    unsigned setup_pipe_grid = 148;       // its persistent grid: SMs x resident CTAs per SM (x RAST_SETUP_PIPE_WAVES)
     uint32_t shade_wt_min_tiles = 16384; // batches with at least this many 32 x 16 tiles take the one-warp-per-tile shade kernel (RAST_SHADE_WT_MIN_TILES)
     unsigned shade_wt_grid = 148;         // persistent flavour of it (RAST_SHADE_PERSIST): SMs x resident CTAs per SM
     DeviceBuffer d_shade_cursor;
@@ -350,6 +352,7 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     }
     if (sc.T && vw.band_pixels) {
         if (tile_mode) rk::k_setup<true><<<dim3(grid_for(sc.T, 256 * rk::SETUP_TRIS), count), 256, 0, st>>>(sc, vw, bt, tb);
+        else if (ctx->setup_pipe && sc.T >= rk::SETUP_PIPE_MIN_TRIANGLES) rk::k_setup_pipe<false><<<dim3(std::min(grid_for(sc.T, 256), ctx->setup_pipe_grid), count), 256, 0, st>>>(sc, vw, bt, tb);
         else if (rk::SETUP_TRIS == 1 && sc.T >= rk::SETUP_TRIS2_MIN_TRIANGLES) rk::k_setup<false, 2><<<dim3(grid_for(sc.T, 256 * 2), count), 256, 0, st>>>(sc, vw, bt, tb);
         else rk::k_setup<false><<<dim3(grid_for(sc.T, 256 * rk::SETUP_TRIS), count), 256, 0, st>>>(sc, vw, bt, tb);
     }
@@ -783,6 +786,11 @@ int rast_create(int device, rast_ctx **out) {
         ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rk::k_raster_chunks, rk::RASTER_WARPS * 32, 0) == cudaSuccess;
         if (const char *e = getenv("RAST_RASTER_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
         ctx->raster_grid = (unsigned)(sms > 0 ? sms : 148) * (unsigned)(per_sm > 0 ? per_sm : 1);
+        int sp_per_sm = 0;
+        ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sp_per_sm, rk::k_setup_pipe<false>, 256, 0) == cudaSuccess;
+        int waves = 1;
+        if (const char *e = getenv("RAST_SETUP_PIPE_WAVES")) waves = std::max(1, atoi(e));
+        ctx->setup_pipe_grid = (unsigned)(sms > 0 ? sms : 148) * (unsigned)(sp_per_sm > 0 ? sp_per_sm : 1) * (unsigned)waves;
         int wt_per_sm = 0;
         ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wt_per_sm, rk::k_resolve_shade_wt<true, true, false, RAST_SHADE_PREP != 0>, rk::SHADE_WT_WARPS * 32, 0) == cudaSuccess;
         ctx->shade_wt_grid = (unsigned)(sms > 0 ? sms : 148) * (unsigned)(wt_per_sm > 0 ? wt_per_sm : 1);
@@ -795,6 +803,7 @@ int rast_create(int device, rast_ctx **out) {
     }
     ctx->stream = ctx->own_stream;
     if (const char *e = getenv("RAST_SPARSE_COPY")) ctx->sparse_copy = atoi(e) != 0;
+    if (const char *e = getenv("RAST_SETUP_PIPE")) ctx->setup_pipe = atoi(e) != 0;
     if (const char *e = getenv("RAST_SHADE_WT_MIN_TILES")) ctx->shade_wt_min_tiles = (uint32_t)atoll(e);
     if (const char *e = getenv("RAST_OVERLAP")) ctx->overlap = atoi(e) != 0;
 #if RAST_SHADE_PREP
@@ -943,7 +952,7 @@ int rast_upload_materials(rast_ctx *ctx, const rast_material *materials, uint32_
     for (uint32_t i = 0; i < n_materials; ++i) {
         const rast_material &m = materials[i];
         md[i].kd[0] = m.kd[0]; md[i].kd[1] = m.kd[1]; md[i].kd[2] = m.kd[2];
-        md[i].has_texture = m.has_texture ? 1 : 0;
+        md[i].has_texture = m.has_texture ? (1 | (m.has_texture & RAST_TEXTURE_MODULATE_KD)) : 0;
         md[i].tex_w = m.tex_w; md[i].tex_h = m.tex_h;
         md[i].texel_offset = (long long)texel_total;
         if (m.has_texture) {

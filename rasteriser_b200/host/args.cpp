@@ -49,6 +49,7 @@ const Flag kFlags[] = {
     {"", "mesh-cache", Kind::String, false, "file.rastmesh", "[extension] binary copy of the parsed model: read it if present, else parse the .obj and write it"},
     {"", "load-threads", Kind::UInt, false, "count", "[extension] threads parsing the .obj (default: all hardware threads)"},
     {"", "flat-mode", Kind::String, false, "reference|face", "[extension] what -f does: 'reference' = nothing, like the reference (default); 'face' = one normal per face"},
+    {"", "material-mode", Kind::String, false, "reference|kd-texture", "[extension] textured materials: 'reference' = the texture replaces Kd, like the reference (default); 'kd-texture' = texel x Kd"},
 };
 const int kNumFlags = (int)(sizeof kFlags / sizeof kFlags[0]);
 
@@ -146,6 +147,10 @@ ParseResult parse_args(int argc, const char *const *argv, Args &args, std::strin
         else if (n == "flat-mode") {
             if (value != "reference" && value != "face") { message = "PARSE ERROR: Argument: (--flat-mode)\n             Value '" + value + "' does not meet constraint: reference|face"; return ParseResult::Error; }
             args.flat_face = value == "face";
+        }
+        else if (n == "material-mode") {
+            if (value != "reference" && value != "kd-texture") { message = "PARSE ERROR: Argument: (--material-mode)\n             Value '" + value + "' does not meet constraint: reference|kd-texture"; return ParseResult::Error; }
+            args.modulate_kd = value == "kd-texture";
         }
     }
     for (int k = 0; k < kNumFlags; ++k)

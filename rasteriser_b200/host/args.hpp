@@ -33,6 +33,7 @@ struct Args {
     bool timing = false;              // --timing: stage wall times on stderr
     std::string mesh_cache;           // --mesh-cache FILE: binary copy of the parsed model (read if present, else written after parsing)
     unsigned int load_threads = 0;    // --load-threads N: OBJ parser threads (0 = all hardware threads)
+    bool modulate_kd = false;         // --material-mode kd-texture: texel x Kd for textured materials (extension; the reference drops Kd there)
     bool flat_face = false;           // --flat-mode face: with -f, shade with one normal per face (extension; default keeps the reference's no-op)
 };
 

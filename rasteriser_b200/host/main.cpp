@@ -92,6 +92,7 @@ int main(int argc, char **argv) {
 
     try {
         rast::Session session(arguments.device);
+        if (arguments.modulate_kd) session.set_texture_bits(RAST_TEXTURE_MODULATE_KD);
         stage("create context");
         const int flat_code = (arguments.flat && arguments.flat_face) ? RAST_FLAT_FACE : (arguments.flat ? 1 : 0);
         if (!arguments.spin) {

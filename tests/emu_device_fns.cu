@@ -100,7 +100,7 @@ extern "C" int emu_draw(const float *pos, uint32_t V, const float *nrm, uint32_t
     std::vector<float4> texels;
     for (uint32_t i = 0; i < M; ++i) {
         md[i].kd[0] = mats[i].kd[0]; md[i].kd[1] = mats[i].kd[1]; md[i].kd[2] = mats[i].kd[2];
-        md[i].has_texture = mats[i].has_texture ? 1 : 0;
+        md[i].has_texture = mats[i].has_texture ? (1 | (mats[i].has_texture & 2)) : 0;
         md[i].tex_w = mats[i].tex_w; md[i].tex_h = mats[i].tex_h;
         md[i].texel_offset = (long long)texels.size();
         if (mats[i].has_texture) {

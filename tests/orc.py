@@ -141,7 +141,7 @@ class Scene:
         for i, m in enumerate(self.materials):
             mats[i].kd = (C.c_float * 3)(*m["kd"])
             t = m.get("texels")
-            mats[i].has_texture = 0 if t is None else 1
+            mats[i].has_texture = 0 if t is None else (3 if m.get("modulate_kd") else 1)
             if t is not None:
                 mats[i].tex_h, mats[i].tex_w = t.shape[1], t.shape[2]
                 mats[i].texels = t.ctypes.data

@@ -67,7 +67,7 @@ def emu_draw(emu, scene, lights7, oa, flags, tiny_max=16, band=None):
     for i, m in enumerate(scene.materials):
         mats[i].kd = (C.c_float * 3)(*m["kd"])
         t = m.get("texels")
-        mats[i].has_texture = 0 if t is None else 1
+        mats[i].has_texture = 0 if t is None else (3 if m.get("modulate_kd") else 1)
         if t is not None:
             mats[i].tex_h, mats[i].tex_w = t.shape[1], t.shape[2]
             mats[i].texels = t.ctypes.data
@@ -209,3 +209,18 @@ def test_lockstep_warp_emulation(emu, emu_blockz):
         if oa.image_width * oa.image_height > 100000 or len(scene.tris) > 2000:
             continue
         assert_exact(emu_draw(emu_blockz, scene, lights, oa, ALL_CHUNKS | EARLY_Z | WARP), orc.oracle_draw(scene, lights, oa, threads=2), "seed %d" % seed)
+
+
+@pytest.mark.parametrize("flags", [PRE_NORMALS, PREP | TIGHT])
+def test_extension_texture_modulates_kd_on_the_host(emu, flags):
+    """The device's shade_pixel / shade_pixel_prep with has_texture = 1 | RAST_TEXTURE_MODULATE_KD (texel x Kd, an extension the
+    reference does not have) against the oracle's definition; Kd = 1 must reproduce the reference mode."""
+    base = S.scene("suzanne")
+    lights = S.lights("threepoint")
+    oa = orc.make_args(160, 120, angles=(0.1, 0.6, 0.0))
+    scene = orc.Scene(base.positions, base.normals, base.uvs, base.tris, [{"kd": (0.64, 0.3, 0.9), "texels": base.materials[0]["texels"], "modulate_kd": True}])
+    got = emu_draw(emu, scene, lights, oa, flags)
+    assert_exact(got, orc.oracle_draw(scene, lights, oa), "texture x Kd")
+    assert not np.array_equal(got[0], orc.oracle_draw(base, lights, oa)[0])
+    white = orc.Scene(base.positions, base.normals, base.uvs, base.tris, [{"kd": (1.0, 1.0, 1.0), "texels": base.materials[0]["texels"], "modulate_kd": True}])
+    assert np.array_equal(emu_draw(emu, white, lights, oa, flags)[0], orc.oracle_draw(base, lights, oa)[0])

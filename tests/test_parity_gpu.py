@@ -356,3 +356,26 @@ def test_flat_face_soup_and_cli(tmp_path):
     fa.flat = 2
     assert np.array_equal(ref_img, orc.oracle_draw(S.scene("suzanne"), S.lights("threepoint"), sm)[0])   # -f == no -f, as in the reference
     assert np.array_equal(face_img, orc.oracle_draw(S.scene("suzanne"), S.lights("threepoint"), fa)[0])
+
+
+def test_extension_texture_modulates_kd():
+    """EXTENSION (not reference behaviour): has_texture = 1 | RAST_TEXTURE_MODULATE_KD makes the texel modulate the
+    material's Kd (the reference drops Kd of a textured material, material.cpp:19-21).  Defined identically in oracle and device;
+    with Kd = (1,1,1) it must equal the reference mode bit for bit."""
+    base = S.scene("suzanne")
+    lights = S.lights("threepoint")
+    oa = orc.make_args(320, 240, angles=(0.1, 0.6, 0.0))
+    frames = {}
+    for kd in ((0.64, 0.3, 0.9), (1.0, 1.0, 1.0)):
+        mats = [{"kd": kd, "texels": base.materials[0]["texels"], "modulate_kd": True}]
+        scene = orc.Scene(base.positions, base.normals, base.uvs, base.tris, mats)
+        r = make_renderer(scene, lights)
+        try:
+            got = gpu_draw(r, oa)
+        finally:
+            r.close()
+        assert_parity(got, orc.oracle_draw(scene, lights, oa), "texture x Kd %s" % (kd,))
+        assert orc.oracle_draw(scene, lights, oa)[0].tobytes() == got[0].tobytes()
+        frames[kd] = got[0]
+    ref_mode = orc.oracle_draw(base, lights, oa)[0]
+    assert np.array_equal(frames[(1.0, 1.0, 1.0)], ref_mode) and not np.array_equal(frames[(0.64, 0.3, 0.9)], ref_mode)

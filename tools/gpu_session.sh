@@ -38,6 +38,8 @@ if has ncu; then
   cap k_prepare_tris 12 prepare spin1080p
   cap k_setup 5 setup tess4k
   cap k_setup 5 setup50m tess4k_64lights
-  cap k_raster 5 raster_over overdraw8k
+  cap k_raster_tiles 3 raster_over overdraw8k
+  cap k_resolve_shade 3 shade_over overdraw8k
+  cap k_resolve_shade 5 shade_tess tess4k
 fi
 ls -la $o | grep $tag
