@@ -241,9 +241,9 @@ def run_reference_arm(opts, wl):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-# pass -> kernels that implement it (the library picks per batch: chunk queue or screen-tile bins, 4-rows-per-warp or warp-per-tile shading);
-# the captured one (profiles/r*_traffic.json, same workload) names the record
-KERNEL_OF_PASS = {"vertex": ("k_vertex",), "setup": ("k_setup",), "raster": ("k_raster_tiles", "k_raster_chunks"), "shade": ("k_resolve_shade_wt", "k_resolve_shade"), "clear": ("k_clear",)}
+# pass -> kernel; setup / raster / shade have several flavours and the library picks per batch (chunk queue or screen-tile bins, one warp per
+# 4 rows or per tile, ...): rast_last_schedule says which one ran, these are only the names when that is not available
+KERNEL_OF_PASS = {"vertex": "k_vertex", "setup": "k_setup", "raster": "k_raster_chunks", "shade": "k_resolve_shade", "clear": "k_clear"}
 # golden hashes produced by the REFERENCE's own code (tests/golden/make_golden*.py): workload -> (file, case)
 GOLDEN_OF_WORKLOAD = {"suzanne640": ("cases.json", "suzanne_640x480"), "tess4k": ("large_cases.json", "config3_tess91_4k"),
                       "tess4k_64lights": ("large_cases.json", "config5_tess227_64lights_4k"), "overdraw8k": ("large_cases.json", "config4_overdraw_8k")}
@@ -308,7 +308,7 @@ def profile_passes(api, r, step, n_steps=2):
     return pass_ms
 
 
-def roofline_record(wl, workload, pass_ms, n_frames, P, visible_tris, step_ms, world_frames_per_step):
+def roofline_record(wl, workload, pass_ms, n_frames, P, visible_tris, step_ms, world_frames_per_step, schedule=None):
     """Roofline of the dominant kernel: algorithmic bytes per launch / its average launch duration."""
     peak, peak_src = hbm_peak()
     batches = (n_frames + 31) // 32
@@ -320,14 +320,15 @@ def roofline_record(wl, workload, pass_ms, n_frames, P, visible_tris, step_ms, w
     avg_ms = pass_ms[dominant] / batches
     achieved = alg / (avg_ms * 1e-3) / 1e9
     tr, tr_file = ncu_traffic(workload)
-    kname = ([k for k in KERNEL_OF_PASS[dominant] if k in tr] or [KERNEL_OF_PASS[dominant][-1]])[0]
+    kfull = (schedule or {}).get(dominant) or KERNEL_OF_PASS[dominant]  # e.g. k_setup<0,2>
+    kname = kfull.split("<")[0]
     traffic, limiter = None, None
     if kname in tr:
         k = tr[kname]
         traffic = k["dram_bytes_per_launch"] * frames_per_launch / k["frames_per_launch"]
         limiter = {key: k[key] for key in ("issue_active_pct", "l1tex_throughput_pct", "warp_instructions_per_launch", "lanes_per_instruction", "top_stall") if key in k}
         limiter["source"] = tr_file
-    rec = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+    rec = {"bound": "hbm", "kernel": kfull, "schedule": schedule, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
            "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms, "frames_per_launch": frames_per_launch, "pass_ms_per_step": pass_ms, "limiter": limiter,
            # every pass of a frame against the HBM roofline, two ways: SURVEY 8(d)'s frame total B (which counts a clear and a key write-back
            # this pipeline never performs), and the DRAM bytes ncu measured for the kernels of one batch (profiles/), both / step time
@@ -391,6 +392,7 @@ def run_single_frame_workload(api, torch, name, dev, local, steps):
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / steps
     pass_ms = profile_passes(api, r, step)
+    schedule = r.last_schedule()
     r.set_keep_visibility(True)  # after the timed region: the last frame keeps its keys for the statistics and the id hash
     step()
     r.sync()
@@ -407,7 +409,7 @@ def run_single_frame_workload(api, torch, name, dev, local, steps):
         verify["ok"] = verify["ok"] and verify["tri_ok"]
     rec = {"workload": wl["label"], "value": 1e3 / ms, "unit": UNIT, "ms_per_frame": ms, "steps": steps, "mtris_per_s": len(wl["tris"]) / ms / 1e3,
            "image": [W, H], "triangles": len(wl["tris"]), "lights": len(wl["lights"]), "stats": st,
-           "roofline": roofline_record(wl, name, pass_ms, 1, P, visible_tris, ms, 1), "verify": verify}
+           "roofline": roofline_record(wl, name, pass_ms, 1, P, visible_tris, ms, 1, schedule), "verify": verify}
     del frame_dev, depth_dev
     r.close()
     return rec
@@ -446,6 +448,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # N > 1: every rank keeps its host threads and pinned buffers next to its own GPU (host-buffer draws are bound by host-memory ingest)
+    host_binding = multi.bind_host_to_gpu(local, int(os.environ.get("LOCAL_WORLD_SIZE", world))) if world > 1 and not os.environ.get("RAST_BENCH_NO_BIND") else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.Stream(dev)  # the kernels and the timing events share this stream
@@ -556,13 +560,24 @@ def main():
                "note": "rast_draw_frames with pinned host outputs, %d frames per call: RGB8 + f32 depth of every frame delivered complete in host memory inside the timed region (wall clock, max over ranks); the library copies each frame's covered rectangle over PCIe (d2h_bytes_per_step, counted by the library) and writes the constant background of the host buffers itself on 4 host threads (RAST_SPARSE_COPY=0 copies whole frames)" % chunk}
         checksum = int(frames_host[len(chunks[-1]) // 2].astype(np.uint64).sum())
         v, d2h_step = host_run(False)  # colour only (the reference's spin loop shows frames; its depth buffer is scratch)
+        if host_binding is not None:
+            gathered_b = [None] * world
+            dist.all_gather_object(gathered_b, host_binding)
+            e2e["host_binding_per_rank"] = gathered_b
         e2e["frames_only"] = {"value": v, "d2h_bytes_per_step": int(d2h_step), "host_bytes_delivered_per_step": int(n * 3 * P),
                               "note": "same call with depths=NULL: only the RGB8 frames cross PCIe"}
+        # the reference's own loop redraws into the same buffers (renderer.cpp:105-111); with that promise the library rewrites only what changes
+        r.set_retained_outputs(True)
+        v, d2h_step = host_run(True)
+        r.set_retained_outputs(False)
+        e2e["retained_outputs"] = {"value": v, "d2h_bytes_per_step": int(d2h_step),
+                                   "note": "rast_set_retained_outputs(1): the caller promises that the buffers still hold the previous call's frames (each call here redraws the same %d host frame / depth buffers with the next poses of the sequence); the covered rectangle of every frame still crosses PCIe, but only the part of the old rectangle outside the new one is reset on the host instead of the whole background; same bytes in the buffers (tests/test_api_gpu.py)" % chunk}
         lib.rast_host_free(fb)
         lib.rast_host_free(db)
 
     # ---- per-pass kernel durations (CUDA events around each launch, same stream) and the roofline of the dominant kernel ----
     pass_ms = profile_passes(api, r, step_device)
+    schedule = r.last_schedule()
     r.set_keep_visibility(True)  # after the timed regions: the last frame keeps its keys for the statistics
     r.draw_frames_device(arr[n - 1:n] if n > 1 else arr, frames_dev.data_ptr(), depths_dev.data_ptr())
     r.sync()
@@ -570,7 +585,7 @@ def main():
     tri_ids = r.triangle_ids(W, rows)
     r.set_keep_visibility(False)
     visible_tris = int(len(np.unique(tri_ids[tri_ids != api.NO_TRIANGLE])))
-    roofline = roofline_record(wl, opts.workload, pass_ms, n, P, visible_tris, ms_step, n)
+    roofline = roofline_record(wl, opts.workload, pass_ms, n, P, visible_tris, ms_step, n, schedule)
 
     # ---- the frames against the reference's golden hashes (in-process) ----
     verify = None

@@ -174,6 +174,16 @@ int rast_draw_frames(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
 
 int rast_sync(rast_ctx *ctx);
 
+/* Retained outputs (off by default).  The reference's spin loop redraws into the SAME frame / depth buffers every frame
+ * (renderer.cpp:105-111).  With this switch on the caller promises that the host buffers handed to rast_draw_frame(s) still
+ * hold, unmodified, what this context's previous host-buffer draw wrote into them (same pointers, same image size and band, at
+ * most as many frames).  The library then rewrites only what changes: the newly covered rectangle of each frame is copied from
+ * the device and the part of the previously covered rectangle outside it is reset to the cleared values (0 / 1.0f), instead of
+ * rewriting the whole background of every frame on every call.  The buffers end up byte-identical to a draw without the
+ * promise; a call with other buffers, another size, or the first call after switching it on is a normal full draw.  Breaking
+ * the promise (buffers modified in between) leaves the caller's modifications in the background. */
+int rast_set_retained_outputs(rast_ctx *ctx, int enabled);
+
 /* ---- auxiliary outputs -------------------------------------------------------------------- */
 /* Winning triangle index per pixel of the most recent frame (RAST_NO_TRIANGLE = background),
  * [H][W] u32, host pointer.  This is the visibility buffer's low word; parity tests compare it
@@ -190,6 +200,10 @@ int rast_depth_to_u8(rast_ctx *ctx, uint8_t *out);
 int rast_get_stats(rast_ctx *ctx, rast_stats *out);
 int rast_set_profiling(rast_ctx *ctx, int enabled);
 int rast_get_pass_ms(rast_ctx *ctx, float ms[RAST_PASS_COUNT]);
+/* Which kernel flavour each pass of the most recent batch took, e.g. "setup=k_setup<0,2> raster=k_raster_tiles
+ * shade=k_resolve_shade_wt" (the library picks per batch: chunk queue or screen-tile bins, one warp per 4 rows or per tile).
+ * Waits for the context's streams; the string lives until the next call of this function on the context. */
+const char *rast_last_schedule(rast_ctx *ctx);
 /* number of kernel launches issued by this context since creation */
 uint64_t rast_launch_count(const rast_ctx *ctx);
 /* Bytes of frame / depth data this context has copied device -> host so far.  Host-buffer draws copy only the

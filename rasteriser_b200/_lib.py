@@ -65,6 +65,8 @@ SYMBOLS = {
     "rast_depth_to_u8": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rast_get_stats": (C.c_int, [C.c_void_p, C.POINTER(RastStats)]),
     "rast_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "rast_set_retained_outputs": (C.c_int, [C.c_void_p, C.c_int]),
+    "rast_last_schedule": (C.c_char_p, [C.c_void_p]),
     "rast_get_pass_ms": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rast_launch_count": (C.c_uint64, [C.c_void_p]),
     "rast_d2h_bytes": (C.c_uint64, [C.c_void_p]),

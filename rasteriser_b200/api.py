@@ -251,6 +251,16 @@ class Renderer:
         self._check(self._lib.rast_get_stats(self._h, C.byref(s)), "rast_get_stats")
         return dict(triangles=s.triangles, front_facing=s.front_facing, queued_chunks=s.queued_chunks, visible_pixels=s.visible_pixels)
 
+    def last_schedule(self):
+        """{'setup': ..., 'raster': ..., 'shade': ...}: the kernel flavour each pass of the most recent batch took."""
+        txt = self._lib.rast_last_schedule(self._h).decode()
+        return dict(kv.split("=", 1) for kv in txt.split(" ") if "=" in kv) if txt else {}
+
+    def set_retained_outputs(self, on):
+        """The caller promises that the host buffers of a draw still hold what the previous host-buffer draw of this renderer wrote
+        (the reference's spin loop reuses its buffers): only the changed rectangles are rewritten.  Same bytes in the buffers."""
+        self._check(self._lib.rast_set_retained_outputs(self._h, int(bool(on))), "rast_set_retained_outputs")
+
     def set_profiling(self, on):
         self._check(self._lib.rast_set_profiling(self._h, int(bool(on))), "rast_set_profiling")
 

@@ -281,8 +281,13 @@ RAST_HD void test_and_commit(const TriSetup &s, uint32_t x, uint32_t y, uint32_t
 // renderer.cpp:85-86 / :107-108 (frame = 0, depth = 1.0f) become "no triangle" in the visibility buffer.
 // Only needed for slots that are not known to be empty: the shade pass hands every key it consumes
 // back as VIS_EMPTY, so in steady state the buffer is already clear when the next batch starts.
+// (The 16-byte stores need a 16-byte aligned start; an odd slot of a band with an odd pixel count -- the one kept slot of
+// rast_set_keep_visibility, 641 x 483 -- starts 8 bytes off: its first key is written on its own.)
 __global__ void k_clear(unsigned long long *vis, size_t n) {
-    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    const size_t head = (reinterpret_cast<uintptr_t>(vis) & 8u) ? 1u : 0u;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (head && t == 0 && n) vis[0] = VIS_EMPTY;
+    const size_t i = head + t * 2;
     if (i + 1 < n) {
         *reinterpret_cast<ulonglong2 *>(vis + i) = make_ulonglong2(VIS_EMPTY, VIS_EMPTY);
     } else if (i < n) {
@@ -1220,6 +1225,9 @@ RAST_HD void load_prep_record(PrepRec &r, uint32_t tri, const Scene &sc, const f
     r.tex_w = mt.x; r.tex_h = mt.y;
     const long long toff = ((long long)(uint32_t)mt.z) | ((long long)mt.w << 32);
     r.tex_base = (unsigned long long)(sc.texels + toff);
+#ifdef __CUDA_ARCH__
+    asm volatile("" : "+l"(r.tex_base)); // opaque base: each corner becomes one IMAD.WIDE instead of a 64-bit add + LEA pair
+#endif
 }
 
 // shade_pixel for a prepared triangle: the same operations on the same values, in the same order, from the record
@@ -1484,7 +1492,7 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32) k_resolve_shade(
 // RAST_SHADE_CTA_WARPS = warps per CTA (side by side in x); RAST_SHADE_PERSIST = 1: a persistent grid whose warps fetch tiles
 // from a counter (RAST_SHADE_GRAB consecutive tiles per fetch) instead of one CTA per RAST_SHADE_CTA_WARPS tiles.
 #ifndef RAST_SHADE_CTA_WARPS
-#define RAST_SHADE_CTA_WARPS 1
+#define RAST_SHADE_CTA_WARPS 4
 #endif
 #ifndef RAST_SHADE_PERSIST
 #define RAST_SHADE_PERSIST 0
@@ -1652,8 +1660,11 @@ __device__ __forceinline__ void shade_warp_tile(uint32_t t, uint32_t lane, uint8
     }
 }
 
+// Measured on a B200 (120-frame 1080p calls, shade pass per call, one session): 1 warp per CTA 1.71 ms, 2: 1.61, 4: 1.57, 4 with
+// __launch_bounds__(128, 6): 1.49 -- the hint lets ptxas take 72 registers instead of 64 (28 instead of 32 resident warps, but fewer
+// serialised dependent chains per pixel); (128, 8) is the 64-register code again.
 #ifndef RAST_SHADE_WT_MIN_BLOCKS
-#define RAST_SHADE_WT_MIN_BLOCKS 0
+#define RAST_SHADE_WT_MIN_BLOCKS 6
 #endif
 template <bool WIDE, bool PRE_NORMALS, bool FLAT, bool PREP>
 #if RAST_SHADE_WT_MIN_BLOCKS > 0

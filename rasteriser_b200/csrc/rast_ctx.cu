@@ -179,6 +179,19 @@ struct rast_ctx {
     PinnedBuffer h_frames, h_lights, h_status, h_bbox[2];
     DeviceBuffer d_bbox[2];
     bool sparse_copy = true;     // host-buffer draws copy only each frame's covered rectangle back (RAST_SPARSE_COPY=0: whole frames)
+    // rast_set_retained_outputs: the caller promises that the host buffers of a draw still hold what this context's previous
+    // host-buffer draw wrote there.  `retained` remembers that previous draw (buffers, geometry, one rectangle per frame: what
+    // is NOT the cleared background); finish_batch then resets only the part of the old rectangle the new one does not cover.
+    struct HostRect { uint32_t x0, y0, x1, y1; bool empty; };
+    struct Retained {
+        const uint8_t *frames = nullptr;
+        const float *depths = nullptr;
+        uint32_t W = 0, rows = 0, y0 = 0;
+        std::vector<HostRect> rects; // per frame of the buffers
+        bool valid = false;
+    } retained;
+    bool retained_outputs = false; // the promise (off by default)
+    bool retained_now = false;     // this call: the promise holds for these buffers
     unsigned host_threads = 0;   // helpers of the background fill (RAST_HOST_THREADS = total threads; default min(4, hardware / 2))
     HostPool pool;
     cudaEvent_t ev_params = nullptr, ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
@@ -204,6 +217,11 @@ struct rast_ctx {
     uint64_t last_queue_count = 0;
     size_t call_frames = 0; // frames of the call being launched
     unsigned long long last_batch_pixels = 0; // pixels (all frames) of the last batch launched
+
+    // which kernel flavour each pass of the most recent batch took (rast_last_schedule)
+    const char *sched_setup = "", *sched_shade = "";
+    bool sched_bins_requested = false;
+    std::string schedule_text;
 
     // profiling
     bool profiling = false;
@@ -350,11 +368,12 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
         tb.items_cap = ctx->items_cap;
         RAST_CUDA(ctx, cudaMemsetAsync(tb.count, 0, n_tiles * 4, st));
     }
+    ctx->sched_bins_requested = tile_mode;
     if (sc.T && vw.band_pixels) {
-        if (tile_mode) rk::k_setup<true><<<dim3(grid_for(sc.T, 256 * rk::SETUP_TRIS), count), 256, 0, st>>>(sc, vw, bt, tb);
-        else if (ctx->setup_pipe && sc.T >= rk::SETUP_PIPE_MIN_TRIANGLES) rk::k_setup_pipe<false><<<dim3(std::min(grid_for(sc.T, 256), ctx->setup_pipe_grid), count), 256, 0, st>>>(sc, vw, bt, tb);
-        else if (rk::SETUP_TRIS == 1 && sc.T >= rk::SETUP_TRIS2_MIN_TRIANGLES) rk::k_setup<false, 2><<<dim3(grid_for(sc.T, 256 * 2), count), 256, 0, st>>>(sc, vw, bt, tb);
-        else rk::k_setup<false><<<dim3(grid_for(sc.T, 256 * rk::SETUP_TRIS), count), 256, 0, st>>>(sc, vw, bt, tb);
+        if (tile_mode) { rk::k_setup<true><<<dim3(grid_for(sc.T, 256 * rk::SETUP_TRIS), count), 256, 0, st>>>(sc, vw, bt, tb); ctx->sched_setup = "k_setup<1,1>"; }
+        else if (ctx->setup_pipe && sc.T >= rk::SETUP_PIPE_MIN_TRIANGLES) { rk::k_setup_pipe<false><<<dim3(std::min(grid_for(sc.T, 256), ctx->setup_pipe_grid), count), 256, 0, st>>>(sc, vw, bt, tb); ctx->sched_setup = "k_setup_pipe<0>"; }
+        else if (rk::SETUP_TRIS == 1 && sc.T >= rk::SETUP_TRIS2_MIN_TRIANGLES) { rk::k_setup<false, 2><<<dim3(grid_for(sc.T, 256 * 2), count), 256, 0, st>>>(sc, vw, bt, tb); ctx->sched_setup = "k_setup<0,2>"; }
+        else { rk::k_setup<false><<<dim3(grid_for(sc.T, 256 * rk::SETUP_TRIS), count), 256, 0, st>>>(sc, vw, bt, tb); ctx->sched_setup = "k_setup<0,1>"; }
     }
     if (prof) cudaEventRecord(ctx->ev_pass[3], st);
     if (tile_mode && vw.band_pixels) {
@@ -387,6 +406,7 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
         // one warp per whole tile for big batches, four warps per tile (4 rows each) when the batch has few tiles (kernels.cuh)
         const uint32_t n_tiles = (uint32_t)(flags_per_frame * count);
         const bool warp_tiles = n_tiles >= ctx->shade_wt_min_tiles;
+        ctx->sched_shade = warp_tiles ? "k_resolve_shade_wt" : "k_resolve_shade";
         unsigned int *cursor = nullptr;
         unsigned wt_grid = grid_for(n_tiles, rk::SHADE_WT_WARPS);
 #if RAST_SHADE_PERSIST
@@ -481,6 +501,9 @@ int finish_batch(rast_ctx *ctx, const PendingBatch &b, const rk::View &vw, uint8
     const uint32_t *bb = ctx->h_bbox[b.slot].as<uint32_t>();
     struct Rect { uint32_t x0, y0, x1, y1; bool empty, whole; };
     std::vector<Rect> rects(b.count);
+    // retained outputs: what each of these frames' buffers held outside the cleared background before this call
+    std::vector<rast_ctx::HostRect> old_rects;
+    if (ctx->retained_now) old_rects.assign(ctx->retained.rects.begin() + b.first, ctx->retained.rects.begin() + b.first + b.count);
     for (uint32_t i = 0; i < b.count; ++i) {
         Rect &r = rects[i];
         r.empty = bb[4 * i] == 0xFFFFFFFFu;
@@ -491,6 +514,13 @@ int finish_batch(rast_ctx *ctx, const PendingBatch &b, const rk::View &vw, uint8
         r.y0 = bb[4 * i + 1];
         r.y1 = rows - 1u - bb[4 * i + 3];
         r.whole = (uint64_t)(r.x1 - r.x0 + 1u) * (r.y1 - r.y0 + 1u) * 4u > (uint64_t)P * 3u; // > 75 %: one contiguous copy is cheaper
+    }
+    if (ctx->retained_outputs) { // remember what these buffers will hold (for the next call that keeps the promise)
+        if (ctx->retained.rects.size() < (size_t)b.first + b.count) ctx->retained.rects.resize((size_t)b.first + b.count, rast_ctx::HostRect{0u, 0u, W - 1u, rows - 1u, false});
+        for (uint32_t i = 0; i < b.count; ++i) {
+            const Rect &r = rects[i];
+            ctx->retained.rects[b.first + i] = r.empty ? rast_ctx::HostRect{0u, 0u, 0u, 0u, true} : (r.whole ? rast_ctx::HostRect{0u, 0u, W - 1u, rows - 1u, false} : rast_ctx::HostRect{r.x0, r.y0, r.x1, r.y1, false});
+        }
     }
     for (uint32_t i = 0; i < b.count; ++i) {
         const Rect &r = rects[i];
@@ -528,10 +558,18 @@ int finish_batch(rast_ctx *ctx, const PendingBatch &b, const rk::View &vw, uint8
             if (is_depth) stream_fill(depths + f * P + (size_t)y * W + xa, (size_t)(xb - xa) * 4, 0x3F800000u /* 1.0f */);
             else stream_fill(frames + (f * 3 + plane) * P + (size_t)y * W + xa, xb - xa, 0u);
         };
-        for (uint32_t y = ya; y < yb; ++y) {
-            if (r.empty || y < r.y0 || y > r.y1) { fill_span(y, 0u, W); continue; }
-            fill_span(y, 0u, r.x0);
-            fill_span(y, r.x1 + 1u, W);
+        // the span of row y that must become background: the whole row, or -- retained outputs -- only what the previous draw left there
+        uint32_t oa = 0u, ob = W; // [oa, ob) of the rows [oy0, oy1]
+        uint32_t oy0 = 0u, oy1 = rows - 1u;
+        if (!old_rects.empty()) {
+            const rast_ctx::HostRect &o = old_rects[i];
+            if (o.empty) return;
+            oa = o.x0; ob = o.x1 + 1u; oy0 = o.y0; oy1 = o.y1;
+        }
+        for (uint32_t y = std::max(ya, oy0); y < yb && y <= oy1; ++y) {
+            if (r.empty || y < r.y0 || y > r.y1) { fill_span(y, oa, ob); continue; }
+            fill_span(y, oa, std::min(ob, r.x0));
+            fill_span(y, std::max(oa, r.x1 + 1u), ob);
         }
         _mm_sfence(); // the streaming stores of this task are globally visible before it counts as done
     };
@@ -675,6 +713,15 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
 
     if (ctx->profiling) memset(ctx->pass_ms, 0, sizeof ctx->pass_ms);
     ctx->call_frames = n;
+    if (!device_ptrs) {
+        // retained outputs: the promise covers exactly the buffers of the previous host-buffer draw, same geometry, and only frames that draw wrote
+        rast_ctx::Retained &rt = ctx->retained;
+        ctx->retained_now = ctx->retained_outputs && ctx->sparse_copy && rt.valid && rt.frames == frames && rt.depths == depths && rt.W == vw.W &&
+                            rt.rows == vw.y1 - vw.y0 && rt.y0 == vw.y0 && n <= rt.rects.size();
+        if (!ctx->retained_now) rt.rects.clear();
+        rt.valid = false; // until this call has completed
+        rt.frames = frames; rt.depths = depths; rt.W = vw.W; rt.rows = vw.y1 - vw.y0; rt.y0 = vw.y0;
+    }
 
     int slot = 0, ps = ctx->next_ps;
     PendingBatch pending;
@@ -738,6 +785,8 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
         RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->copied_pending[0] = ctx->copied_pending[1] = false;
         ctx->last_queue_count = ctx->h_status.as<unsigned long long>()[0];
+        ctx->retained.valid = ctx->retained_outputs && ctx->sparse_copy; // (whole-frame copies keep no rectangles)
+        ctx->retained_now = false;
     }
     return RAST_OK;
 }
@@ -1178,6 +1227,24 @@ int rast_get_stats(rast_ctx *ctx, rast_stats *out) {
 int rast_set_keep_visibility(rast_ctx *ctx, int enabled) {
     if (!ctx) return RAST_EINVAL;
     ctx->keep_visibility = enabled != 0;
+    return RAST_OK;
+}
+
+const char *rast_last_schedule(rast_ctx *ctx) {
+    if (!ctx) return "";
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->front_stream);
+    cudaStreamSynchronize(ctx->stream); // the counters of the call's last batch are in h_status now
+    const bool bins = ctx->sched_bins_requested && ctx->h_status.as<unsigned long long>()[rk::CNT_TILE_MODE] != 0ull;
+    ctx->schedule_text = std::string("setup=") + ctx->sched_setup + " raster=" + (bins ? "k_raster_tiles" : "k_raster_chunks") + " shade=" + ctx->sched_shade;
+    return ctx->schedule_text.c_str();
+}
+
+int rast_set_retained_outputs(rast_ctx *ctx, int enabled) {
+    if (!ctx) return RAST_EINVAL;
+    ctx->retained_outputs = enabled != 0;
+    ctx->retained.valid = false;
+    ctx->retained.rects.clear();
     return RAST_OK;
 }
 

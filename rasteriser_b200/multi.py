@@ -10,6 +10,56 @@ import torch
 import torch.distributed as dist
 
 
+def _cpulist(text):
+    out = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        out.extend(range(int(a), int(b or a) + 1))
+    return out
+
+
+def bind_host_to_gpu(local_rank, local_world):
+    """Pin this process (and every thread it starts later: the library's background-fill pool, the pinned allocations' first
+    touch) to CPUs next to GPU `local_rank`: the cores of the GPU's NUMA node (sysfs numa_node of its PCI function) -- split
+    among the ranks that share the node -- or, where the platform reports no NUMA node for the device (VMs), an even share of the
+    process's CPUs.  Host-buffer draws are bound by host-memory ingest at N > 1 (DMA writes + background fill); without this
+    every rank's helpers roam all sockets and the ranks whose GPU sits on the far socket see a fraction of the copy rate.
+    Returns a dict describing what was done (bench.py prints it)."""
+    import os
+    info = {"numa_node": None, "cpus": None, "how": "unchanged"}
+    if not hasattr(os, "sched_setaffinity"):
+        return info
+    allowed = sorted(os.sched_getaffinity(0))
+    node, node_cpus, sharers, my_slot = -1, None, local_world, local_rank
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        nodes = []
+        for g in range(local_world):
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(g)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            path = "/sys/bus/pci/devices/%s/numa_node" % bus[-12:].lower()
+            nodes.append(int(open(path).read()) if os.path.exists(path) else -1)
+        node = nodes[local_rank]
+        if node >= 0:
+            node_cpus = [c for c in _cpulist(open("/sys/devices/system/node/node%d/cpulist" % node).read()) if c in allowed]
+            same = [g for g in range(local_world) if nodes[g] == node]
+            sharers, my_slot = len(same), same.index(local_rank)
+    except Exception:
+        node = -1
+    pool = node_cpus if node_cpus else allowed
+    share = max(1, len(pool) // max(1, sharers))
+    cpus = pool[my_slot * share:(my_slot + 1) * share] or pool
+    try:
+        os.sched_setaffinity(0, cpus)
+        info.update(numa_node=node if node >= 0 else None, cpus="%d-%d (%d)" % (cpus[0], cpus[-1], len(cpus)), how="numa node of the GPU" if node_cpus else "even share of the allowed CPUs")
+    except OSError:
+        pass
+    return info
+
+
 def frames_of_rank(n_frames_total, rank, world):
     """Indices of the global sequence this rank renders (round-robin: k mod world == rank)."""
     return list(range(rank, n_frames_total, world))

@@ -147,6 +147,90 @@ def test_sparse_host_copy_delivers_the_same_bytes(monkeypatch):
     assert sparse[1] < 0.9 * whole[1]  # fewer bytes crossed PCIe (two of the seven poses cover most of the frame)
 
 
+def test_kept_visibility_slot_is_cleared_at_any_alignment():
+    """rast_set_keep_visibility keeps the keys of a call's last frame; the next call clears that one slot.  With an odd pixel
+    count an odd slot starts 8 bytes off a 16-byte boundary (k_clear stores 16 bytes at a time): 2, 3, 6 and 7 frames of
+    641 x 483 and of 33 x 1, each drawn twice, must equal frame-by-frame draws."""
+    from rasteriser_b200 import api
+    r = make_renderer(S.scene("suzanne"), S.lights("threepoint"))  # keeps visibility
+    one = make_renderer(S.scene("suzanne"), S.lights("threepoint"))
+    try:
+        for W, H in ((641, 483), (33, 1)):
+            for n in (2, 3, 6, 7):
+                poses = [api.Args(W, H, tait_bryan_angles=(0.2, 0.7 * k + 0.1 * n, 0.0)) for k in range(n)]
+                want = [one.draw_frame(a) for a in poses]
+                for _ in range(2):
+                    fs, ds = r.draw_frames(poses, want_depth=True)
+                    for k in range(n):
+                        assert np.array_equal(fs[k], want[k][0]) and np.array_equal(ds[k].view(np.uint32), want[k][1].view(np.uint32)), (W, H, n, k)
+    finally:
+        r.close()
+        one.close()
+
+
+def test_retained_outputs_rewrite_only_what_changes():
+    """rast_set_retained_outputs: the caller redraws into the buffers of the previous draw (the reference's spin loop does) and the
+    library resets only the part of the previously covered rectangle that the new frame leaves.  Every draw must leave the
+    buffers byte-identical to a draw without the promise -- moving, shrinking, vanishing and full-screen models, fewer frames
+    than before, colour only, other buffers, a band."""
+    from rasteriser_b200 import api
+    scene, lights = S.scene("suzanne"), S.lights("threepoint")
+    W, H = 641, 483
+    def seq(k0):
+        p = [api.Args(W, H, tait_bryan_angles=(0.1 * k, 0.9 * (k + k0), 0.0), displacement=(0.5 * ((k + k0) % 3) - 0.5, 0.2 * k0, 0.0), scale=1.0 - 0.15 * k0) for k in range(4)]
+        p.append(api.Args(W, H, displacement=(40.0, 0.0, 0.0)) if k0 % 2 else api.Args(W, H, scale=6.0, displacement=(0.0, 0.0, 1.0)))  # nothing on screen / covered edge to edge
+        p.append(api.Args(W, H, scale=0.3, displacement=(-0.8 + 0.4 * k0, 0.5, 0.0)))
+        return p
+    plain = make_renderer(scene, lights)
+    r = make_renderer(scene, lights)
+    try:
+        r.set_retained_outputs(True)
+        fs, ds = np.full((6, 3, H, W), 0xAB, np.uint8), np.full((6, H, W), -7.0, np.float32)
+        moved = 0
+        for k0 in range(4):
+            b0 = r.d2h_bytes()
+            r.draw_frames(seq(k0), fs, ds)
+            moved = r.d2h_bytes() - b0
+            want_f, want_d = plain.draw_frames(seq(k0), want_depth=True)
+            assert np.array_equal(fs, want_f), "call %d" % k0
+            assert np.array_equal(ds.view(np.uint32), want_d.view(np.uint32)), "call %d" % k0
+        assert moved < 0.8 * fs.nbytes + ds.nbytes
+        # fewer frames than the buffers hold: the rest keeps the previous call's frames
+        r.draw_frames(seq(5)[:3], fs[:3], ds[:3])
+        want_f3, want_d3 = plain.draw_frames(seq(5)[:3], want_depth=True)
+        assert np.array_equal(fs[:3], want_f3) and np.array_equal(fs[3:], want_f[3:]) and np.array_equal(ds[:3].view(np.uint32), want_d3.view(np.uint32))
+        r.draw_frames(seq(2), fs, ds)  # ... and all six again
+        want_f, want_d = plain.draw_frames(seq(2), want_depth=True)
+        assert np.array_equal(fs, want_f) and np.array_equal(ds.view(np.uint32), want_d.view(np.uint32))
+        # colour only into the same colour buffer is another pair of buffers: a full draw (garbage must disappear), then retained again
+        fs[:] = 0x5A
+        r.draw_frames(seq(1), fs, None)
+        assert np.array_equal(fs, plain.draw_frames(seq(1))[0])
+        r.draw_frames(seq(3), fs, None)
+        assert np.array_equal(fs, plain.draw_frames(seq(3))[0])
+        # single frames through rast_draw_frame into one reused pair of buffers (the reference's loop), then a band
+        f1, d1 = np.full((3, H, W), 0x33, np.uint8), np.full((H, W), 2.0, np.float32)
+        for a in seq(0) + seq(1):
+            r.draw_frame(a, f1, d1)
+            wf, wd = plain.draw_frame(a)
+            assert np.array_equal(f1, wf) and np.array_equal(d1.view(np.uint32), wd.view(np.uint32))
+        r.set_band(100, 333)
+        plain.set_band(100, 333)
+        fb, db = np.full((3, 233, W), 0x11, np.uint8), np.full((233, W), 9.0, np.float32)
+        for a in seq(2)[:3]:
+            r.draw_frame(a, fb, db)
+            wf, wd = plain.draw_frame(a)
+            assert np.array_equal(fb, wf) and np.array_equal(db.view(np.uint32), wd.view(np.uint32))
+        # switching the promise off: a full draw again
+        r.set_retained_outputs(False)
+        fb[:] = 0x77
+        r.draw_frame(seq(2)[0], fb, db)
+        assert np.array_equal(fb, plain.draw_frame(seq(2)[0])[0])
+    finally:
+        r.close()
+        plain.close()
+
+
 @pytest.mark.gpu
 def test_drop_in_draw_frame_sees_edits_and_new_scenes():
     """The reference re-reads its vectors on every call (headers/drawing.h:16-18).  The drop-in keeps the scene on the GPU

@@ -11,6 +11,8 @@ import torch.multiprocessing as mp
 
 from rasteriser_b200 import multi
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 def _free_port():
     s = socket.socket()
@@ -65,3 +67,25 @@ def test_partition_properties():
         for h in (1, 5, 1080, 4320):
             bands = [multi.band_of_rank(h, r, world) for r in range(world)]
             assert bands[0][0] == 0 and bands[-1][1] == h and all(bands[i][1] == bands[i + 1][0] for i in range(world - 1))
+
+
+def test_bind_host_to_gpu_splits_the_allowed_cpus():
+    """multi.bind_host_to_gpu without a GPU (no NVML here): every local rank gets its own contiguous share of the CPUs this
+    process may use; the shares do not overlap and the binding is really applied (child process: the test keeps its own mask)."""
+    import os
+    import subprocess
+    import sys
+    assert multi._cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    allowed = sorted(os.sched_getaffinity(0))
+    world = min(4, len(allowed))
+    code = ("import os, sys, json; sys.path.insert(0, %r); from rasteriser_b200 import multi; "
+            "info = multi.bind_host_to_gpu(int(sys.argv[1]), int(sys.argv[2])); print(json.dumps([sorted(os.sched_getaffinity(0)), info]))" % ROOT)
+    import json
+    seen = []
+    for rank in range(world):
+        out = subprocess.run([sys.executable, "-c", code, str(rank), str(world)], capture_output=True, text=True, check=True).stdout
+        cpus, info = json.loads(out.strip().splitlines()[-1])
+        assert cpus and set(cpus) <= set(allowed) and len(cpus) == max(1, len(allowed) // world)
+        assert not (set(cpus) & set(seen))
+        assert info["how"] != "unchanged"
+        seen += cpus
