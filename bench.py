@@ -328,6 +328,11 @@ def roofline_record(wl, workload, pass_ms, n_frames, P, visible_tris, step_ms, w
         traffic = k["dram_bytes_per_launch"] * frames_per_launch / k["frames_per_launch"]
         limiter = {key: k[key] for key in ("issue_active_pct", "l1tex_throughput_pct", "warp_instructions_per_launch", "lanes_per_instruction", "top_stall") if key in k}
         limiter["source"] = tr_file
+        if "warp_instructions_per_launch" in k and avg_ms > 0:
+            # the same launch against the SM's issue rate: warp instructions of the captured launch (scaled to this launch's frames) / live duration,
+            # over 148 SMs x 4 schedulers x 1 instruction per clock at the 1965 MHz the bench runs at -- the limit the exact-arithmetic passes sit on
+            instr = k["warp_instructions_per_launch"] * frames_per_launch / k["frames_per_launch"]
+            limiter["issue_slot_frac_live"] = instr / (avg_ms * 1e-3) / (148 * 4 * 1.965e9)
     rec = {"bound": "hbm", "kernel": kfull, "schedule": schedule, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
            "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms, "frames_per_launch": frames_per_launch, "pass_ms_per_step": pass_ms, "limiter": limiter,
            # every pass of a frame against the HBM roofline, two ways: SURVEY 8(d)'s frame total B (which counts a clear and a key write-back
