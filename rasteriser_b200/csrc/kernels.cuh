@@ -111,7 +111,9 @@ struct MaterialDev {          // material.h:11-25
 
 struct Scene {
     const float *pos;         // xyz [V]
-    const float *nrm;         // xyz [Nn]
+    const float *nrm;         // xyz [Nn] (k_vertex: coalesced)
+    const float4 *nrm4;       // the same normals padded to 16 bytes (x, y, z, 0): the shade pass of a huge mesh gathers three per pixel --
+                              // one 16-byte load each instead of three scattered 4-byte ones (k_pad_normals at upload)
     const float2 *uv;         // [Nuv]
     const int *vidx0, *vidx1, *vidx2; // vertex indices, SoA [T] (coalesced in the per-triangle pass)
     const int4 *tri_rec;      // [3T]: (v0,v1,v2,n0) (n1,n2,t0,t1) (t2,material,-,-): one 48-byte record per
@@ -1094,13 +1096,13 @@ RAST_HD Shaded shade_pixel(uint32_t tri, uint32_t x, uint32_t y, const Scene &sc
     } else if (PRE_NORMALS) {
         n0 = exact::ldg(cn + r0.w); n1 = exact::ldg(cn + r1.x); n2 = exact::ldg(cn + r1.y);
     } else {
-        const float *m0 = sc.nrm + 3 * (size_t)r0.w, *m1 = sc.nrm + 3 * (size_t)r1.x, *m2 = sc.nrm + 3 * (size_t)r1.y;
+        const float4 m0 = exact::ldg(sc.nrm4 + r0.w), m1 = exact::ldg(sc.nrm4 + r1.x), m2 = exact::ldg(sc.nrm4 + r1.y);
         float nm[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) nm[k] = exact::ldg(normal_m + k);
-        n0 = mat_vec(nm, exact::ldg(m0), exact::ldg(m0 + 1), exact::ldg(m0 + 2), 0.f);
-        n1 = mat_vec(nm, exact::ldg(m1), exact::ldg(m1 + 1), exact::ldg(m1 + 2), 0.f);
-        n2 = mat_vec(nm, exact::ldg(m2), exact::ldg(m2 + 1), exact::ldg(m2 + 2), 0.f);
+        n0 = mat_vec(nm, m0.x, m0.y, m0.z, 0.f);
+        n1 = mat_vec(nm, m1.x, m1.y, m1.z, 0.f);
+        n2 = mat_vec(nm, m2.x, m2.y, m2.z, 0.f);
     }
     const MaterialDev *mp = sc.mats + r2.y;
     const float4 mk = exact::ldg(reinterpret_cast<const float4 *>(mp));      // kd.rgb, has_texture
@@ -1783,6 +1785,12 @@ __global__ void k_resolve_materials(int4 *tri_rec, uint64_t n_tris, uint32_t n_m
     int4 r = tri_rec[3 * t + 2];
     r.y = (r.z < 0 || (uint32_t)r.z >= n_materials) ? (int)n_materials : r.z;
     tri_rec[3 * t + 2] = r;
+}
+
+// xyz normals -> (x, y, z, 0) at 16-byte stride for the shade pass (once per upload; entry n is the zero sentinel)
+__global__ void k_pad_normals(const float *__restrict__ nrm, float4 *__restrict__ nrm4, uint32_t n_with_sentinel) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_with_sentinel) nrm4[i] = make_float4(nrm[3 * (size_t)i], nrm[3 * (size_t)i + 1], nrm[3 * (size_t)i + 2], 0.f);
 }
 
 __global__ void k_extract_tri_ids(const unsigned long long *vis, uint32_t *ids, uint32_t n) {

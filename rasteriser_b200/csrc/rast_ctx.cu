@@ -132,7 +132,7 @@ struct rast_ctx {
 
     // scene
     rk::Scene scene{};
-    DeviceBuffer d_pos, d_nrm, d_uv, d_vidx, d_attr, d_mats, d_texels;
+    DeviceBuffer d_pos, d_nrm, d_nrm4, d_uv, d_vidx, d_attr, d_mats, d_texels;
     bool have_mesh = false;
     bool mesh_materials_dirty = false; // material indices in d_attr still have to be clamped against n_materials
     uint32_t n_materials = 0;
@@ -875,7 +875,7 @@ void rast_destroy(rast_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->front_stream) cudaStreamSynchronize(ctx->front_stream);
-    DeviceBuffer *dev[] = {&ctx->d_pos, &ctx->d_nrm, &ctx->d_uv, &ctx->d_vidx, &ctx->d_attr, &ctx->d_mats, &ctx->d_texels, &ctx->d_frames[0], &ctx->d_frames[1], &ctx->d_lights[0], &ctx->d_lights[1],
+    DeviceBuffer *dev[] = {&ctx->d_pos, &ctx->d_nrm, &ctx->d_nrm4, &ctx->d_uv, &ctx->d_vidx, &ctx->d_attr, &ctx->d_mats, &ctx->d_texels, &ctx->d_frames[0], &ctx->d_frames[1], &ctx->d_lights[0], &ctx->d_lights[1],
                            &ctx->d_rv[0], &ctx->d_rv[1], &ctx->d_cn[0], &ctx->d_cn[1], &ctx->d_tiles, &ctx->d_list, &ctx->d_items, &ctx->d_vis[0], &ctx->d_vis[1], &ctx->d_flags[0], &ctx->d_flags[1], &ctx->d_bbox[0], &ctx->d_bbox[1], &ctx->d_queue, &ctx->d_counters, &ctx->d_shade_cursor, &ctx->d_aux, &ctx->d_rgb[0], &ctx->d_rgb[1], &ctx->d_depth[0], &ctx->d_depth[1]};
     for (DeviceBuffer *b : dev) b->release();
 #if RAST_SHADE_PREP
@@ -932,6 +932,7 @@ int rast_upload_mesh(rast_ctx *ctx, const float *positions, uint32_t n_positions
     RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     RAST_CUDA(ctx, ctx->d_pos.reserve((size_t)n_positions * 12));
     RAST_CUDA(ctx, ctx->d_nrm.reserve(((size_t)n_normals + 1) * 12));
+    RAST_CUDA(ctx, ctx->d_nrm4.reserve(((size_t)n_normals + 1) * 16));
     RAST_CUDA(ctx, ctx->d_uv.reserve(((size_t)n_uvs + 1) * 8));
     RAST_CUDA(ctx, ctx->d_vidx.reserve((size_t)n_tris * 3 * 4));
     RAST_CUDA(ctx, ctx->d_attr.reserve((size_t)n_tris * 3 * 16));
@@ -943,6 +944,8 @@ int rast_upload_mesh(rast_ctx *ctx, const float *positions, uint32_t n_positions
     if (n_positions) RAST_CUDA(ctx, cudaMemcpyAsync(ctx->d_pos.p, positions, (size_t)n_positions * 12, cudaMemcpyHostToDevice, ctx->stream));
     if (n_normals) RAST_CUDA(ctx, cudaMemcpyAsync(ctx->d_nrm.p, normals, (size_t)n_normals * 12, cudaMemcpyHostToDevice, ctx->stream));
     if (n_uvs) RAST_CUDA(ctx, cudaMemcpyAsync(ctx->d_uv.p, uvs, (size_t)n_uvs * 8, cudaMemcpyHostToDevice, ctx->stream));
+    rk::k_pad_normals<<<grid_for((size_t)n_normals + 1, 256), 256, 0, ctx->stream>>>(ctx->d_nrm.as<float>(), ctx->d_nrm4.as<float4>(), n_normals + 1u);
+    ++ctx->launches;
     if (n_tris) {
         DeviceBuffer raw; // freed on return
         struct Release { DeviceBuffer &b; ~Release() { b.release(); } } release_raw{raw};
@@ -969,6 +972,7 @@ int rast_upload_mesh(rast_ctx *ctx, const float *positions, uint32_t n_positions
     rk::Scene &s = ctx->scene;
     s.pos = ctx->d_pos.as<float>();
     s.nrm = ctx->d_nrm.as<float>();
+    s.nrm4 = ctx->d_nrm4.as<float4>();
     s.uv = ctx->d_uv.as<float2>();
     s.vidx0 = ctx->d_vidx.as<int>();
     s.vidx1 = s.vidx0 + n_tris;

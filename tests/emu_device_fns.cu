@@ -113,8 +113,10 @@ extern "C" int emu_draw(const float *pos, uint32_t V, const float *nrm, uint32_t
     md[M].has_texture = 0; md[M].tex_w = md[M].tex_h = 0; md[M].texel_offset = 0;
     texels.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
 
+    std::vector<float4> nrm4((size_t)Nn + 1); // what k_pad_normals writes at upload
+    for (size_t i = 0; i <= (size_t)Nn; ++i) nrm4[i] = make_float4(nrm_s[3 * i], nrm_s[3 * i + 1], nrm_s[3 * i + 2], 0.f);
     Scene sc{};
-    sc.pos = pos; sc.nrm = nrm_s.data(); sc.uv = uv_s.data();
+    sc.pos = pos; sc.nrm = nrm_s.data(); sc.nrm4 = nrm4.data(); sc.uv = uv_s.data();
     sc.tri_rec = rec.data(); sc.mats = md.data(); sc.texels = texels.data();
     sc.V = V; sc.Nn = Nn + 1; sc.Nuv = Nuv + 1; sc.M = M + 1; sc.T = T;
 
