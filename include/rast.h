@@ -224,6 +224,14 @@ uint64_t rast_fnv1a64(const void *data, uint64_t bytes);
 /* pinned host memory for frame / depth buffers */
 void *rast_host_alloc(uint64_t bytes);
 void rast_host_free(void *p);
+/* Page-lock a buffer the caller already owns (the reference's CImg frame / depth buffers live for the whole run): host-buffer
+ * draws into pageable memory go through the driver's staging copies and are several times slower (a 640x480 frame: 0.49 ms per
+ * call pageable).  The buffer must be unregistered before it is freed.  Registering twice is not an error. */
+int rast_host_register(void *p, uint64_t bytes);
+int rast_host_unregister(void *p);
+/* 64-bit content hash at memory speed (not cryptographic): what the drop-in shims use to see that the scene arrays a caller
+ * passes on every draw_frame call are still the ones on the device. */
+uint64_t rast_hash64(const void *data, uint64_t bytes, uint64_t seed);
 
 #ifdef __cplusplus
 }

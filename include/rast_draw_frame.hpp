@@ -38,7 +38,7 @@ public:
     explicit Session(int device = 0) {
         if (rast_create(device, &ctx_) != RAST_OK) throw std::runtime_error(std::string("rast_create: ") + rast_last_error(nullptr));
     }
-    ~Session() { rast_destroy(ctx_); }
+    ~Session() { unpin_outputs(); rast_destroy(ctx_); }
     Session(const Session &) = delete;
     Session &operator=(const Session &) = delete;
     rast_ctx *ctx() const { return ctx_; }
@@ -69,6 +69,22 @@ public:
     // Extension (default off, the reference ignores Kd of a textured material: material.cpp:19-21): RAST_TEXTURE_MODULATE_KD makes the
     // texel modulate Kd.  Takes effect at the next upload.
     void set_texture_bits(int bits) { if (bits != texture_bits_) { texture_bits_ = bits; uploaded_ = false; } }
+
+    // Opt-in: page-lock the frame / depth buffers handed to draw_frame (rast_host_register) the first time they are seen -- draws into
+    // pageable memory go through the driver's staging copies and are several times slower.  The caller promises that the buffers
+    // outlive the Session or calls unpin_outputs() before freeing them (the reference's frame_buffer / depth_buffer live for the whole
+    // run: renderer.cpp:85-86).  retained_outputs(true) adds the promise of rast_set_retained_outputs (the spin loop's own behaviour).
+    void pin_outputs(bool on) { pin_outputs_ = on; if (!on) unpin_outputs(); }
+    void retained_outputs(bool on) { check(rast_set_retained_outputs(ctx_, on ? 1 : 0), "rast_set_retained_outputs"); }
+    void unpin_outputs() {
+        for (void *p : pinned_) rast_host_unregister(p);
+        pinned_.clear();
+    }
+    void note_output(void *p, size_t bytes) {
+        if (!pin_outputs_ || !p || !bytes) return;
+        for (void *q : pinned_) if (q == p) return;
+        if (rast_host_register(p, bytes) == RAST_OK) pinned_.push_back(p);
+    }
 
     // The caller promises that the scene arrays do not change between draws (no per-call content hash); invalidate() when they do.
     void assume_unchanged(bool on) { assume_unchanged_ = on; }
@@ -121,8 +137,9 @@ private:
     }
     rast_ctx *ctx_ = nullptr;
     Key key_{};
-    bool uploaded_ = false, assume_unchanged_ = false;
+    bool uploaded_ = false, assume_unchanged_ = false, pin_outputs_ = false;
     int texture_bits_ = 0;
+    std::vector<void *> pinned_;
 };
 
 template <class ArgsT> inline rast_args to_rast_args(const ArgsT &a) {
@@ -151,6 +168,8 @@ void draw_frame(Session &session, const Vec3s &model_vertices, const Faces &face
     rast_light *l = reinterpret_cast<rast_light *>(lights.data());
     session.check(rast_set_lights(session.ctx(), l, (uint32_t)lights.size()), "rast_set_lights");
     const rast_args a = to_rast_args(arguments);
+    session.note_output(frame_buffer->data(), (size_t)a.image_width * a.image_height * 3);
+    if (depth_buffer) session.note_output(depth_buffer->data(), (size_t)a.image_width * a.image_height * sizeof(float));
     session.check(rast_draw_frame(session.ctx(), &a, frame_buffer->data(), depth_buffer ? depth_buffer->data() : nullptr, l), "rast_draw_frame");
 }
 

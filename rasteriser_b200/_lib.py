@@ -67,6 +67,9 @@ SYMBOLS = {
     "rast_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "rast_set_retained_outputs": (C.c_int, [C.c_void_p, C.c_int]),
     "rast_last_schedule": (C.c_char_p, [C.c_void_p]),
+    "rast_host_register": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "rast_host_unregister": (C.c_int, [C.c_void_p]),
+    "rast_hash64": (C.c_uint64, [C.c_void_p, C.c_uint64, C.c_uint64]),
     "rast_get_pass_ms": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rast_launch_count": (C.c_uint64, [C.c_void_p]),
     "rast_d2h_bytes": (C.c_uint64, [C.c_void_p]),

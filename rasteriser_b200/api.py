@@ -256,6 +256,13 @@ class Renderer:
         txt = self._lib.rast_last_schedule(self._h).decode()
         return dict(kv.split("=", 1) for kv in txt.split(" ") if "=" in kv) if txt else {}
 
+    def pin_host(self, array):
+        """Page-lock a numpy output buffer the caller keeps alive (rast_host_register); unpin_host before freeing it."""
+        self._check(self._lib.rast_host_register(C.c_void_p(array.ctypes.data), array.nbytes), "rast_host_register")
+
+    def unpin_host(self, array):
+        self._lib.rast_host_unregister(C.c_void_p(array.ctypes.data))
+
     def set_retained_outputs(self, on):
         """The caller promises that the host buffers of a draw still hold what the previous host-buffer draw of this renderer wrote
         (the reference's spin loop reuses its buffers): only the changed rectangles are rewritten.  Same bytes in the buffers."""
@@ -305,15 +312,44 @@ CONTENT_KEY_MAX_BYTES = 64 << 20  # scenes up to this size are fingerprinted on 
 
 
 def _fingerprint(arrays):
-    """Content fingerprint of the scene arrays (shape, dtype and every byte): zlib.crc32 + adler32 run at GB/s, i.e.
-    microseconds on a Suzanne-sized scene."""
-    import zlib
+    """Content fingerprint of the scene arrays (shape, dtype and every byte): rast_hash64 runs at memory speed (Suzanne with
+    its 12 MB texture: about a millisecond; zlib.crc32 + adler32 took six)."""
+    lib = _lib.load()
     out = []
     for a in arrays:
         b = np.ascontiguousarray(a)
-        mv = memoryview(b).cast("B") if b.size else b""
-        out.append((b.shape, b.dtype.str, zlib.crc32(mv), zlib.adler32(mv)))
+        out.append((b.shape, b.dtype.str, int(lib.rast_hash64(b.ctypes.data if b.size else None, b.nbytes, len(out) + 1))))
     return tuple(out)
+
+
+# Output buffers the drop-in has page-locked (rast_host_register): draws into pageable memory are several times slower.  The
+# registry holds a reference to each array, so a registered buffer cannot be freed under the driver; the oldest entries are
+# unregistered when more than PINNED_OUTPUTS_MAX distinct buffers have been seen.
+_pinned_outputs = {}
+PINNED_OUTPUTS_MAX = 4
+
+
+def _pin_output(a):
+    if a is None or a.nbytes < (64 << 10):
+        return
+    key = (a.ctypes.data, a.nbytes)
+    if key in _pinned_outputs:
+        return
+    lib = _lib.load()
+    while len(_pinned_outputs) >= PINNED_OUTPUTS_MAX:
+        old_key = next(iter(_pinned_outputs))
+        lib.rast_host_unregister(C.c_void_p(old_key[0]))
+        del _pinned_outputs[old_key]
+    if lib.rast_host_register(C.c_void_p(a.ctypes.data), a.nbytes) == 0:
+        _pinned_outputs[key] = a
+
+
+def unpin_outputs():
+    """Unregister every output buffer draw_frame() has page-locked."""
+    lib = _lib.load()
+    for key in list(_pinned_outputs):
+        lib.rast_host_unregister(C.c_void_p(key[0]))
+    _pinned_outputs.clear()
 
 
 def _material_arrays(materials):
@@ -327,7 +363,7 @@ def _material_arrays(materials):
 
 
 def invalidate():
-    """Forget the scene cached by draw_frame(): the next call uploads again."""
+    """Forget the scene cached by draw_frame(): the next call uploads again.  (Page-locked output buffers stay: unpin_outputs().)"""
     for r in _cached.values():
         r.close()
     _cached.clear()
@@ -370,6 +406,8 @@ def draw_frame(model_vertices, faces, model_vertnormals, vertuvs, lights, materi
         r.upload_materials(materials)
         _cached[key if key is not None else (device, "uncached")] = r
     r.set_lights(np.asarray(lights, np.float32)[:, :7])
+    _pin_output(frame_buffer)
+    _pin_output(depth_buffer)
     r.draw_frame(a, frame_buffer, depth_buffer, want_depth=depth_buffer is not None)
     if isinstance(lights, np.ndarray) and lights.ndim == 2 and lights.shape[1] >= 10:
         lights[:, 7:10] = r.light_trans_dirs()

@@ -31,6 +31,7 @@ thread_local std::string g_create_error;
 constexpr uint32_t MAX_BATCH = 32;                 // frames in flight through one launch sequence (<= 256: 8-bit frame tag)
 constexpr size_t BATCH_BYTES_BUDGET = 6ull << 30;  // per-batch device scratch budget
 constexpr unsigned long long TILE_MODE_OVERDRAW = 8; // queued bbox area per pixel above which the next call bins by screen tile
+constexpr size_t SPARSE_MIN_FRAME_BYTES = 4u << 20; // host-buffer draws: frames smaller than this are copied whole (RAST_SPARSE_MIN_BYTES)
 constexpr uint32_t QUEUE_MIN = 1u << 23;           // work items (8 B each); grows on demand when a frame overflows it
 
 struct DeviceBuffer {
@@ -179,6 +180,8 @@ struct rast_ctx {
     PinnedBuffer h_frames, h_lights, h_status, h_bbox[2];
     DeviceBuffer d_bbox[2];
     bool sparse_copy = true;     // host-buffer draws copy only each frame's covered rectangle back (RAST_SPARSE_COPY=0: whole frames)
+    bool sparse_now = true;      // this call: sparse_copy and frames big enough for it to pay (sparse_min_bytes)
+    size_t sparse_min_bytes = SPARSE_MIN_FRAME_BYTES; // RAST_SPARSE_MIN_BYTES
     // rast_set_retained_outputs: the caller promises that the host buffers of a draw still hold what this context's previous
     // host-buffer draw wrote there.  `retained` remembers that previous draw (buffers, geometry, one rectangle per frame: what
     // is NOT the cleared background); finish_batch then resets only the part of the old rectangle the new one does not cover.
@@ -488,7 +491,7 @@ int finish_batch(rast_ctx *ctx, const PendingBatch &b, const rk::View &vw, uint8
     const size_t P = vw.band_pixels;
     const uint32_t W = vw.W, rows = vw.y1 - vw.y0;
     cudaStream_t cs = ctx->copy_stream;
-    if (!ctx->sparse_copy) {
+    if (!ctx->sparse_now) {
         RAST_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_done[b.slot], 0));
         if (frames) RAST_CUDA(ctx, cudaMemcpyAsync(frames + (size_t)b.first * 3 * P, b.rgb_dev, (size_t)b.count * 3 * P, cudaMemcpyDeviceToHost, cs));
         if (depths) RAST_CUDA(ctx, cudaMemcpyAsync(depths + (size_t)b.first * P, b.depth_dev, (size_t)b.count * P * 4, cudaMemcpyDeviceToHost, cs));
@@ -713,10 +716,13 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
 
     if (ctx->profiling) memset(ctx->pass_ms, 0, sizeof ctx->pass_ms);
     ctx->call_frames = n;
+    // Small frames go back whole: the sparse copy waits on the host for the frame's covered rectangle, issues four 2-D copies and wakes the
+    // fill threads -- more than the 40 us a 2 MB frame needs over PCIe (640x480 into page-locked buffers: 181 us per call sparse)
+    ctx->sparse_now = ctx->sparse_copy && (size_t)vw.band_pixels * ((frames ? 3u : 0u) + (depths ? 4u : 0u)) >= ctx->sparse_min_bytes;
     if (!device_ptrs) {
         // retained outputs: the promise covers exactly the buffers of the previous host-buffer draw, same geometry, and only frames that draw wrote
         rast_ctx::Retained &rt = ctx->retained;
-        ctx->retained_now = ctx->retained_outputs && ctx->sparse_copy && rt.valid && rt.frames == frames && rt.depths == depths && rt.W == vw.W &&
+        ctx->retained_now = ctx->retained_outputs && ctx->sparse_now && rt.valid && rt.frames == frames && rt.depths == depths && rt.W == vw.W &&
                             rt.rows == vw.y1 - vw.y0 && rt.y0 == vw.y0 && n <= rt.rects.size();
         if (!ctx->retained_now) rt.rects.clear();
         rt.valid = false; // until this call has completed
@@ -749,7 +755,7 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
         // the last frame of the call keeps its visibility keys for rast_read_triangle_ids / rast_get_stats
         const uint32_t keep_frame = (ctx->keep_visibility && first + count == n) ? count - 1 : 0xFFFFFFFFu;
         uint32_t *bbox_dev = nullptr;
-        if (!device_ptrs && ctx->sparse_copy) {
+        if (!device_ptrs && ctx->sparse_now) {
             RAST_CUDA(ctx, ctx->d_bbox[slot].reserve((size_t)nb * 16));
             RAST_CUDA(ctx, ctx->h_bbox[slot].reserve((size_t)nb * 16));
             bbox_dev = ctx->d_bbox[slot].as<uint32_t>();
@@ -785,7 +791,7 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
         RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->copied_pending[0] = ctx->copied_pending[1] = false;
         ctx->last_queue_count = ctx->h_status.as<unsigned long long>()[0];
-        ctx->retained.valid = ctx->retained_outputs && ctx->sparse_copy; // (whole-frame copies keep no rectangles)
+        ctx->retained.valid = ctx->retained_outputs && ctx->sparse_now; // (whole-frame copies keep no rectangles)
         ctx->retained_now = false;
     }
     return RAST_OK;
@@ -852,6 +858,7 @@ int rast_create(int device, rast_ctx **out) {
     }
     ctx->stream = ctx->own_stream;
     if (const char *e = getenv("RAST_SPARSE_COPY")) ctx->sparse_copy = atoi(e) != 0;
+    if (const char *e = getenv("RAST_SPARSE_MIN_BYTES")) ctx->sparse_min_bytes = (size_t)atoll(e);
     if (const char *e = getenv("RAST_SETUP_PIPE")) ctx->setup_pipe = atoi(e) != 0;
     if (const char *e = getenv("RAST_SHADE_WT_MIN_TILES")) ctx->shade_wt_min_tiles = (uint32_t)atoll(e);
     if (const char *e = getenv("RAST_OVERLAP")) ctx->overlap = atoi(e) != 0;
@@ -1290,5 +1297,38 @@ void *rast_host_alloc(uint64_t bytes) {
 }
 
 void rast_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int rast_host_register(void *p, uint64_t bytes) {
+    if (!p || !bytes) return RAST_EINVAL;
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return RAST_OK; }
+    return e == cudaSuccess ? RAST_OK : RAST_ECUDA;
+}
+
+int rast_host_unregister(void *p) {
+    if (!p) return RAST_EINVAL;
+    const cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) cudaGetLastError();
+    return e == cudaSuccess ? RAST_OK : RAST_ECUDA;
+}
+
+uint64_t rast_hash64(const void *data, uint64_t bytes, uint64_t seed) {
+    // multiply-xorshift over 8-byte words in four independent lanes: runs at memory speed (the same function as
+    // include/rast_draw_frame.hpp's Session uses for its per-call scene fingerprint)
+    const unsigned char *b = static_cast<const unsigned char *>(data);
+    uint64_t l[4] = {seed ^ 0x9E3779B97F4A7C15ull, seed ^ 0xC2B2AE3D27D4EB4Full, seed ^ 0x165667B19E3779F9ull, seed ^ 0x27D4EB2F165667C5ull};
+    uint64_t i = 0;
+    for (; i + 32 <= bytes; i += 32) {
+        uint64_t w[4];
+        memcpy(w, b + i, 32);
+        for (int k = 0; k < 4; ++k) { l[k] = (l[k] ^ w[k]) * 0x100000001B3ull; l[k] ^= l[k] >> 29; }
+    }
+    uint64_t tail[4] = {0, 0, 0, 0};
+    if (i < bytes) memcpy(tail, b + i, bytes - i);
+    for (int k = 0; k < 4; ++k) { l[k] = (l[k] ^ tail[k]) * 0x100000001B3ull; l[k] ^= l[k] >> 29; }
+    uint64_t out = bytes;
+    for (int k = 0; k < 4; ++k) { out = (out ^ l[k]) * 0xFF51AFD7ED558CCDull; out ^= out >> 33; }
+    return out;
+}
 
 } // extern "C"

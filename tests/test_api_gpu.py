@@ -115,6 +115,7 @@ def test_sparse_host_copy_delivers_the_same_bytes(monkeypatch):
     poses.append(api.Args(641, 483, displacement=(40.0, 0.0, 0.0)))             # nothing on screen
     poses.append(api.Args(641, 483, scale=6.0, displacement=(0.0, 0.0, 1.0)))    # camera inside the model: covered edge to edge
     results = {}
+    monkeypatch.setenv("RAST_SPARSE_MIN_BYTES", "0")  # (frames below 4 MB are copied whole by default)
     for sparse in ("0", "1"):
         monkeypatch.setenv("RAST_SPARSE_COPY", sparse)
         r = make_renderer(scene, lights)
@@ -168,12 +169,49 @@ def test_kept_visibility_slot_is_cleared_at_any_alignment():
         one.close()
 
 
-def test_retained_outputs_rewrite_only_what_changes():
+def test_page_locked_caller_buffers_and_the_drop_in_registry():
+    """rast_host_register on buffers the caller owns: same bytes as a draw into pageable memory, registering twice is fine;
+    the drop-in draw_frame page-locks the buffers it is handed, keeps at most PINNED_OUTPUTS_MAX of them and releases them
+    in unpin_outputs()."""
+    from rasteriser_b200 import api
+    scene, lights = S.scene("suzanne"), S.lights("threepoint")
+    r = make_renderer(scene, lights)
+    try:
+        a = api.Args(320, 240, tait_bryan_angles=(0.1, 0.6, 0.0))
+        want_f, want_d = r.draw_frame(a)
+        f, d = np.full((3, 240, 320), 0x77, np.uint8), np.full((240, 320), 3.0, np.float32)
+        r.pin_host(f); r.pin_host(d); r.pin_host(f)
+        for _ in range(3):
+            r.draw_frame(a, f, d)
+            assert np.array_equal(f, want_f) and np.array_equal(d.view(np.uint32), want_d.view(np.uint32))
+        r.unpin_host(f); r.unpin_host(d)
+        b0 = r.d2h_bytes()
+        r.draw_frame(a, f, d)
+        assert np.array_equal(f, want_f)
+        assert r.d2h_bytes() - b0 == 320 * 240 * 7  # a frame this small comes back whole (no rectangle, no host-side fill)
+    finally:
+        r.close()
+    import orc
+    l10 = orc.lights_array(lights)
+    try:
+        for k in range(api.PINNED_OUTPUTS_MAX + 3):
+            fb, db = np.empty((3, 240, 320), np.uint8), np.empty((240, 320), np.float32)
+            api.draw_frame(scene.positions, scene.tris, scene.normals, scene.uvs, l10, scene.materials, a, fb, db)
+            assert np.array_equal(fb, want_f) and np.array_equal(db.view(np.uint32), want_d.view(np.uint32))
+            assert len(api._pinned_outputs) <= api.PINNED_OUTPUTS_MAX
+    finally:
+        api.invalidate()
+        api.unpin_outputs()
+    assert not api._pinned_outputs
+
+
+def test_retained_outputs_rewrite_only_what_changes(monkeypatch):
     """rast_set_retained_outputs: the caller redraws into the buffers of the previous draw (the reference's spin loop does) and the
     library resets only the part of the previously covered rectangle that the new frame leaves.  Every draw must leave the
     buffers byte-identical to a draw without the promise -- moving, shrinking, vanishing and full-screen models, fewer frames
     than before, colour only, other buffers, a band."""
     from rasteriser_b200 import api
+    monkeypatch.setenv("RAST_SPARSE_MIN_BYTES", "0")  # (frames below 4 MB are copied whole by default: nothing would be retained)
     scene, lights = S.scene("suzanne"), S.lights("threepoint")
     W, H = 641, 483
     def seq(k0):

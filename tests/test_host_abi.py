@@ -122,3 +122,27 @@ def test_scene_fingerprint_sees_in_place_edits():
     assert k0 == api._fingerprint([a.copy() for a in arrays])  # same content at other addresses: same scene
     arrays[0][17, 1] = np.nextafter(arrays[0][17, 1], np.float32(9))
     assert api._fingerprint(arrays) != k0
+
+
+def test_hash64_sees_every_byte_and_needs_no_gpu():
+    """rast_hash64 (the drop-in's scene fingerprint) is a host function: equal buffers hash equal, any single-byte change, a
+    changed length or a changed seed changes the hash -- for sizes around the 32-byte block and for an empty buffer."""
+    import ctypes as C
+    import numpy as np
+    from rasteriser_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 7, 31, 32, 33, 64, 1000, 4099):
+        a = rng.integers(0, 256, n, dtype=np.uint8)
+        h = lib.rast_hash64(a.ctypes.data if n else None, n, 1)
+        c = a.copy()  # (kept alive across the call)
+        assert h == lib.rast_hash64(c.ctypes.data if n else None, n, 1)
+        assert h != lib.rast_hash64(a.ctypes.data if n else None, n, 2)
+        for i in range(0, n, max(1, n // 13)):
+            b = a.copy()
+            b[i] ^= 0x40
+            assert lib.rast_hash64(b.ctypes.data, n, 1) != h, (n, i)
+        if n:
+            assert lib.rast_hash64(a.ctypes.data, n - 1, 1) != h
+    z = np.zeros(64, np.uint8)
+    assert lib.rast_hash64(z.ctypes.data, 32, 1) != lib.rast_hash64(z.ctypes.data, 64, 1)  # zero padding is not invisible
