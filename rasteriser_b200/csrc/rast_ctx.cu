@@ -1300,6 +1300,9 @@ void rast_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 int rast_host_register(void *p, uint64_t bytes) {
     if (!p || !bytes) return RAST_EINVAL;
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost) return RAST_OK; // already page-locked
+    cudaGetLastError();
     const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
     if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return RAST_OK; }
     return e == cudaSuccess ? RAST_OK : RAST_ECUDA;
