@@ -175,13 +175,14 @@ int rast_draw_frames(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
 int rast_sync(rast_ctx *ctx);
 
 /* Retained outputs (off by default).  The reference's spin loop redraws into the SAME frame / depth buffers every frame
- * (renderer.cpp:105-111).  With this switch on the caller promises that the host buffers handed to rast_draw_frame(s) still
- * hold, unmodified, what this context's previous host-buffer draw wrote into them (same pointers, same image size and band, at
- * most as many frames).  The library then rewrites only what changes: the newly covered rectangle of each frame is copied from
+ * (renderer.cpp:105-111).  With this switch on the caller promises that the host buffers handed to rast_draw_frame(s) are the
+ * ones this context's previous host-buffer draw wrote (same pointers, same image size and band, at most as many frames) and
+ * that OUTSIDE the rectangle that draw covered they still hold the cleared values -- true when they were left alone, and also
+ * when the caller cleared them in between as renderer.cpp:107-108 does.  The library then rewrites only what changes: the newly covered rectangle of each frame is copied from
  * the device and the part of the previously covered rectangle outside it is reset to the cleared values (0 / 1.0f), instead of
  * rewriting the whole background of every frame on every call.  The buffers end up byte-identical to a draw without the
  * promise; a call with other buffers, another size, or the first call after switching it on is a normal full draw.  Breaking
- * the promise (buffers modified in between) leaves the caller's modifications in the background. */
+ * the promise (something else written outside that rectangle in between) leaves it in the background. */
 int rast_set_retained_outputs(rast_ctx *ctx, int enabled);
 
 /* ---- auxiliary outputs -------------------------------------------------------------------- */

@@ -44,7 +44,7 @@ static uint64_t fnv(const void *p, size_t n) {
 }
 
 int main(int argc, char **argv) {
-    if (argc < 6) { std::fprintf(stderr, "usage: %s model.obj materials_dir/ lights.csv width height\n", argv[0]); return 2; }
+    if (argc < 6) { std::fprintf(stderr, "usage: %s model.obj materials_dir/ lights.csv width height [opt-ins]\n", argv[0]); return 2; }
     Args arguments(0, nullptr);
     arguments.obj_file = argv[1];
     arguments.materials_directory = argv[2];
@@ -63,6 +63,8 @@ int main(int argc, char **argv) {
 
     try {
         rast::Session gpu(0);
+        const bool opt_ins = argc > 6; // any 6th argument: the two optional lines of INTEGRATION.md section 3
+        if (opt_ins) { gpu.pin_outputs(true); gpu.retained_outputs(true); }
         std::vector<RastMaterialView> mats(materials.begin(), materials.end());
         cimg_library::CImg<unsigned char> frame_buffer(arguments.image_width, arguments.image_height, 1, 3, 0); // renderer.cpp:85
         cimg_library::CImg<float> depth_buffer(arguments.image_width, arguments.image_height, 1, 1, 1.f);       // renderer.cpp:86
@@ -73,6 +75,11 @@ int main(int argc, char **argv) {
         frame_buffer.fill(0); depth_buffer.fill(1.f);
         rast::draw_frame(gpu, model_vertices, faces, model_vertnormals, vertuvs, lights, mats, arguments, &frame_buffer, &depth_buffer);
         std::printf("EDITED %016llx %016llx\n", (unsigned long long)fnv(frame_buffer.data(), frame_buffer.size()),
+                    (unsigned long long)fnv(depth_buffer.data(), depth_buffer.size() * sizeof(float)));
+        for (glm::vec3 &v : model_vertices) v.x = v.x * 2.0f; // back to the original (exact in binary32)
+        if (!opt_ins) { frame_buffer.fill(0); depth_buffer.fill(1.f); } // with retained outputs the buffers keep the previous draw: the library resets what it must
+        rast::draw_frame(gpu, model_vertices, faces, model_vertnormals, vertuvs, lights, mats, arguments, &frame_buffer, &depth_buffer);
+        std::printf("AGAIN %016llx %016llx\n", (unsigned long long)fnv(frame_buffer.data(), frame_buffer.size()),
                     (unsigned long long)fnv(depth_buffer.data(), depth_buffer.size() * sizeof(float)));
     } catch (const std::exception &e) {
         std::fprintf(stderr, "shim_real_headers: %s\n", e.what());

@@ -51,3 +51,22 @@ def test_reference_types_through_the_shim_reproduce_the_reference_hashes(tmp_pat
     assert res[0][3] == "968" and res[0][4] == "3"
     assert abs(float(res[0][5])) > 0.1  # lights[0].trans_dir was written back (geometry.cpp:126)
     assert res[1][0] == "EDITED" and res[1][1] != res[0][1] and res[1][2] != res[0][2]  # vertices edited in place were re-read
+
+
+@pytest.mark.gpu
+def test_shim_opt_ins_page_locked_and_retained_cimg_buffers(tmp_path):
+    """The two optional lines of INTEGRATION.md section 3 on the reference's own CImg buffers at 1920x1080 (large enough for the sparse
+    copy): Session::pin_outputs page-locks them, Session::retained_outputs makes the third draw -- into buffers that still hold the
+    second frame, not cleared by the caller -- rewrite only what changed.  First and third frame must carry the reference's hashes."""
+    exe = orc.build_shim_real_headers()
+    if not exe:
+        pytest.skip("oracle/_ref/shim_real_headers was not built (needs /root/reference at build time)")
+    case = [c for c in S.golden_cases() if c["name"] == "suzanne_1920x1080"][0]
+    d = _scene_dir(tmp_path)
+    for extra in ([], ["opt-ins"]):
+        p = subprocess.run([exe, d + "Suzanne.obj", d, d + "threepoint.csv", "1920", "1080"] + extra, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr
+        res = {l.split()[0]: l.split()[1:] for l in p.stdout.splitlines() if l.startswith(("RESULT", "EDITED", "AGAIN"))}
+        assert res["RESULT"][0] == case["frame_fnv"] and res["RESULT"][1] == case["depth_fnv"], (extra, res)
+        assert res["EDITED"][0] != res["RESULT"][0]
+        assert res["AGAIN"][:2] == res["RESULT"][:2], (extra, res)
