@@ -177,22 +177,26 @@ struct rast_ctx {
     bool keep_visibility = false; // rast_set_keep_visibility: the last frame of a call keeps its keys (rast_read_triangle_ids / rast_get_stats)
     int last_ps = 0; // pipeline slot of the most recent batch (rast_read_triangle_ids / rast_get_stats)
     DeviceBuffer d_rgb[2], d_depth[2];
-    PinnedBuffer h_frames, h_lights, h_status, h_bbox[2];
-    DeviceBuffer d_bbox[2];
+    PinnedBuffer h_frames, h_lights, h_status, h_spans[2];
+    DeviceBuffer d_spans[2];
     bool sparse_copy = true;     // host-buffer draws copy only each frame's covered rectangle back (RAST_SPARSE_COPY=0: whole frames)
     bool sparse_now = true;      // this call: sparse_copy and frames big enough for it to pay (sparse_min_bytes)
     size_t sparse_min_bytes = SPARSE_MIN_FRAME_BYTES; // RAST_SPARSE_MIN_BYTES
     // rast_set_retained_outputs: the caller promises that the host buffers of a draw still hold what this context's previous
     // host-buffer draw wrote there.  `retained` remembers that previous draw (buffers, geometry, one rectangle per frame: what
     // is NOT the cleared background); finish_batch then resets only the part of the old rectangle the new one does not cover.
-    struct HostRect { uint32_t x0, y0, x1, y1; bool empty; };
     struct Retained {
         const uint8_t *frames = nullptr;
         const float *depths = nullptr;
         uint32_t W = 0, rows = 0, y0 = 0;
-        std::vector<HostRect> rects; // per frame of the buffers
+        std::vector<uint32_t> ext; // per frame and row of the buffers: [xa, xb) = what is not the cleared background
         bool valid = false;
     } retained;
+    // zero-copy delivery (k_deliver): this call's host buffers as the device sees them, or nullptr (copy-engine path)
+    uint8_t *frames_mapped = nullptr;
+    float *depths_mapped = nullptr;
+    bool deliver_now = false;
+    bool deliver_enabled = true; // RAST_DELIVER=0: always the copy engine
     bool retained_outputs = false; // the promise (off by default)
     bool retained_now = false;     // this call: the promise holds for these buffers
     unsigned host_threads = 0;   // helpers of the background fill (RAST_HOST_THREADS = total threads; default min(4, hardware / 2))
@@ -293,9 +297,9 @@ uint32_t batch_capacity(const rast_ctx *ctx, const rk::View &vw) {
 // ps = pipeline slot (which copy of rv / cn / vis); two_streams: the shade pass goes to ctx->front_stream, ordered after this
 // batch's raster pass by an event.  *done_stream receives the stream on which the batch's last kernel was launched.
 int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count, uint8_t *rgb_dev, float *depth_dev, uint32_t keep_frame,
-                 uint32_t *bbox_dev, int ps, bool two_streams, cudaStream_t *done_stream) {
+                 uint32_t *spans_dev, int ps, bool two_streams, cudaStream_t *done_stream) {
     rk::Batch bt;
-    bt.bbox = bbox_dev;
+    bt.spans = spans_dev;
     bt.frames = ctx->d_frames[ctx->cs].as<rk::FrameParams>() + first;
     bt.n_frames = count;
     bt.rv = ctx->d_rv[ps].as<float4>();
@@ -399,7 +403,7 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
         st = ctx->stream;
         RAST_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_raster[ps], 0));
     }
-    if (bbox_dev) cudaMemsetAsync(bbox_dev, 0xFF, (size_t)count * 16, st);
+    if (spans_dev) cudaMemsetAsync(spans_dev, 0xFF, (size_t)count * (vw.y1 - vw.y0) * 8, st);
     if (vw.band_pixels) {
         const rk::LightDev *lights = ctx->d_lights[ctx->cs].as<rk::LightDev>();
         const uint32_t rows = vw.y1 - vw.y0;
@@ -500,60 +504,117 @@ int finish_batch(rast_ctx *ctx, const PendingBatch &b, const rk::View &vw, uint8
         ctx->copied_pending[b.slot] = true;
         return RAST_OK;
     }
-    RAST_CUDA(ctx, cudaEventSynchronize(ctx->ev_done[b.slot])); // kernels done, rectangles in h_bbox[slot]
-    const uint32_t *bb = ctx->h_bbox[b.slot].as<uint32_t>();
-    struct Rect { uint32_t x0, y0, x1, y1; bool empty, whole; };
-    std::vector<Rect> rects(b.count);
-    // retained outputs: what each of these frames' buffers held outside the cleared background before this call
-    std::vector<rast_ctx::HostRect> old_rects;
-    if (ctx->retained_now) old_rects.assign(ctx->retained.rects.begin() + b.first, ctx->retained.rects.begin() + b.first + b.count);
-    for (uint32_t i = 0; i < b.count; ++i) {
-        Rect &r = rects[i];
-        r.empty = bb[4 * i] == 0xFFFFFFFFu;
-        r.whole = false;
-        if (r.empty) continue;
-        r.x0 = bb[4 * i] & ~63u;                                  // 64-pixel columns: no cache line is shared between
-        r.x1 = std::min(W - 1u, (W - 1u - bb[4 * i + 2]) | 63u);  // the copy engine and the filling threads
-        r.y0 = bb[4 * i + 1];
-        r.y1 = rows - 1u - bb[4 * i + 3];
-        r.whole = (uint64_t)(r.x1 - r.x0 + 1u) * (r.y1 - r.y0 + 1u) * 4u > (uint64_t)P * 3u; // > 75 %: one contiguous copy is cheaper
-    }
-    if (ctx->retained_outputs) { // remember what these buffers will hold (for the next call that keeps the promise)
-        if (ctx->retained.rects.size() < (size_t)b.first + b.count) ctx->retained.rects.resize((size_t)b.first + b.count, rast_ctx::HostRect{0u, 0u, W - 1u, rows - 1u, false});
+    RAST_CUDA(ctx, cudaEventSynchronize(ctx->ev_done[b.slot])); // kernels done, row spans in h_spans[slot]
+    const uint32_t *sp = ctx->h_spans[b.slot].as<uint32_t>();
+    constexpr uint32_t S = rk::BBOX_STRIPS;
+    const uint32_t bpp = (frames ? 3u : 0u) + (depths ? 4u : 0u);
+    // ext[(i * rows + y) * 2 .. +1] = [xa, xb): the part of row y of frame i that is DELIVERED from the device (k_deliver: the row's span;
+    // copy engine: the strip rectangle the row lies in); everything else of the row is background and written by the host.  Widened
+    // to 64-pixel columns, so that no cache line is shared between the two writers.
+    std::vector<uint32_t> ext((size_t)b.count * rows * 2, 0u);
+    auto span_of = [&](uint32_t i, uint32_t y, uint32_t &xa, uint32_t &xb) {
+        const uint32_t *q = sp + ((size_t)i * rows + y) * 2;
+        if (q[0] == 0xFFFFFFFFu) { xa = xb = 0u; return; }
+        xa = q[0] & ~63u;
+        xb = std::min(W, ((W - 1u - q[1]) | 63u) + 1u);
+    };
+    struct Rect { uint32_t x0, y0, x1, y1; bool empty; };
+    std::vector<Rect> rects;               // copy-engine path: one rectangle per (frame, strip of tile rows)
+    std::vector<uint8_t> whole(b.count, 0); // copy-engine path: the rectangles cover more than 75 % of the frame -- one contiguous copy is cheaper
+    if (ctx->deliver_now) {
+        unsigned long long px = 0;
+        for (uint32_t i = 0; i < b.count; ++i)
+            for (uint32_t y = 0; y < rows; ++y) {
+                uint32_t xa, xb;
+                span_of(i, y, xa, xb);
+                ext[((size_t)i * rows + y) * 2] = xa; ext[((size_t)i * rows + y) * 2 + 1] = xb;
+                px += xb - xa;
+            }
+        ctx->d2h_bytes += px * bpp; // (k_deliver for this batch was queued behind its shade pass when the batch was launched)
+    } else {
+        rects.assign((size_t)b.count * S, Rect{0u, 0u, 0u, 0u, true});
+        const uint32_t tiles_y = rk::flag_tiles_y(vw);
         for (uint32_t i = 0; i < b.count; ++i) {
-            const Rect &r = rects[i];
-            ctx->retained.rects[b.first + i] = r.empty ? rast_ctx::HostRect{0u, 0u, 0u, 0u, true} : (r.whole ? rast_ctx::HostRect{0u, 0u, W - 1u, rows - 1u, false} : rast_ctx::HostRect{r.x0, r.y0, r.x1, r.y1, false});
+            for (uint32_t y = 0; y < rows; ++y) {
+                uint32_t xa, xb;
+                span_of(i, y, xa, xb);
+                if (xa == xb) continue;
+                Rect &r = rects[(size_t)i * S + rk::bbox_strip_of_tile_row(y / rk::SHADE_TILE_H, tiles_y)];
+                if (r.empty) r = Rect{xa, y, xb - 1u, y, false};
+                else { r.x0 = std::min(r.x0, xa); r.x1 = std::max(r.x1, xb - 1u); r.y1 = y; }
+            }
+            uint64_t area = 0;
+            for (uint32_t k = 0; k < S; ++k) {
+                const Rect &r = rects[(size_t)i * S + k];
+                if (!r.empty) area += (uint64_t)(r.x1 - r.x0 + 1u) * (r.y1 - r.y0 + 1u);
+            }
+            whole[i] = area * 4u > (uint64_t)P * 3u;
+            for (uint32_t k = 0; k < S; ++k) {
+                const Rect &r = rects[(size_t)i * S + k];
+                if (whole[i]) continue;
+                if (!r.empty)
+                    for (uint32_t y = r.y0; y <= r.y1; ++y) { ext[((size_t)i * rows + y) * 2] = r.x0; ext[((size_t)i * rows + y) * 2 + 1] = r.x1 + 1u; }
+            }
+            if (whole[i])
+                for (uint32_t y = 0; y < rows; ++y) { ext[((size_t)i * rows + y) * 2] = 0u; ext[((size_t)i * rows + y) * 2 + 1] = W; }
         }
     }
-    for (uint32_t i = 0; i < b.count; ++i) {
-        const Rect &r = rects[i];
-        if (r.empty) continue;
+    // retained outputs: what each of these frames' buffers held outside the cleared background before this call
+    std::vector<uint32_t> old_ext;
+    if (ctx->retained_now) old_ext.assign(ctx->retained.ext.begin() + (size_t)b.first * rows * 2, ctx->retained.ext.begin() + ((size_t)b.first + b.count) * rows * 2);
+    if (ctx->retained_outputs) { // remember what these buffers will hold (for the next call that keeps the promise)
+        std::vector<uint32_t> &keep = ctx->retained.ext;
+        if (keep.size() < ((size_t)b.first + b.count) * rows * 2) keep.resize(((size_t)b.first + b.count) * rows * 2, 0u);
+        std::copy(ext.begin(), ext.end(), keep.begin() + (size_t)b.first * rows * 2);
+    }
+    // copy-engine path: the three colour planes of a rectangle are ONE 3-D copy (planes are P bytes apart), the depth plane a 2-D copy
+    std::atomic<int> copy_error{(int)cudaSuccess};
+    std::atomic<unsigned long long> copied{0};
+    auto issue_copies = [&](uint32_t i) {
         const size_t f = (size_t)b.first + i;
-        if (r.whole) {
-            if (frames) RAST_CUDA(ctx, cudaMemcpyAsync(frames + f * 3 * P, b.rgb_dev + (size_t)i * 3 * P, 3 * P, cudaMemcpyDeviceToHost, cs));
-            if (depths) RAST_CUDA(ctx, cudaMemcpyAsync(depths + f * P, b.depth_dev + (size_t)i * P, P * 4, cudaMemcpyDeviceToHost, cs));
-            ctx->d2h_bytes += P * ((frames ? 3u : 0u) + (depths ? 4u : 0u));
-            continue;
+        auto ok = [&](cudaError_t e) { if (e != cudaSuccess) { int want = (int)cudaSuccess; copy_error.compare_exchange_strong(want, (int)e); } };
+        if (whole[i]) {
+            if (frames) ok(cudaMemcpyAsync(frames + f * 3 * P, b.rgb_dev + (size_t)i * 3 * P, 3 * P, cudaMemcpyDeviceToHost, cs));
+            if (depths) ok(cudaMemcpyAsync(depths + f * P, b.depth_dev + (size_t)i * P, P * 4, cudaMemcpyDeviceToHost, cs));
+            copied += P * bpp;
+            return;
         }
-        const size_t off = (size_t)r.y0 * W + r.x0, w = r.x1 - r.x0 + 1u, h = r.y1 - r.y0 + 1u;
-        ctx->d2h_bytes += w * h * ((frames ? 3u : 0u) + (depths ? 4u : 0u));
-        if (frames)
-            for (int c = 0; c < 3; ++c)
-                RAST_CUDA(ctx, cudaMemcpy2DAsync(frames + (f * 3 + c) * P + off, W, b.rgb_dev + ((size_t)i * 3 + c) * P + off, W, w, h, cudaMemcpyDeviceToHost, cs));
-        if (depths)
-            RAST_CUDA(ctx, cudaMemcpy2DAsync(depths + f * P + off, (size_t)W * 4, b.depth_dev + (size_t)i * P + off, (size_t)W * 4, w * 4, h, cudaMemcpyDeviceToHost, cs));
-    }
-    RAST_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b.slot], cs));
-    ctx->copied_pending[b.slot] = true;
-    // the background, in tasks of one plane x 64 rows
+        for (uint32_t k = 0; k < S; ++k) {
+            const Rect &r = rects[(size_t)i * S + k];
+            if (r.empty) continue;
+            const size_t off = (size_t)r.y0 * W + r.x0, w = r.x1 - r.x0 + 1u, h = r.y1 - r.y0 + 1u;
+            copied += w * h * bpp;
+            if (frames) {
+                cudaMemcpy3DParms c3{};
+                c3.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t *>(b.rgb_dev) + (size_t)i * 3 * P, W, W, rows);
+                c3.dstPtr = make_cudaPitchedPtr(frames + f * 3 * P, W, W, rows);
+                c3.srcPos = c3.dstPos = make_cudaPos(r.x0, r.y0, 0);
+                c3.extent = make_cudaExtent(w, h, 3);
+                c3.kind = cudaMemcpyDeviceToHost;
+                ok(cudaMemcpy3DAsync(&c3, cs));
+            }
+            if (depths)
+                ok(cudaMemcpy2DAsync(depths + f * P + off, (size_t)W * 4, b.depth_dev + (size_t)i * P + off, (size_t)W * 4, w * 4, h, cudaMemcpyDeviceToHost, cs));
+        }
+    };
+    // the background, in tasks of one plane x 64 rows; on the copy-engine path task 0 issues the copies meanwhile
     const uint32_t chunk = 64, chunks = (rows + chunk - 1) / chunk, planes = (frames ? 3u : 0u) + (depths ? 1u : 0u);
     if (planes == 0) return RAST_OK;
     ctx->pool.start(ctx->host_threads);
+    const bool retained = !old_ext.empty();
+    const bool ce = !ctx->deliver_now;
+    const int device = ctx->device;
     const std::function<void(size_t)> fill = [&](size_t task) {
+        if (ce) {
+            if (task == 0) {
+                cudaSetDevice(device); // (a pool thread has no current device of its own)
+                for (uint32_t i = 0; i < b.count; ++i) issue_copies(i);
+                return;
+            }
+            --task;
+        }
         const uint32_t i = (uint32_t)(task / ((size_t)planes * chunks)), rest = (uint32_t)(task % ((size_t)planes * chunks));
         const uint32_t plane = rest / chunks, ya = (rest % chunks) * chunk, yb = std::min(rows, ya + chunk);
-        const Rect &r = rects[i];
-        if (!r.empty && r.whole) return;
         const size_t f = (size_t)b.first + i;
         const bool is_depth = frames ? plane == 3u : true;
         auto fill_span = [&](uint32_t y, uint32_t xa, uint32_t xb) { // [xa, xb) of row y
@@ -561,23 +622,26 @@ int finish_batch(rast_ctx *ctx, const PendingBatch &b, const rk::View &vw, uint8
             if (is_depth) stream_fill(depths + f * P + (size_t)y * W + xa, (size_t)(xb - xa) * 4, 0x3F800000u /* 1.0f */);
             else stream_fill(frames + (f * 3 + plane) * P + (size_t)y * W + xa, xb - xa, 0u);
         };
-        // the span of row y that must become background: the whole row, or -- retained outputs -- only what the previous draw left there
-        uint32_t oa = 0u, ob = W; // [oa, ob) of the rows [oy0, oy1]
-        uint32_t oy0 = 0u, oy1 = rows - 1u;
-        if (!old_rects.empty()) {
-            const rast_ctx::HostRect &o = old_rects[i];
-            if (o.empty) return;
-            oa = o.x0; ob = o.x1 + 1u; oy0 = o.y0; oy1 = o.y1;
-        }
-        for (uint32_t y = std::max(ya, oy0); y < yb && y <= oy1; ++y) {
-            if (r.empty || y < r.y0 || y > r.y1) { fill_span(y, oa, ob); continue; }
-            fill_span(y, oa, std::min(ob, r.x0));
-            fill_span(y, std::max(oa, r.x1 + 1u), ob);
+        for (uint32_t y = ya; y < yb; ++y) {
+            const uint32_t xa = ext[((size_t)i * rows + y) * 2], xb = ext[((size_t)i * rows + y) * 2 + 1];
+            // what of row y must become background: everything outside the delivered extent, or -- retained outputs -- only what the previous draw left there
+            uint32_t oa = 0u, ob = W;
+            if (retained) { oa = old_ext[((size_t)i * rows + y) * 2]; ob = old_ext[((size_t)i * rows + y) * 2 + 1]; }
+            if (oa >= ob) continue;
+            if (xa >= xb) { fill_span(y, oa, ob); continue; }
+            fill_span(y, oa, std::min(ob, xa));
+            fill_span(y, std::max(oa, xb), ob);
         }
         _mm_sfence(); // the streaming stores of this task are globally visible before it counts as done
     };
-    ctx->pool.run(fill, (size_t)b.count * planes * chunks);
+    ctx->pool.run(fill, (ce ? 1u : 0u) + (size_t)b.count * planes * chunks);
     _mm_sfence();
+    if (ce) {
+        ctx->d2h_bytes += copied.load();
+        if (copy_error.load() != (int)cudaSuccess) return fail(ctx, RAST_ECUDA, "device-to-host copy of a covered rectangle", (cudaError_t)copy_error.load());
+        RAST_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b.slot], cs));
+        ctx->copied_pending[b.slot] = true;
+    }
     return RAST_OK;
 }
 
@@ -719,12 +783,27 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
     // Small frames go back whole: the sparse copy waits on the host for the frame's covered rectangle, issues four 2-D copies and wakes the
     // fill threads -- more than the 40 us a 2 MB frame needs over PCIe (640x480 into page-locked buffers: 181 us per call sparse)
     ctx->sparse_now = ctx->sparse_copy && (size_t)vw.band_pixels * ((frames ? 3u : 0u) + (depths ? 4u : 0u)) >= ctx->sparse_min_bytes;
+    // Zero-copy delivery: buffers that are page-locked AND mapped into the device's address space (rast_host_alloc, rast_host_register) receive
+    // their covered row spans straight from a kernel (k_deliver); anything else goes through the copy engine, one rectangle per strip.
+    ctx->deliver_now = false;
+    ctx->frames_mapped = nullptr; ctx->depths_mapped = nullptr;
+    if (!device_ptrs && ctx->sparse_now && ctx->deliver_enabled && vw.W % 16u == 0u && frames && (((uintptr_t)frames | (uintptr_t)depths) & 15u) == 0u) {
+        auto mapped = [](const void *p) -> void * {
+            cudaPointerAttributes a{};
+            if (cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeHost && a.devicePointer != nullptr) return a.devicePointer;
+            cudaGetLastError();
+            return nullptr;
+        };
+        ctx->frames_mapped = static_cast<uint8_t *>(mapped(frames));
+        ctx->depths_mapped = depths ? static_cast<float *>(mapped(depths)) : nullptr;
+        ctx->deliver_now = ctx->frames_mapped != nullptr && (depths == nullptr || ctx->depths_mapped != nullptr);
+    }
     if (!device_ptrs) {
         // retained outputs: the promise covers exactly the buffers of the previous host-buffer draw, same geometry, and only frames that draw wrote
         rast_ctx::Retained &rt = ctx->retained;
         ctx->retained_now = ctx->retained_outputs && ctx->sparse_now && rt.valid && rt.frames == frames && rt.depths == depths && rt.W == vw.W &&
-                            rt.rows == vw.y1 - vw.y0 && rt.y0 == vw.y0 && n <= rt.rects.size();
-        if (!ctx->retained_now) rt.rects.clear();
+                            rt.rows == vw.y1 - vw.y0 && rt.y0 == vw.y0 && (size_t)n * (vw.y1 - vw.y0) * 2 <= rt.ext.size();
+        if (!ctx->retained_now) rt.ext.clear();
         rt.valid = false; // until this call has completed
         rt.frames = frames; rt.depths = depths; rt.W = vw.W; rt.rows = vw.y1 - vw.y0; rt.y0 = vw.y0;
     }
@@ -754,14 +833,15 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
         }
         // the last frame of the call keeps its visibility keys for rast_read_triangle_ids / rast_get_stats
         const uint32_t keep_frame = (ctx->keep_visibility && first + count == n) ? count - 1 : 0xFFFFFFFFu;
-        uint32_t *bbox_dev = nullptr;
+        uint32_t *spans_dev = nullptr;
+        const size_t span_bytes = (size_t)(vw.y1 - vw.y0) * 8; // per frame
         if (!device_ptrs && ctx->sparse_now) {
-            RAST_CUDA(ctx, ctx->d_bbox[slot].reserve((size_t)nb * 16));
-            RAST_CUDA(ctx, ctx->h_bbox[slot].reserve((size_t)nb * 16));
-            bbox_dev = ctx->d_bbox[slot].as<uint32_t>();
+            RAST_CUDA(ctx, ctx->d_spans[slot].reserve((size_t)nb * span_bytes));
+            RAST_CUDA(ctx, ctx->h_spans[slot].reserve((size_t)nb * span_bytes));
+            spans_dev = ctx->d_spans[slot].as<uint32_t>();
         }
         cudaStream_t done_stream = ctx->stream;
-        int rc = launch_batch(ctx, vw, first, count, rgb_dst, depth_dst, keep_frame, bbox_dev, ps, two_streams, &done_stream);
+        int rc = launch_batch(ctx, vw, first, count, rgb_dst, depth_dst, keep_frame, spans_dev, ps, two_streams, &done_stream);
         if (rc != RAST_OK) return rc;
 
         ctx->last_view = vw;
@@ -773,8 +853,19 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
         ctx->have_visibility = keep_frame < count;
 
         if (!device_ptrs) {
-            if (bbox_dev) RAST_CUDA(ctx, cudaMemcpyAsync(ctx->h_bbox[slot].p, bbox_dev, (size_t)count * 16, cudaMemcpyDeviceToHost, done_stream));
+            if (spans_dev) RAST_CUDA(ctx, cudaMemcpyAsync(ctx->h_spans[slot].p, spans_dev, (size_t)count * span_bytes, cudaMemcpyDeviceToHost, done_stream));
             RAST_CUDA(ctx, cudaEventRecord(ctx->ev_done[slot], done_stream));
+            if (spans_dev && ctx->deliver_now) {
+                // the covered spans leave for the caller's buffers as soon as the shade pass is done, behind nothing on the host
+                RAST_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[slot], 0));
+                const uint32_t rows_b = vw.y1 - vw.y0;
+                rk::k_deliver<<<grid_for((size_t)count * rows_b * 32, 256), 256, 0, ctx->copy_stream>>>(spans_dev, rgb_dst, depths ? depth_dst : nullptr, ctx->frames_mapped + (size_t)first * 3 * P,
+                                                                                                     ctx->depths_mapped ? ctx->depths_mapped + (size_t)first * P : nullptr, vw.W, rows_b, count);
+                ctx->launches++;
+                RAST_CUDA(ctx, cudaGetLastError());
+                RAST_CUDA(ctx, cudaEventRecord(ctx->ev_copied[slot], ctx->copy_stream));
+                ctx->copied_pending[slot] = true;
+            }
             // the previous batch is brought back now, with this one already queued behind it on the GPU
             if (pending.valid) { rc = finish_batch(ctx, pending, vw, frames, depths); if (rc != RAST_OK) return rc; }
             pending.valid = true; pending.slot = slot; pending.first = first; pending.count = count;
@@ -859,6 +950,7 @@ int rast_create(int device, rast_ctx **out) {
     ctx->stream = ctx->own_stream;
     if (const char *e = getenv("RAST_SPARSE_COPY")) ctx->sparse_copy = atoi(e) != 0;
     if (const char *e = getenv("RAST_SPARSE_MIN_BYTES")) ctx->sparse_min_bytes = (size_t)atoll(e);
+    if (const char *e = getenv("RAST_DELIVER")) ctx->deliver_enabled = atoi(e) != 0;
     if (const char *e = getenv("RAST_SETUP_PIPE")) ctx->setup_pipe = atoi(e) != 0;
     if (const char *e = getenv("RAST_SHADE_WT_MIN_TILES")) ctx->shade_wt_min_tiles = (uint32_t)atoll(e);
     if (const char *e = getenv("RAST_OVERLAP")) ctx->overlap = atoi(e) != 0;
@@ -883,7 +975,7 @@ void rast_destroy(rast_ctx *ctx) {
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->front_stream) cudaStreamSynchronize(ctx->front_stream);
     DeviceBuffer *dev[] = {&ctx->d_pos, &ctx->d_nrm, &ctx->d_nrm4, &ctx->d_uv, &ctx->d_vidx, &ctx->d_attr, &ctx->d_mats, &ctx->d_texels, &ctx->d_frames[0], &ctx->d_frames[1], &ctx->d_lights[0], &ctx->d_lights[1],
-                           &ctx->d_rv[0], &ctx->d_rv[1], &ctx->d_cn[0], &ctx->d_cn[1], &ctx->d_tiles, &ctx->d_list, &ctx->d_items, &ctx->d_vis[0], &ctx->d_vis[1], &ctx->d_flags[0], &ctx->d_flags[1], &ctx->d_bbox[0], &ctx->d_bbox[1], &ctx->d_queue, &ctx->d_counters, &ctx->d_shade_cursor, &ctx->d_aux, &ctx->d_rgb[0], &ctx->d_rgb[1], &ctx->d_depth[0], &ctx->d_depth[1]};
+                           &ctx->d_rv[0], &ctx->d_rv[1], &ctx->d_cn[0], &ctx->d_cn[1], &ctx->d_tiles, &ctx->d_list, &ctx->d_items, &ctx->d_vis[0], &ctx->d_vis[1], &ctx->d_flags[0], &ctx->d_flags[1], &ctx->d_spans[0], &ctx->d_spans[1], &ctx->d_queue, &ctx->d_counters, &ctx->d_shade_cursor, &ctx->d_aux, &ctx->d_rgb[0], &ctx->d_rgb[1], &ctx->d_depth[0], &ctx->d_depth[1]};
     for (DeviceBuffer *b : dev) b->release();
 #if RAST_SHADE_PREP
     ctx->d_prep[0].release();
@@ -892,8 +984,8 @@ void rast_destroy(rast_ctx *ctx) {
     ctx->h_frames.release();
     ctx->h_lights.release();
     ctx->h_status.release();
-    ctx->h_bbox[0].release();
-    ctx->h_bbox[1].release();
+    ctx->h_spans[0].release();
+    ctx->h_spans[1].release();
     if (ctx->ev_params) cudaEventDestroy(ctx->ev_params);
     for (int i = 0; i < 2; ++i) {
         if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
@@ -1255,7 +1347,7 @@ int rast_set_retained_outputs(rast_ctx *ctx, int enabled) {
     if (!ctx) return RAST_EINVAL;
     ctx->retained_outputs = enabled != 0;
     ctx->retained.valid = false;
-    ctx->retained.rects.clear();
+    ctx->retained.ext.clear();
     return RAST_OK;
 }
 

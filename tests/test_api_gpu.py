@@ -205,6 +205,75 @@ def test_page_locked_caller_buffers_and_the_drop_in_registry():
     assert not api._pinned_outputs
 
 
+class _Mapped:
+    """numpy views of page-locked, device-mapped host memory (rast_host_alloc): the buffers k_deliver can store into."""
+    def __init__(self):
+        import ctypes as C
+        from rasteriser_b200 import _lib
+        self.C, self.lib, self.ptrs = C, _lib.load(), []
+
+    def empty(self, shape, dtype, fill):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = self.lib.rast_host_alloc(n)
+        assert p
+        self.ptrs.append(p)
+        a = np.ctypeslib.as_array(self.C.cast(p, self.C.POINTER(self.C.c_uint8)), (n,)).view(dtype).reshape(shape)
+        a[...] = fill
+        return a
+
+    def free(self):
+        for p in self.ptrs:
+            self.lib.rast_host_free(self.C.c_void_p(p))
+        self.ptrs = []
+
+
+@pytest.mark.parametrize("size", [(640, 480), (1920, 1080), (48, 40), (160, 121)])
+def test_zero_copy_delivery_writes_the_same_bytes_as_the_copy_engine(size, monkeypatch):
+    """Page-locked mapped host buffers receive their covered row spans from k_deliver (no copy engine); the buffers -- pre-filled with
+    garbage -- must end up byte-identical to the copy-engine path (RAST_DELIVER=0) and to pageable buffers, for single frames, a batch
+    with an empty and a full-screen frame, colour only, a band, and with retained outputs on."""
+    from rasteriser_b200 import api
+    monkeypatch.setenv("RAST_SPARSE_MIN_BYTES", "0")
+    W, H = size
+    scene, lights = S.scene("suzanne"), S.lights("threepoint")
+    poses = [api.Args(W, H, tait_bryan_angles=(0.1 * k, 0.9 * k, 0.0), displacement=(0.3 * (k % 3) - 0.3, 0.1 * k - 0.2, 0.0), scale=1.0 - 0.1 * k) for k in range(5)]
+    poses.append(api.Args(W, H, displacement=(40.0, 0.0, 0.0)))            # nothing on screen
+    poses.append(api.Args(W, H, scale=6.0, displacement=(0.0, 0.0, 1.0)))   # covered edge to edge
+    monkeypatch.setenv("RAST_DELIVER", "0")
+    ce = make_renderer(scene, lights)
+    monkeypatch.setenv("RAST_DELIVER", "1")
+    r = make_renderer(scene, lights)
+    m = _Mapped()
+    try:
+        want_f, want_d = ce.draw_frames(poses, want_depth=True)
+        fs, ds = m.empty((len(poses), 3, H, W), np.uint8, 0xAB), m.empty((len(poses), H, W), np.float32, -7.0)
+        b0 = r.d2h_bytes()
+        r.draw_frames(poses, fs, ds)
+        moved = r.d2h_bytes() - b0
+        assert np.array_equal(fs, want_f) and np.array_equal(ds.view(np.uint32), want_d.view(np.uint32))
+        if W % 16 == 0:
+            assert moved < 0.8 * (fs.nbytes + ds.nbytes)  # spans, not frames
+        fs[...] = 0x5A
+        r.draw_frames(poses, fs, None)  # colour only
+        assert np.array_equal(fs, want_f)
+        f1, d1 = m.empty((3, H, W), np.uint8, 0x33), m.empty((H, W), np.float32, 2.0)
+        r.set_retained_outputs(True)
+        for k in (0, 3, 5, 1, 6, 2):  # one pair of buffers redrawn, incl. empty and full-screen frames in between
+            r.draw_frame(poses[k], f1, d1)
+            assert np.array_equal(f1, want_f[k]) and np.array_equal(d1.view(np.uint32), want_d[k].view(np.uint32)), k
+        r.set_retained_outputs(False)
+        if H >= 40:
+            y0, y1 = H // 5, H - H // 3
+            r.set_band(y0, y1)
+            fb, db = m.empty((3, y1 - y0, W), np.uint8, 0x11), m.empty((y1 - y0, W), np.float32, 9.0)
+            r.draw_frame(poses[1], fb, db)
+            assert np.array_equal(fb, want_f[1][:, y0:y1]) and np.array_equal(db.view(np.uint32), want_d[1][y0:y1].view(np.uint32))
+    finally:
+        r.close()
+        ce.close()
+        m.free()
+
+
 def test_retained_outputs_rewrite_only_what_changes(monkeypatch):
     """rast_set_retained_outputs: the caller redraws into the buffers of the previous draw (the reference's spin loop does) and the
     library resets only the part of the previously covered rectangle that the new frame leaves.  Every draw must leave the
