@@ -207,11 +207,13 @@ int rast_get_pass_ms(rast_ctx *ctx, float ms[RAST_PASS_COUNT]);
 const char *rast_last_schedule(rast_ctx *ctx);
 /* number of kernel launches issued by this context since creation */
 uint64_t rast_launch_count(const rast_ctx *ctx);
-/* Bytes of frame / depth data this context has copied device -> host so far.  Host-buffer draws copy only the
- * rectangle of each frame that holds drawn pixels and write the constant rest of the caller's buffers (frame 0,
- * depth 1.0f: the clear of renderer.cpp:85-86) on the host, so this can be well below 7 bytes per pixel and frame;
- * the buffers the caller sees are the same bytes either way.  RAST_SPARSE_COPY=0 in the environment copies whole
- * frames; RAST_HOST_THREADS sets the threads that write the background (default min(4, hardware / 2)). */
+/* Bytes of frame / depth data this context has moved device -> host so far.  Host-buffer draws move only what holds drawn
+ * pixels -- the covered span of every row, stored by a kernel straight into buffers that are page-locked and mapped
+ * (rast_host_alloc, rast_host_register; image width a multiple of 16), else one rectangle per strip of rows through the copy
+ * engine -- and write the constant rest of the caller's buffers (frame 0, depth 1.0f: the clear of renderer.cpp:85-86) on the
+ * host, so this can be well below 7 bytes per pixel and frame; the buffers the caller sees are the same bytes either way.
+ * Frames below 4 MB are copied whole.  Environment: RAST_SPARSE_COPY=0 whole frames always, RAST_DELIVER=0 never the kernel,
+ * RAST_HOST_THREADS the threads that write the background (default min(4, hardware / 2)). */
 uint64_t rast_d2h_bytes(rast_ctx *ctx);
 /* Diagnostic: the kernels divide several numerators by one divisor with a shared reciprocal (the compiler's
  * own div.rn.f32 fast-path sequence, csrc/exact.cuh).  This compares that against IEEE division on the GPU
