@@ -467,18 +467,22 @@ const __grid_constant__ Scene sc, const __grid_constant__ View vw, const __grid_
                                                const __grid_constant__ TileBins tb) {
     const uint32_t f = blockIdx.y;
     const uint64_t t0 = (uint64_t)blockIdx.x * (256 * TRIS) + threadIdx.x;
-    const float4 *rv = bt.rv + (size_t)f * sc.V;
+    // The frame's vertices behind an opaque base, UNSIGNED 32-bit indices (validated at upload) and read-only loads (k_vertex wrote them in
+    // an earlier launch): a gather is IMAD.WIDE + LDG instead of a sign extension, a 64-bit multiply-add of the frame offset and a LEA pair
+    unsigned long long rv_base = (unsigned long long)(bt.rv + (size_t)f * sc.V);
+    asm volatile("" : "+l"(rv_base));
+    const float4 *rv = reinterpret_cast<const float4 *>(rv_base);
     // phase 1: the (coalesced) index loads of all this thread's triangles, then all the vertex gathers
-    int i0[TRIS], i1[TRIS], i2[TRIS];
+    uint32_t i0[TRIS], i1[TRIS], i2[TRIS];
 #pragma unroll
     for (int k = 0; k < TRIS; ++k) {
         const uint64_t t = t0 + (uint64_t)k * 256;
         const bool in = t < sc.T;
-        i0[k] = in ? sc.vidx0[t] : 0; i1[k] = in ? sc.vidx1[t] : 0; i2[k] = in ? sc.vidx2[t] : 0;
+        i0[k] = in ? (uint32_t)sc.vidx0[t] : 0u; i1[k] = in ? (uint32_t)sc.vidx1[t] : 0u; i2[k] = in ? (uint32_t)sc.vidx2[t] : 0u;
     }
     float4 v0[TRIS], v1[TRIS], v2[TRIS];
 #pragma unroll
-    for (int k = 0; k < TRIS; ++k) { v0[k] = rv[i0[k]]; v1[k] = rv[i1[k]]; v2[k] = rv[i2[k]]; }
+    for (int k = 0; k < TRIS; ++k) { v0[k] = exact::ldg(rv + i0[k]); v1[k] = exact::ldg(rv + i1[k]); v2[k] = exact::ldg(rv + i2[k]); }
     const bool cw = bt.frames[f].wind_clockwise != 0u;
     // phase 2
 #pragma unroll
@@ -500,22 +504,24 @@ template <bool BINS>
 __global__ void __launch_bounds__(256) k_setup_pipe(const __grid_constant__ Scene sc, const __grid_constant__ View vw, const __grid_constant__ Batch bt,
                                                     const __grid_constant__ TileBins tb) {
     const uint32_t f = blockIdx.y;
-    const float4 *rv = bt.rv + (size_t)f * sc.V;
+    unsigned long long rv_base = (unsigned long long)(bt.rv + (size_t)f * sc.V); // (opaque base + unsigned indices + read-only loads, as in k_setup)
+    asm volatile("" : "+l"(rv_base));
+    const float4 *rv = reinterpret_cast<const float4 *>(rv_base);
     const bool cw = bt.frames[f].wind_clockwise != 0u;
     const uint64_t stride = (uint64_t)gridDim.x * 256u;
     uint64_t t = (uint64_t)blockIdx.x * 256u + threadIdx.x;
     // prologue: indices of the first two triangles, vertices of the first
-    int a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
-    if (t < sc.T) { a0 = sc.vidx0[t]; a1 = sc.vidx1[t]; a2 = sc.vidx2[t]; }
-    if (t + stride < sc.T) { b0 = sc.vidx0[t + stride]; b1 = sc.vidx1[t + stride]; b2 = sc.vidx2[t + stride]; }
-    float4 v0 = rv[a0], v1 = rv[a1], v2 = rv[a2];
+    uint32_t a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
+    if (t < sc.T) { a0 = (uint32_t)sc.vidx0[t]; a1 = (uint32_t)sc.vidx1[t]; a2 = (uint32_t)sc.vidx2[t]; }
+    if (t + stride < sc.T) { b0 = (uint32_t)sc.vidx0[t + stride]; b1 = (uint32_t)sc.vidx1[t + stride]; b2 = (uint32_t)sc.vidx2[t + stride]; }
+    float4 v0 = exact::ldg(rv + a0), v1 = exact::ldg(rv + a1), v2 = exact::ldg(rv + a2);
 #pragma unroll 1
     for (; t < sc.T; t += stride) {
         // vertices of the next triangle (its indices arrived during the previous iteration), indices of the one after
-        const float4 n0 = rv[b0], n1 = rv[b1], n2 = rv[b2];
-        int c0 = 0, c1 = 0, c2 = 0;
+        const float4 n0 = exact::ldg(rv + b0), n1 = exact::ldg(rv + b1), n2 = exact::ldg(rv + b2);
+        uint32_t c0 = 0, c1 = 0, c2 = 0;
         const uint64_t t2 = t + 2 * stride;
-        if (t2 < sc.T) { c0 = sc.vidx0[t2]; c1 = sc.vidx1[t2]; c2 = sc.vidx2[t2]; }
+        if (t2 < sc.T) { c0 = (uint32_t)sc.vidx0[t2]; c1 = (uint32_t)sc.vidx1[t2]; c2 = (uint32_t)sc.vidx2[t2]; }
         setup_triangle<BINS>((uint32_t)t, f, v0, v1, v2, cw, vw, bt, tb);
         v0 = n0; v1 = n1; v2 = n2;
         b0 = c0; b1 = c1; b2 = c2;
