@@ -44,6 +44,26 @@ def test_device_outputs_on_a_torch_stream_equal_host_outputs():
         r.close()
 
 
+def test_device_draws_of_more_frames_than_one_batch():
+    """Device-pointer draws run up to 120 frames per launch sequence, host-buffer draws 32: 130 small frames into device memory span two
+    batches there (and five on the host path) and must equal the host result frame by frame."""
+    import torch
+    r = make_renderer(S.scene("suzanne"), S.lights("threepoint"))
+    try:
+        W, H, n = 64, 48, 130
+        poses = [api.Args(W, H, tait_bryan_angles=(0.05 * k, api.spin_angle(0.3, k, n), 0.0), scale=0.6 + 0.003 * k) for k in range(n)]
+        host_frames, host_depths = r.draw_frames(poses, want_depth=True)
+        frames = torch.full((n, 3, H, W), 7, dtype=torch.uint8, device="cuda")
+        depths = torch.full((n, H, W), -1.0, dtype=torch.float32, device="cuda")
+        for _ in range(2):
+            r.draw_frames_device(poses, frames.data_ptr(), depths.data_ptr())
+            r.sync()
+            assert np.array_equal(frames.cpu().numpy(), host_frames)
+            assert np.array_equal(depths.cpu().numpy().view(np.uint32), host_depths.view(np.uint32))
+    finally:
+        r.close()
+
+
 def test_profiling_launch_count_and_stats():
     scene, lights = S.scene("suzanne"), S.lights("threepoint")
     r = make_renderer(scene, lights)

@@ -31,11 +31,11 @@ if has launches; then
 fi
 if has ncu; then
   cap() { ncu --set full --clock-control none --import-source on -k regex:$1 -s $2 -c 1 -f -o $o/${tag}_$3 python tools/quick_ab.py $4 --calls 2 > $o/${tag}_ncu_$3.log 2>&1; }
-  cap k_resolve_shade 12 shade spin1080p
-  cap k_raster_chunks 12 raster spin1080p
-  cap k_vertex 12 vertex spin1080p
-  cap k_setup 12 setup_spin spin1080p
-  cap k_prepare_tris 12 prepare spin1080p
+  cap k_resolve_shade 4 shade spin1080p
+  cap k_raster_chunks 4 raster spin1080p
+  cap k_vertex 4 vertex spin1080p
+  cap k_setup 4 setup_spin spin1080p
+  cap k_prepare_tris 4 prepare spin1080p
   cap k_setup 5 setup tess4k
   cap k_setup 5 setup50m tess4k_64lights
   cap k_raster_tiles 3 raster_over overdraw8k

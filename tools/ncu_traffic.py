@@ -15,7 +15,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # capture name (tools/gpu_session.sh) -> (workload, frames per launch of the captured kernel)
-CAPTURES = {"shade": ("spin1080p", 32), "raster": ("spin1080p", 32), "vertex": ("spin1080p", 32), "setup_spin": ("spin1080p", 32), "prepare": ("spin1080p", 32),
+# (tools/quick_ab.py renders the spin workload in 120-frame device-pointer calls = one launch sequence of 120 frames)
+CAPTURES = {"shade": ("spin1080p", 120), "raster": ("spin1080p", 120), "vertex": ("spin1080p", 120), "setup_spin": ("spin1080p", 120), "prepare": ("spin1080p", 120),
             "setup": ("tess4k", 1), "shade_tess": ("tess4k", 1), "setup50m": ("tess4k_64lights", 1), "raster_over": ("overdraw8k", 1), "shade_over": ("overdraw8k", 1)}
 STALLS = ['long_scoreboard', 'wait', 'short_scoreboard', 'branch_resolving', 'no_instruction', 'barrier', 'not_selected', 'lg_throttle',
           'math_pipe_throttle', 'dispatch_stall', 'mio_throttle', 'drain', 'membar', 'imc_miss', 'tex_throttle', 'sleeping']
