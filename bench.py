@@ -694,7 +694,7 @@ def main():
                            "partition": (("sort-first row bands, each rank's shade pass stores its band into rank 0's image over NVLink peer memory (CUDA IPC), one 4-byte all-reduce per frame orders completion, all inside the timed region" if opts.band_gather == "peer" else
                                           "sort-first row bands, band slabs gathered to rank 0 with NCCL inside the timed region") if band_mode else
                                          "frame k of the global sequence on rank k mod N; no collective (the gathers to rank 0 are measured in the `gathered` and `bands` records of this line)"),
-                           "l2": "working set per 120-frame batch ~4 GB >> 126 MB L2 (inputs/outputs larger than L2)",
+                           "l2": "working set per 240-frame batch ~7 GB >> 126 MB L2 (inputs/outputs larger than L2)",
                            "outputs": "RGB8 planes + f32 depth per frame, written to HBM"},
                 "mtris_per_s": fps * len(wl["tris"]) / 1e6, "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
                 "verify": verify, "workloads": workloads, "gathered": gathered_rec, "bands": bands_rec,

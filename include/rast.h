@@ -202,7 +202,7 @@ int rast_get_stats(rast_ctx *ctx, rast_stats *out);
 int rast_set_profiling(rast_ctx *ctx, int enabled);
 int rast_get_pass_ms(rast_ctx *ctx, float ms[RAST_PASS_COUNT]);
 /* Which kernel flavour each pass of the most recent batch took, e.g. "setup=k_setup<0,2> raster=k_raster_tiles
- * shade=k_resolve_shade_wt batch=120" (the library picks per batch: chunk queue or screen-tile bins, one warp per 4 rows or per tile;
+ * shade=k_resolve_shade_wt batch=240" (the library picks per batch: chunk queue or screen-tile bins, one warp per 4 rows or per tile;
  * batch = frames per launch sequence of the most recent call).
  * Waits for the context's streams; the string lives until the next call of this function on the context. */
 const char *rast_last_schedule(rast_ctx *ctx);

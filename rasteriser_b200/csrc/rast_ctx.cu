@@ -30,13 +30,17 @@ thread_local std::string g_create_error;
 
 // Frames in flight through one launch sequence (<= 256: 8-bit frame tag).  Device-pointer draws take big batches: a launch sequence has fixed
 // costs (ten launches, the ramp and the tail of every grid, a persistent raster grid that needs several grabs per warp to balance) -- 120-frame
-// 1080p calls on a B200: 32 frames per batch 1.908 ms, 64: 1.853, 120: 1.816.  Host-buffer draws keep 32: a batch is also the unit in which
-// frames travel back, and the first delivery should not wait for 120 frames.
+// 1080p calls on a B200: 32 frames per batch 1.908 ms, 64: 1.853, 120: 1.816; the 720-frame step of bench.py at 90 / 120 / 180 / 240 per batch:
+// 70.5 / 71.0 / 71.6 / 71.9 k frames/s (32: 67.7 k).  Host-buffer draws keep 32: a batch is also the unit in which frames travel back, and the
+// first delivery should not wait for 240 frames.
 #ifndef RAST_MAX_BATCH
-#define RAST_MAX_BATCH 120
+#define RAST_MAX_BATCH 240
 #endif
 constexpr uint32_t MAX_BATCH = RAST_MAX_BATCH, MAX_BATCH_HOST = 32;
-constexpr size_t BATCH_BYTES_BUDGET = 6ull << 30;  // per-batch device scratch budget
+#ifndef RAST_BATCH_GB
+#define RAST_BATCH_GB 12
+#endif
+constexpr size_t BATCH_BYTES_BUDGET = (size_t)RAST_BATCH_GB << 30;  // per-batch device scratch budget
 constexpr unsigned long long TILE_MODE_OVERDRAW = 8; // queued bbox area per pixel above which the next call bins by screen tile
 constexpr size_t SPARSE_MIN_FRAME_BYTES = 4u << 20; // host-buffer draws: frames smaller than this are copied whole (RAST_SPARSE_MIN_BYTES)
 constexpr uint32_t QUEUE_MIN = 1u << 23;           // work items (8 B each); grows on demand when a frame overflows it

@@ -45,12 +45,12 @@ def test_device_outputs_on_a_torch_stream_equal_host_outputs():
 
 
 def test_device_draws_of_more_frames_than_one_batch():
-    """Device-pointer draws run up to 120 frames per launch sequence, host-buffer draws 32: 130 small frames into device memory span two
-    batches there (and five on the host path) and must equal the host result frame by frame."""
+    """Device-pointer draws run up to 240 frames per launch sequence, host-buffer draws 32: 250 small frames into device memory span two
+    batches there (and eight on the host path) and must equal the host result frame by frame."""
     import torch
     r = make_renderer(S.scene("suzanne"), S.lights("threepoint"))
     try:
-        W, H, n = 64, 48, 130
+        W, H, n = 64, 48, 250
         poses = [api.Args(W, H, tait_bryan_angles=(0.05 * k, api.spin_angle(0.3, k, n), 0.0), scale=0.6 + 0.003 * k) for k in range(n)]
         host_frames, host_depths = r.draw_frames(poses, want_depth=True)
         frames = torch.full((n, 3, H, W), 7, dtype=torch.uint8, device="cuda")

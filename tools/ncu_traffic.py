@@ -15,7 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # capture name (tools/gpu_session.sh) -> (workload, frames per launch of the captured kernel)
-# (tools/quick_ab.py renders the spin workload in 120-frame device-pointer calls = one launch sequence of 120 frames)
+# (tools/quick_ab.py renders the spin workload in 120-frame device-pointer calls = one launch sequence of 120 frames; bench.py's 720-frame calls run 240 per sequence)
 CAPTURES = {"shade": ("spin1080p", 120), "raster": ("spin1080p", 120), "vertex": ("spin1080p", 120), "setup_spin": ("spin1080p", 120), "prepare": ("spin1080p", 120),
             "setup": ("tess4k", 1), "shade_tess": ("tess4k", 1), "setup50m": ("tess4k_64lights", 1), "raster_over": ("overdraw8k", 1), "shade_over": ("overdraw8k", 1)}
 STALLS = ['long_scoreboard', 'wait', 'short_scoreboard', 'branch_resolving', 'no_instruction', 'barrier', 'not_selected', 'lg_throttle',
