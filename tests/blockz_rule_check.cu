@@ -89,6 +89,12 @@ int main(int argc, char **argv) {
                 const float plane = Zo + gx * (float)(x - rx0) + gy * (float)(y - ry0);
                 const double used = ((double)plane - (double)z) / (double)M;
                 if (used > worst) worst = used;
+                // the shipped test itself (block_behind, used by k_raster_tiles for whole 16 x 8 blocks): a block that holds this pixel must not be
+                // declared behind a farthest stored depth equal to the pixel's own depth -- the pixel could still tie or win there
+                const uint32_t blk = ((y - ry0) / 8u) * 2u + ((x - rx0) / 16u);
+                if (block_behind(blk, depth_key(z), rx0, ry0, rx1, ry1, rx0, ry0, Zo, gx, gy, M)) {
+                    if (violations++ < 5) fprintf(stderr, "BLOCK VIOLATION px (%u,%u) block %u z %a\n", x, y, blk, z);
+                }
                 if (!(z >= plane - M)) {
                     if (violations++ < 5)
                         fprintf(stderr, "VIOLATION px (%u,%u) z %a plane %a M %a v (%a,%a,%a) (%a,%a,%a) (%a,%a,%a)\n", x, y, z, plane, M, v[0].x, v[0].y, v[0].z,
