@@ -652,7 +652,11 @@ RAST_HD bool block_behind(uint32_t b, uint32_t kmax, uint32_t rx0, uint32_t ry0,
     const uint32_t bxa = max(ox + bc * 16u, rx0), bxb = min(ox + bc * 16u + 15u, rx1);
     const uint32_t bya = max(oy + bs * 8u, ry0), byb = min(oy + bs * 8u + 7u, ry1);
     const float dxa = (float)(bxa - rx0), dxb = (float)(bxb - rx0), dya = (float)(bya - ry0), dyb = (float)(byb - ry0);
+#ifdef RAST_BLOCK_Z_TEST_BIAS // (tests/test_emu_device_fns.py builds with a positive bias to show that a wrong bound is caught)
+    const float lb = bz_o + fminf(bz_gx * dxa, bz_gx * dxb) + fminf(bz_gy * dya, bz_gy * dyb) - bz_m + RAST_BLOCK_Z_TEST_BIAS;
+#else
     const float lb = bz_o + fminf(bz_gx * dxa, bz_gx * dxb) + fminf(bz_gy * dya, bz_gy * dyb) - bz_m;
+#endif
     const uint32_t far_bits = (kmax & 0x80000000u) ? (kmax ^ 0x80000000u) : ~kmax; // inverse of depth_key
     return lb > exact::u2f(far_bits);
 }

@@ -10,6 +10,7 @@
 // product path: nothing under rasteriser_b200/ or include/ builds, loads or calls it.
 //
 // Build (tests/test_emu_device_fns.py): nvcc -std=c++17 -O2 -Xcompiler -fPIC,-ffp-contract=off -shared -o libemu.so emu_device_fns.cu
+#include <algorithm>
 #include <atomic>
 #include <cstdint>
 #include <cstring>
@@ -61,7 +62,7 @@ struct EmuMaterial { // = rast_material (include/rast.h): planar normalised texe
     const float *texels;
 };
 
-enum { EMU_TIGHT = 1, EMU_PRE_NORMALS = 2, EMU_EARLY_Z = 4, EMU_ALL_CHUNKS = 8, EMU_FLAT_FACE = 16, EMU_PREP = 32, EMU_WARP = 64 };
+enum { EMU_TIGHT = 1, EMU_PRE_NORMALS = 2, EMU_EARLY_Z = 4, EMU_ALL_CHUNKS = 8, EMU_FLAT_FACE = 16, EMU_PREP = 32, EMU_WARP = 64, EMU_TILES = 128 };
 
 // One frame.  lights: n x 10 floats (rast_light: direction, intensity, colour, trans_dir -- trans_dir already computed by
 // rast_transform_lights).  Outputs: rgb planar [3][rows][W], depth [rows][W], tri_ids [rows][W] for the band [y0, y1).
@@ -163,6 +164,7 @@ extern "C" int emu_draw(const float *pos, uint32_t V, const float *nrm, uint32_t
                 }
             });
     }
+    std::vector<uint32_t> tile_list;
     for (uint64_t t = 0; t < T; ++t) {
         const float4 v0 = rv[tris[10 * t]], v1 = rv[tris[10 * t + 1]], v2 = rv[tris[10 * t + 2]];
         const float a2 = signed_area_2d(v0, v1, v2);
@@ -178,6 +180,8 @@ extern "C" int emu_draw(const float *pos, uint32_t V, const float *nrm, uint32_t
             if ((flags & EMU_TIGHT) && !rast_tight_bbox(v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, s.literal ? 0.f : s.area, &wx0, &wy0, &wx1, &wy1)) continue;
             for (uint32_t y = wy0; y <= wy1; ++y)
                 for (uint32_t x = wx0; x <= wx1; ++x) test_and_commit(s, x, y, (uint32_t)t, vis.data(), vw);
+        } else if (flags & EMU_TILES) {
+            tile_list.push_back((uint32_t)t); // the screen-tile schedule: binned below
         } else {
             const uint32_t ncx = (w + CHUNK - 1) / CHUNK, ncy = (h + CHUNK - 1) / CHUNK;
             for (uint32_t cy = 0; cy < ncy; ++cy)
@@ -201,6 +205,64 @@ extern "C" int emu_draw(const float *pos, uint32_t V, const float *nrm, uint32_t
         emu_warp::barrier(&gate, 33);
         for (std::thread &t : lanes) t.join();
     }
+#if RAST_BLOCK_Z
+    if (flags & EMU_TILES) {
+        // ---- k_fill_tiles / k_raster_tiles, one tile after the other: the bin near to far (nearest-vertex depth key), the tile's keys in a
+        //      private array, the farthest stored depth of each 16 x 8 block refreshed after every item, an item's eight blocks tested against
+        //      them with the kernel's own block_behind (the vote of k_raster_tiles: lane b = block b) and the survivors handed to
+        //      raster_item<tile schedule> lane by lane with that mask; finally the tile is merged into the visibility buffer ----
+        const uint32_t tiles_x = (W + TILE - 1) / TILE, tiles_y = (y1 - y0 + TILE - 1) / TILE;
+        std::vector<std::vector<std::pair<uint32_t, uint32_t>>> bins((size_t)tiles_x * tiles_y); // (nearest depth key, triangle)
+        for (uint32_t t : tile_list) {
+            const float4 v0 = rv[tris[10 * (size_t)t]], v1 = rv[tris[10 * (size_t)t + 1]], v2 = rv[tris[10 * (size_t)t + 2]];
+            const BBox bb = bounding_box(v0, v1, v2, vw);
+            const uint32_t zkey = depth_key(fminf(fminf(v0.z, v1.z), v2.z));
+            for (uint32_t ty = (bb.y0 - y0) / TILE; ty <= (bb.y1 - y0) / TILE; ++ty)
+                for (uint32_t tx = bb.x0 / TILE; tx <= bb.x1 / TILE; ++tx) bins[(size_t)ty * tiles_x + tx].push_back({zkey, t});
+        }
+        std::vector<unsigned long long> tile_keys(TILE * TILE);
+        for (uint32_t tile = 0; tile < tiles_x * tiles_y; ++tile) {
+            std::vector<std::pair<uint32_t, uint32_t>> &bin = bins[tile];
+            if (bin.empty()) continue;
+            std::stable_sort(bin.begin(), bin.end(), [](const std::pair<uint32_t, uint32_t> &a, const std::pair<uint32_t, uint32_t> &b) { return a.first < b.first; });
+            const uint32_t ox = (tile % tiles_x) * TILE, oy = y0 + (tile / tiles_x) * TILE;
+            for (uint32_t i = 0; i < TILE * TILE; ++i) tile_keys[i] = (ox + (i % TILE) < W && oy + (i / TILE) < y1) ? VIS_EMPTY : 0ull;
+            uint32_t block_far[8];
+            auto refresh = [&]() {
+                for (uint32_t b = 0; b < 8u; ++b) {
+                    uint32_t m = 0u;
+                    for (uint32_t yy = 0; yy < 8u; ++yy)
+                        for (uint32_t xx = 0; xx < 16u; ++xx) m = std::max(m, (uint32_t)(tile_keys[((b >> 1) * 8u + yy) * TILE + (b & 1u) * 16u + xx] >> 32));
+                    block_far[b] = m;
+                }
+            };
+            refresh();
+            for (const std::pair<uint32_t, uint32_t> &e : bin) {
+                const uint32_t t = e.second;
+                const float4 v0 = rv[tris[10 * (size_t)t]], v1 = rv[tris[10 * (size_t)t + 1]], v2 = rv[tris[10 * (size_t)t + 2]];
+                const BBox bb = bounding_box(v0, v1, v2, vw);
+                const uint32_t rx0 = max(bb.x0, ox), ry0 = max(bb.y0, oy), rx1 = min(bb.x1, ox + TILE - 1u), ry1 = min(bb.y1, oy + TILE - 1u);
+                if (rx0 > rx1 || ry0 > ry1) continue;
+                stage_item(*stg, 0u, t, 0u, v0, v1, v2, rx0, ry0, rx1, ry1, ox, oy);
+                uint32_t keep = 0u;
+                for (uint32_t b = 0; b < 8u; ++b)
+                    if (((stg->w[23][0] >> b) & 1u) && !block_behind(b, block_far[b], rx0, ry0, rx1, ry1, ox, oy, exact::u2f(stg->w[27][0]), exact::u2f(stg->w[28][0]),
+                                                                      exact::u2f(stg->w[29][0]), exact::u2f(stg->w[30][0])))
+                        keep |= 1u << b;
+                if (keep == 0u) continue;
+                for (uint32_t lane = 0; lane < 32u; ++lane) raster_item<true, true>(*stg, 0u, lane, vw, nullptr, tile_keys.data(), true, nullptr, keep);
+                refresh();
+            }
+            for (uint32_t i = 0; i < TILE * TILE; ++i) {
+                const uint32_t x = ox + (i % TILE), y = oy + (i / TILE);
+                if (tile_keys[i] != VIS_EMPTY && x < W && y < y1) {
+                    unsigned long long &dst = vis[(size_t)(y - y0) * W + x];
+                    if (tile_keys[i] < dst) dst = tile_keys[i];
+                }
+            }
+        }
+    }
+#endif
     delete stg;
 
     // ---- k_prepare_tris (variant RAST_SHADE_PREP) ----

@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 SRC = os.path.join(ROOT, "tests", "emu_device_fns.cu")
 CSRC = os.path.join(ROOT, "rasteriser_b200", "csrc")
-TIGHT, PRE_NORMALS, EARLY_Z, ALL_CHUNKS, FLAT_FACE, PREP, WARP = 1, 2, 4, 8, 16, 32, 64
+TIGHT, PRE_NORMALS, EARLY_Z, ALL_CHUNKS, FLAT_FACE, PREP, WARP, TILES = 1, 2, 4, 8, 16, 32, 64, 128
 
 
 class EmuMaterial(C.Structure):
@@ -169,6 +169,8 @@ def test_block_level_depth_rejection_is_exercised_and_a_wrong_bound_is_caught():
     want = orc.oracle_draw(scene, lights, oa, threads=4)
     got = emu_draw(broken, scene, lights, oa, PRE_NORMALS | ALL_CHUNKS | EARLY_Z)
     assert not np.array_equal(got[2], want[2])
+    got = emu_draw(broken, scene, lights, oa, PRE_NORMALS | ALL_CHUNKS | TILES)  # the tile schedule's block test (block_behind) likewise
+    assert not np.array_equal(got[2], want[2])
 
 
 def test_block_level_depth_bound_brute_force(tmp_path):
@@ -224,3 +226,32 @@ def test_extension_texture_modulates_kd_on_the_host(emu, flags):
     assert not np.array_equal(got[0], orc.oracle_draw(base, lights, oa)[0])
     white = orc.Scene(base.positions, base.normals, base.uvs, base.tris, [{"kd": (1.0, 1.0, 1.0), "texels": base.materials[0]["texels"], "modulate_kd": True}])
     assert np.array_equal(emu_draw(emu, white, lights, oa, flags)[0], orc.oracle_draw(base, lights, oa)[0])
+
+
+def test_screen_tile_schedule_on_the_host(emu):
+    """The high-overdraw path on the CPU: bins per 32 x 32 tile processed near to far, the tile's keys in a private array, every item's
+    eight 16 x 8 blocks tested with the kernel's own block_behind against the farthest stored depths and the survivors rasterised by
+    raster_item in its tile flavour (rectangle clipped to the tile, block grid anchored at the tile, early depth rejection against the
+    tile's keys), then merged.  Frames must equal the oracle bit for bit: an overdraw scene (most blocks are rejected), golden scenes,
+    fuzz seeds, a band whose edges cut through tiles, and tiny triangles mixed in."""
+    from rasteriser_b200 import synth
+    W, H = 640, 360
+    pos, nrm, uv, tris = synth.overdraw_scene(4000, W, H, radius_px=60.0)
+    over = orc.Scene(pos, nrm, uv, tris, [{"kd": (0.8, 0.8, 0.8), "texels": None}])
+    lights = S.lights("threepoint")
+    oa = orc.make_args(W, H)
+    want = orc.oracle_draw(over, lights, oa, threads=4)
+    assert_exact(emu_draw(emu, over, lights, oa, PRE_NORMALS | ALL_CHUNKS | TILES), want, "overdraw, tiles")
+    assert_exact(emu_draw(emu, over, lights, oa, PRE_NORMALS | TIGHT | TILES, 16), want, "overdraw, tiles, tiny path mixed in")
+    band = (37, 150)
+    assert_exact(emu_draw(emu, over, lights, oa, PRE_NORMALS | ALL_CHUNKS | TILES, band=band), tuple(a[..., band[0]:band[1], :] for a in want), "overdraw band, tiles")
+    for c in S.golden_cases():
+        if c["width"] * c["height"] > 80000:
+            continue
+        scene, lts, ca = S.scene(c["scene"]), S.lights(c["lights"]), S.case_args(c)
+        assert_exact(emu_draw(emu, scene, lts, ca, PRE_NORMALS | ALL_CHUNKS | TILES), orc.oracle_draw(scene, lts, ca), c["name"] + " (tiles)")
+    for seed in range(1000, 1016):
+        scene, lts, fa, mode, kind = _case(seed)
+        if fa.image_width * fa.image_height > 100000 or len(scene.tris) > 4000:
+            continue
+        assert_exact(emu_draw(emu, scene, lts, fa, ALL_CHUNKS | TILES), orc.oracle_draw(scene, lts, fa, threads=2), "seed %d (tiles)" % seed)
