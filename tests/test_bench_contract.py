@@ -39,3 +39,29 @@ def test_product_arm_needs_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1", "--workload", "suzanne640"],
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_roofline_record_follows_the_reported_schedule():
+    """bench.py derives the per-launch roofline from what the library reports (rast_last_schedule): the kernel flavour names the record and
+    the batch size sets frames per launch; traffic and limiter come from the committed ncu table of that kernel, scaled to the launch."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    wl = bench.make_workload("spin1080p")
+    P = 1920 * 1080
+    pass_ms = {"clear": 0.01, "vertex": 0.1, "setup": 0.07, "raster": 3.0, "shade": 7.2}
+    sched = {"setup": "k_setup<0,1>", "raster": "k_raster_chunks", "shade": "k_resolve_shade_wt", "batch": "240"}
+    rec = bench.roofline_record(wl, "spin1080p", pass_ms, 720, P, 600, 10.0, 720, sched)
+    assert rec["kernel"] == "k_resolve_shade_wt" and rec["bound"] == "hbm" and rec["unit"] == "GB/s"
+    assert rec["frames_per_launch"] == 240 and abs(rec["avg_launch_ms"] - 7.2 / 3) < 1e-9
+    alg = (15 * P + 136 * 600) * 240
+    assert abs(rec["algorithmic_bytes_per_launch"] - alg) < 1 and abs(rec["achieved"] - alg / (2.4e-3) / 1e9) < 1e-3
+    assert abs(rec["frac"] - rec["achieved"] / rec["peak"]) < 1e-12
+    tr, tr_file = bench.ncu_traffic("spin1080p")
+    assert tr_file and "k_resolve_shade_wt" in tr, "profiles/r*_traffic.json must hold the kernel the library runs on the headline workload"
+    k = tr["k_resolve_shade_wt"]
+    assert abs(rec["traffic"] - k["dram_bytes_per_launch"] * 240 / k["frames_per_launch"]) < 1
+    assert rec["limiter"]["source"] == tr_file and 0.3 < rec["limiter"]["issue_slot_frac_live"] < 1.0
+    # without a schedule (older library): 32 frames per launch and the default kernel names
+    rec32 = bench.roofline_record(wl, "spin1080p", pass_ms, 720, P, 600, 10.0, 720, None)
+    assert abs(rec32["frames_per_launch"] - 720 / 23) < 1e-9 and rec32["kernel"] == "k_resolve_shade"
