@@ -148,6 +148,9 @@ struct Batch {
     uint32_t queue_cap;
     uint32_t tiny_max_pixels; // bboxes up to this many pixels are rasterised by the setup thread itself
     unsigned long long *counters; // [0] queue count (may exceed queue_cap), [1] queue cursor, [2] overflow flag
+    unsigned long long tile_min_area; // screen-tile schedule requested for this batch (~0ull: not requested): it is taken if no bin overflowed and the
+                              // queued bbox area reaches this many pixels (the host asked for bins because the PREVIOUS call showed high overdraw; a
+                              // batch that turns out not to have it keeps the chunk queue, which k_setup fills as well) -- tile_schedule_taken()
     uint8_t *tile_flags;      // [n_frames][tiles_y][tiles_x]: 1 = some pass may have written a key into that 32 x 16 pixel tile (k_resolve_shade)
     uint32_t *spans;          // [n_frames][rows][2] or nullptr: covered span of every row of every frame, written by the shade pass as
                               // atomicMin of (x, W-1-x) over the row's covered pixels (0xFFFFFFFF = nothing covered in that row): only the
@@ -159,17 +162,19 @@ struct Batch {
 
 // Screen-tile bins of the binned raster schedule (k_plan_tiles / k_fill_tiles / k_raster_tiles).
 struct TileBins {
-    uint32_t *count;       // [n_frames * tiles] items per tile (filled by k_setup)
-    uint32_t *start;       // [n_frames * tiles] exclusive prefix of count (k_plan)
-    uint32_t *fill;        // [n_frames * tiles] running cursor (k_fill)
-    uint2 *list;           // queued triangles (triangle, frame) (k_setup)
-    uint2 *items;          // (triangle id, depth key of its nearest vertex) grouped by tile (k_fill)
-    uint32_t list_cap, items_cap;
+    uint32_t *fill;        // [n_frames * tiles] items appended to each tile's bin so far (zeroed per batch; may exceed cap)
+    uint2 *items;          // [n_frames * tiles][cap]: (triangle id, depth key of its nearest vertex), appended by k_setup
+    uint32_t cap;          // slots per bin; a bin that would need more sets CNT_TILE_OVERFLOW and the batch falls back to the chunk queue
     uint32_t tiles_x, tiles_y; // tiles of one frame (band)
 };
 
 constexpr uint32_t TILE = 32; // screen tile edge of the binned schedule (= CHUNK: both use the same 4 x 2 block grid)
-enum { CNT_QUEUE = 0, CNT_CURSOR = 1, CNT_QUEUE_OVERFLOW = 2, CNT_BBOX_AREA = 3, CNT_LIST = 4, CNT_TILE_ITEMS = 5, CNT_TILE_MODE = 6, CNT_TILE_OVERFLOW = 7, CNT_COUNT = 8 }; // counters[] slots
+enum { CNT_QUEUE = 0, CNT_CURSOR = 1, CNT_QUEUE_OVERFLOW = 2, CNT_BBOX_AREA = 3, CNT_TILE_MODE = 6, CNT_TILE_OVERFLOW = 7, CNT_COUNT = 8 }; // counters[] slots
+
+// Both raster kernels ask this once k_setup has finished: does the batch go through the screen-tile bins (k_raster_tiles) or the chunk queue?
+__device__ __forceinline__ bool tile_schedule_taken(const Batch &bt) {
+    return bt.tile_min_area != ~0ull && bt.counters[CNT_TILE_OVERFLOW] == 0ull && bt.counters[CNT_BBOX_AREA] >= bt.tile_min_area;
+}
 
 // ---- visibility key ------------------------------------------------------------------------
 // Order-preserving map of a finite float below 1.0 to u32.  -0 is canonicalised so that it ties
@@ -411,15 +416,17 @@ __device__ RAST_SETUP_INLINE void setup_triangle(uint32_t t, uint32_t f, float4 
         const unsigned long long area_sum = cg::reduce(grp, (unsigned long long)w * h, cg::plus<unsigned long long>());
         if (grp.thread_rank() == 0) atomicAdd(&bt.counters[3 /*CNT_BBOX_AREA*/], area_sum);
         const uint64_t first = (n <= bt.queue_cap) ? base + before : (uint64_t)bt.queue_cap;
-        if (BINS) { // binned schedule requested: remember the triangle and count it in every tile it touches
-            unsigned long long lbase = 0;
-            if (grp.thread_rank() == 0) lbase = atomicAdd(&bt.counters[CNT_LIST], (unsigned long long)grp.size());
-            const unsigned long long slot = grp.shfl(lbase, 0) + grp.thread_rank();
-            if (slot < tb.list_cap) tb.list[slot] = make_uint2(t, f);
+        if (BINS) { // binned schedule requested: the triangle goes straight into the bin of every tile its bbox touches (one pass: a slot is an atomicAdd away)
+            const uint32_t zkey = depth_key(fminf(fminf(v0.z, v1.z), v2.z)); // nearest vertex: the tile's CTA processes its bin near to far (order only)
             const uint32_t tx0 = bb.x0 / TILE, tx1 = bb.x1 / TILE, ty0 = (bb.y0 - vw.y0) / TILE, ty1 = (bb.y1 - vw.y0) / TILE;
-            uint32_t *cnt = tb.count + (size_t)f * tb.tiles_x * tb.tiles_y;
+            const size_t g0 = (size_t)f * tb.tiles_x * tb.tiles_y;
             for (uint32_t ty = ty0; ty <= ty1; ++ty)
-                for (uint32_t tx = tx0; tx <= tx1; ++tx) atomicAdd(&cnt[ty * tb.tiles_x + tx], 1u);
+                for (uint32_t tx = tx0; tx <= tx1; ++tx) {
+                    const size_t g = g0 + (size_t)ty * tb.tiles_x + tx;
+                    const uint32_t pos = atomicAdd(&tb.fill[g], 1u);
+                    if (pos < tb.cap) tb.items[g * tb.cap + pos] = make_uint2(t, zkey);
+                    else bt.counters[CNT_TILE_OVERFLOW] = 1ull;
+                }
         }
         if (first + n > bt.queue_cap) {
             // queue full: void any slots reserved below the capacity and walk the whole bbox in this
@@ -805,7 +812,7 @@ RAST_HD void raster_item(const StagedTris &stg, uint32_t it, uint32_t lane, cons
 // (64 registers / 4 CTAs per SM measured: 1080p Suzanne raster +4 %, 8K overdraw -8 %; the default favours the former)
 __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_chunks(Scene sc, View vw, Batch bt) {
     __shared__ StagedTris stage_all[RASTER_WARPS];
-    if (bt.counters[CNT_TILE_MODE] != 0ull) return; // this batch is rasterised by k_raster_tiles
+    if (tile_schedule_taken(bt)) return; // this batch is rasterised by k_raster_tiles
     StagedTris &stg = stage_all[threadIdx.x >> 5];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t count = (uint32_t)min(bt.counters[CNT_QUEUE], (unsigned long long)bt.queue_cap);
@@ -855,56 +862,9 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) k_raster_chunks(Scene sc, V
 }
 
 // ---- screen-tile binning ----------------------------------------------------------------------
-// Single CTA: decides whether this batch takes the binned schedule and, if so, turns the per-tile counts into
-// run offsets.  Falls back to the chunk schedule when the list or the item array would overflow.
-__global__ void __launch_bounds__(1024) k_plan_tiles(Batch bt, TileBins tb, unsigned long long min_bbox_area) {
-    __shared__ uint32_t partial[1024];
-    const uint32_t n = bt.n_frames * tb.tiles_x * tb.tiles_y;
-    const uint32_t per = (n + 1023u) / 1024u;
-    const uint32_t lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
-    uint32_t sum = 0;
-    for (uint32_t i = lo; i < hi; ++i) { sum += tb.count[i]; tb.fill[i] = 0u; }
-    partial[threadIdx.x] = sum;
-    __syncthreads();
-    for (uint32_t d = 1; d < 1024u; d <<= 1) { // Hillis-Steele inclusive scan of the 1024 partial sums
-        const uint32_t v = threadIdx.x >= d ? partial[threadIdx.x - d] : 0u;
-        __syncthreads();
-        partial[threadIdx.x] += v;
-        __syncthreads();
-    }
-    const unsigned long long total = partial[1023];
-    // (min_bbox_area: the host asked for bins because the PREVIOUS call showed high overdraw; a batch that turns out not to have it
-    //  keeps the chunk queue, which k_setup filled as well)
-    const bool ok = bt.counters[CNT_LIST] <= tb.list_cap && total <= tb.items_cap && bt.counters[CNT_BBOX_AREA] >= min_bbox_area;
-    uint32_t run = threadIdx.x ? partial[threadIdx.x - 1] : 0u;
-    for (uint32_t i = lo; i < hi; ++i) { tb.start[i] = run; run += tb.count[i]; }
-    if (threadIdx.x == 0) {
-        bt.counters[CNT_TILE_ITEMS] = total;
-        bt.counters[CNT_TILE_MODE] = ok ? 1ull : 0ull;
-        if (bt.counters[CNT_LIST] > tb.list_cap || total > tb.items_cap) bt.counters[CNT_TILE_OVERFLOW] = 1ull;
-    }
-}
-
-// One thread per queued triangle: its id goes into the run of every tile its bbox touches.
-__global__ void __launch_bounds__(256) k_fill_tiles(Scene sc, View vw, Batch bt, TileBins tb) {
-    if (bt.counters[CNT_TILE_MODE] == 0ull) return;
-    const uint32_t n = (uint32_t)min(bt.counters[CNT_LIST], (unsigned long long)tb.list_cap);
-    const uint32_t tiles = tb.tiles_x * tb.tiles_y;
-    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-        const uint2 ent = tb.list[e];
-        const float4 *rv = bt.rv + (size_t)ent.y * sc.V;
-        const float4 v0 = rv[sc.vidx0[ent.x]], v1 = rv[sc.vidx1[ent.x]], v2 = rv[sc.vidx2[ent.x]];
-        const BBox bb = bounding_box(v0, v1, v2, vw);
-        const uint32_t zkey = depth_key(fminf(fminf(v0.z, v1.z), v2.z)); // nearest vertex: the tile's CTA processes its bin near to far (order only)
-        const uint32_t tx0 = bb.x0 / TILE, tx1 = bb.x1 / TILE, ty0 = (bb.y0 - vw.y0) / TILE, ty1 = (bb.y1 - vw.y0) / TILE;
-        for (uint32_t ty = ty0; ty <= ty1; ++ty)
-            for (uint32_t tx = tx0; tx <= tx1; ++tx) {
-                const uint32_t g = ent.y * tiles + ty * tb.tiles_x + tx;
-                tb.items[tb.start[g] + atomicAdd(&tb.fill[g], 1u)] = make_uint2(ent.x, zkey);
-            }
-    }
-}
-
+// (Round 2 began with three passes -- k_setup counted per tile, a single-CTA k_plan_tiles scanned the counts, k_fill_tiles scattered the
+// triangles into exact runs: 86 + 94 us for the 32 400 tiles / 200 k triangles of the 8K overdraw frame, 10 % of it.  Bins of fixed
+// capacity filled by k_setup itself need neither.)
 // One CTA per (tile, frame): the tile's 1024 keys live in shared memory until every triangle of the bin is done, so the depth
 // test, the early rejections and the atomics never leave the SM (the chunk queue re-read 10.8 GB of keys from DRAM on the 8K
 // overdraw frame: 265 MB of keys, 2 x the L2, visited in random order).  What makes the schedule pay at depth complexity 50:
@@ -936,12 +896,12 @@ __global__ void __launch_bounds__(TILE_WARPS * 32) k_raster_tiles(Scene sc, View
     __shared__ uint32_t hist[TILE_SORT_BUCKETS];
     __shared__ uint32_t block_far[8];
     __shared__ uint32_t zrange[2];
-    if (bt.counters[CNT_TILE_MODE] == 0ull) return;
+    if (!tile_schedule_taken(bt)) return;
     const uint32_t f = blockIdx.y, tile = blockIdx.x;
     const uint32_t g = f * tb.tiles_x * tb.tiles_y + tile;
-    const uint32_t n = tb.count[g];
+    if (g == 0u && threadIdx.x == 0u) bt.counters[CNT_TILE_MODE] = 1ull; // for the host: the bins were used (rast_last_schedule, statistics)
+    const uint32_t n = min(tb.fill[g], tb.cap);
     if (n == 0u) return;
-    const uint32_t first = tb.start[g];
     const uint32_t ox = (tile % tb.tiles_x) * TILE, oy = vw.y0 + (tile / tb.tiles_x) * TILE;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     // pixels of the tile that lie outside the image can never be written: key 0 (nearer than anything) keeps them out of the far bounds
@@ -952,7 +912,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32) k_raster_tiles(Scene sc, View
     __syncthreads();
 
     // ---- near-to-far order of the bin (counting sort on the nearest-vertex depth key) ----
-    const uint2 *bin = tb.items + first;
+    const uint2 *bin = tb.items + (size_t)g * tb.cap;
     const bool sorted = n <= TILE_SORT_MAX;
     if (sorted) {
         uint32_t lo = 0xFFFFFFFFu, hi = 0u;

@@ -159,7 +159,7 @@ struct rast_ctx {
     uint32_t band_y0 = 0, band_y1 = 0; // 0,0 = whole frame
 
     // per-call / per-batch buffers
-    DeviceBuffer d_queue, d_counters, d_aux, d_tiles, d_list, d_items;
+    DeviceBuffer d_queue, d_counters, d_aux, d_tiles, d_items;
     // per-call parameter blocks, alternating between calls (cs = call slot): the front passes of call k+1 -- parameter upload
     // included -- may run while the shade pass of call k still reads its own block
     DeviceBuffer d_frames[2], d_lights[2];
@@ -220,7 +220,7 @@ struct rast_ctx {
     bool tiny_max_forced = false;
     int raster_mode_forced = -1; // -1 auto, 0 chunk, 1 tile (RAST_RASTER_MODE)
     bool tile_mode_next = false;
-    uint32_t list_cap = 1u << 22, items_cap = 1u << 25;
+    uint32_t items_cap = 1u << 25; // item slots of the screen-tile bins (all tiles of a batch together)
     // visibility-buffer bookkeeping: slots [0, vis_clean_slots) of band size vis_clean_pixels hold VIS_EMPTY,
     // except vis_dirty_slot (the last frame of the previous call, kept for inspection)
     uint32_t vis_clean_slots[2] = {0, 0}, vis_clean_pixels[2] = {0, 0}, vis_clean_w[2] = {0, 0};
@@ -312,6 +312,7 @@ uint32_t batch_capacity(const rast_ctx *ctx, const rk::View &vw, bool device_ptr
 int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count, uint8_t *rgb_dev, float *depth_dev, uint32_t keep_frame,
                  uint32_t *spans_dev, int ps, bool two_streams, cudaStream_t *done_stream) {
     rk::Batch bt;
+    bt.tile_min_area = ~0ull;
     bt.spans = spans_dev;
     bt.frames = ctx->d_frames[ctx->cs].as<rk::FrameParams>() + first;
     bt.n_frames = count;
@@ -367,26 +368,25 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
     // Raster schedule of this batch: the bbox-anchored chunk queue (k_raster_chunks, any order, global atomicMin) for frames where few
     // fragments compete per pixel, screen-tile bins (k_raster_tiles: the tile's keys in shared memory, bin processed near to far, block
     // and item level depth rejection) at high overdraw.  RAST_RASTER_MODE=chunk|tile forces one.
-    // "auto" bins the batch when the previous call's queued bbox area showed high overdraw (TILE_MODE_OVERDRAW); k_plan_tiles confirms it
-    // for this batch on the device and otherwise leaves the batch to the chunk queue, which k_setup fills in either case
+    // "auto" bins the batch when the previous call's queued bbox area showed high overdraw (TILE_MODE_OVERDRAW); the raster kernels confirm it
+    // for this batch on the device (tile_schedule_taken) and otherwise leave the batch to the chunk queue, which k_setup fills in either case
     const bool tile_mode = sc.T && (ctx->raster_mode_forced == 1 || (ctx->raster_mode_forced == -1 && ctx->tile_mode_next));
     rk::TileBins tb{};
     uint32_t n_tile_launches = 0;
+    bt.tile_min_area = ~0ull;
     if (tile_mode) {
         tb.tiles_x = (vw.W + rk::TILE - 1) / rk::TILE;
         tb.tiles_y = (vw.y1 - vw.y0 + rk::TILE - 1) / rk::TILE;
         const size_t n_tiles = (size_t)count * tb.tiles_x * tb.tiles_y;
-        RAST_CUDA(ctx, ctx->d_tiles.reserve(3 * n_tiles * 4));
-        RAST_CUDA(ctx, ctx->d_list.reserve((size_t)ctx->list_cap * sizeof(uint2)));
-        RAST_CUDA(ctx, ctx->d_items.reserve((size_t)ctx->items_cap * sizeof(uint2)));
-        tb.count = ctx->d_tiles.as<uint32_t>();
-        tb.start = tb.count + n_tiles;
-        tb.fill = tb.start + n_tiles;
-        tb.list = ctx->d_list.as<uint2>();
+        // bins of fixed capacity, filled by k_setup itself: as many slots per tile as the item budget allows (8K frame: 32 400 tiles -> 1 035 slots for
+        // bins of ~160); an overflowing bin sends the batch to the chunk queue and doubles the budget for the next call
+        tb.cap = (uint32_t)std::max<size_t>(16, std::min<size_t>(4096, ctx->items_cap / (n_tiles ? n_tiles : 1)));
+        RAST_CUDA(ctx, ctx->d_tiles.reserve(n_tiles * 4));
+        RAST_CUDA(ctx, ctx->d_items.reserve(n_tiles * tb.cap * sizeof(uint2)));
+        tb.fill = ctx->d_tiles.as<uint32_t>();
         tb.items = ctx->d_items.as<uint2>();
-        tb.list_cap = ctx->list_cap;
-        tb.items_cap = ctx->items_cap;
-        RAST_CUDA(ctx, cudaMemsetAsync(tb.count, 0, n_tiles * 4, st));
+        RAST_CUDA(ctx, cudaMemsetAsync(tb.fill, 0, n_tiles * 4, st));
+        bt.tile_min_area = ctx->raster_mode_forced == 1 ? 0ull : (unsigned long long)(TILE_MODE_OVERDRAW / 2) * vw.band_pixels * count;
     }
     ctx->sched_bins_requested = tile_mode;
     if (sc.T && vw.band_pixels) {
@@ -396,12 +396,6 @@ int launch_batch(rast_ctx *ctx, const rk::View &vw, size_t first, uint32_t count
         else { rk::k_setup<false><<<dim3(grid_for(sc.T, 256 * rk::SETUP_TRIS), count), 256, 0, st>>>(sc, vw, bt, tb); ctx->sched_setup = "k_setup<0,1>"; }
     }
     if (prof) cudaEventRecord(ctx->ev_pass[3], st);
-    if (tile_mode && vw.band_pixels) {
-        const unsigned long long min_area = ctx->raster_mode_forced == 1 ? 0ull : (unsigned long long)(TILE_MODE_OVERDRAW / 2) * vw.band_pixels * count;
-        rk::k_plan_tiles<<<1, 1024, 0, st>>>(bt, tb, min_area);
-        rk::k_fill_tiles<<<ctx->raster_grid, 256, 0, st>>>(sc, vw, bt, tb);
-        n_tile_launches += 2;
-    }
     if (sc.T && vw.band_pixels) rk::k_raster_chunks<<<ctx->raster_grid, rk::RASTER_WARPS * 32, 0, st>>>(sc, vw, bt); // returns at once when the bins are used
     if (tile_mode && vw.band_pixels) {
         rk::k_raster_tiles<<<dim3(tb.tiles_x * tb.tiles_y, count), rk::TILE_WARPS * 32, 0, st>>>(sc, vw, bt, tb);
@@ -706,7 +700,6 @@ int draw_frames_impl(rast_ctx *ctx, const rast_args *args, uint32_t n, uint8_t *
         if (ctx->last_batch_pixels) ctx->tile_mode_next = hs[3] > (unsigned long long)TILE_MODE_OVERDRAW * ctx->last_batch_pixels;
         if (hs[7] != 0ull) { // the bins overflowed (that batch fell back to the chunk queue): grow them
             RAST_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            if (ctx->list_cap < (1u << 27)) ctx->list_cap *= 2;
             if (ctx->items_cap < (1u << 29)) ctx->items_cap *= 2;
             ctx->h_status.as<unsigned long long>()[7] = 0ull;
         }
@@ -989,7 +982,7 @@ void rast_destroy(rast_ctx *ctx) {
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->front_stream) cudaStreamSynchronize(ctx->front_stream);
     DeviceBuffer *dev[] = {&ctx->d_pos, &ctx->d_nrm, &ctx->d_nrm4, &ctx->d_uv, &ctx->d_vidx, &ctx->d_attr, &ctx->d_mats, &ctx->d_texels, &ctx->d_frames[0], &ctx->d_frames[1], &ctx->d_lights[0], &ctx->d_lights[1],
-                           &ctx->d_rv[0], &ctx->d_rv[1], &ctx->d_cn[0], &ctx->d_cn[1], &ctx->d_tiles, &ctx->d_list, &ctx->d_items, &ctx->d_vis[0], &ctx->d_vis[1], &ctx->d_flags[0], &ctx->d_flags[1], &ctx->d_spans[0], &ctx->d_spans[1], &ctx->d_queue, &ctx->d_counters, &ctx->d_shade_cursor, &ctx->d_aux, &ctx->d_rgb[0], &ctx->d_rgb[1], &ctx->d_depth[0], &ctx->d_depth[1]};
+                           &ctx->d_rv[0], &ctx->d_rv[1], &ctx->d_cn[0], &ctx->d_cn[1], &ctx->d_tiles, &ctx->d_items, &ctx->d_vis[0], &ctx->d_vis[1], &ctx->d_flags[0], &ctx->d_flags[1], &ctx->d_spans[0], &ctx->d_spans[1], &ctx->d_queue, &ctx->d_counters, &ctx->d_shade_cursor, &ctx->d_aux, &ctx->d_rgb[0], &ctx->d_rgb[1], &ctx->d_depth[0], &ctx->d_depth[1]};
     for (DeviceBuffer *b : dev) b->release();
 #if RAST_SHADE_PREP
     ctx->d_prep[0].release();
