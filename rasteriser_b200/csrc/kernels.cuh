@@ -160,7 +160,7 @@ struct Batch {
 #endif
 };
 
-// Screen-tile bins of the binned raster schedule (k_plan_tiles / k_fill_tiles / k_raster_tiles).
+// Screen-tile bins of the binned raster schedule (k_setup<bins> fills them, k_raster_tiles consumes them).
 struct TileBins {
     uint32_t *fill;        // [n_frames * tiles] items appended to each tile's bin so far (zeroed per batch; may exceed cap)
     uint2 *items;          // [n_frames * tiles][cap]: (triangle id, depth key of its nearest vertex), appended by k_setup
